@@ -1,0 +1,136 @@
+// Host side of the tcgen05 GEMM: TMA descriptor encoding, tile/split-K selection, C-ABI entry.
+#include <cudaTypedefs.h>
+#include <mutex>
+
+#include "../../include/avsiam_b200.h"
+#include "common.cuh"
+#include "gemm_sm100.cuh"
+
+using namespace avs;
+
+static int g_desc_variant = 0;
+extern "C" void avs_debug_set_desc_variant(int v) { g_desc_variant = v; }
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols] with pitch ld (elements); box = {box_cols (inner), box_rows}, 128B swizzle.
+static int make_tmap_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld,
+                        int box_cols, int box_rows) {
+  auto fn = get_encode_fn();
+  AVS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  AVS_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA: base pointer must be 16-byte aligned");
+  AVS_REQUIRE((ld * 2) % 16 == 0, "TMA: row pitch must be a multiple of 8 bf16 elements (got %lld)", ld);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AVS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld cols=%lld ld=%lld", (int)r,
+              rows, cols, ld);
+  return 0;
+}
+
+template <int AM, int BM, int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int grid,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;  // idempotent; benign race
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<AM, BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      avs_set_error("cudaFuncSetAttribute(gemm smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  gemm_bf16_kernel<AM, BM, BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, args);
+  return avs_check_launch("gemm_bf16_kernel");
+}
+
+extern "C" int avs_gemm_bf16(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major,
+                             void* C, long long ldc, int M, int N, int K, const avs_gemm_epilogue_t* epi,
+                             int split_k, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  AVS_REQUIRE(A && B && C && epi, "avs_gemm_bf16: null pointer");
+  AVS_REQUIRE(M > 0 && N > 0 && K > 0, "avs_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+  AVS_REQUIRE(N % 8 == 0, "avs_gemm_bf16: N must be a multiple of 8 (got %d)", N);
+  AVS_REQUIRE((a_major == 0 || a_major == 1) && (b_major == 0 || b_major == 1), "avs_gemm_bf16: bad major");
+  AVS_REQUIRE(!(a_major == 1 && b_major == 0), "avs_gemm_bf16: (A MN-major, B K-major) is not instantiated");
+  const bool out_f32 = (epi->flags & (AVS_EPI_OUT_F32 | AVS_EPI_OUT_ATOMIC)) != 0;
+  AVS_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc * (out_f32 ? 4 : 2)) % 16 == 0,
+              "avs_gemm_bf16: C must be 16-byte aligned with a 16-byte-multiple pitch");
+  if (epi->flags & AVS_EPI_DGELU) AVS_REQUIRE(epi->aux_in != nullptr, "avs_gemm_bf16: DGELU needs aux_in");
+  if (epi->bias) AVS_REQUIRE((reinterpret_cast<uintptr_t>(epi->bias) & 15) == 0, "avs_gemm_bf16: bias alignment");
+  if (epi->rowadd) AVS_REQUIRE(epi->rowadd_rows > 0, "avs_gemm_bf16: rowadd_rows must be > 0");
+
+  const int BN = (N > 128) ? 256 : 128;
+  const int m_tiles = ceil_div(M, GEMM_BLOCK_M), n_tiles = ceil_div(N, BN);
+  const int total_kb = ceil_div(K, GEMM_BLOCK_K);
+  const int sms = avs_num_sms();
+  if (split_k <= 0) {  // auto: only meaningful with atomic accumulation
+    split_k = 1;
+    if (epi->flags & AVS_EPI_OUT_ATOMIC) {
+      const int mn = m_tiles * n_tiles;
+      if (mn < 2 * sms) split_k = ceil_div(2 * sms, mn);
+      if (split_k > total_kb / 4) split_k = total_kb / 4;  // keep >= 4 k-blocks per split
+      if (split_k < 1) split_k = 1;
+    }
+  }
+  AVS_REQUIRE(split_k == 1 || (epi->flags & AVS_EPI_OUT_ATOMIC), "avs_gemm_bf16: split_k>1 needs AVS_EPI_OUT_ATOMIC");
+  if (split_k > total_kb) split_k = total_kb;
+  const int kb_per_split = ceil_div(total_kb, split_k);
+  split_k = ceil_div(total_kb, kb_per_split);
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (a_major == 0) rc = make_tmap_2d(&ta, A, M, K, lda, GEMM_BLOCK_K, GEMM_BLOCK_M);
+  else rc = make_tmap_2d(&ta, A, K, M, lda, 64, GEMM_BLOCK_K);
+  if (rc) return rc;
+  if (b_major == 0) rc = make_tmap_2d(&tb, B, N, K, ldb, GEMM_BLOCK_K, BN);
+  else rc = make_tmap_2d(&tb, B, K, N, ldb, 64, GEMM_BLOCK_K);
+  if (rc) return rc;
+
+  GemmArgs args;
+  args.M = M; args.N = N; args.K = K;
+  args.C = C; args.ldc = ldc;
+  args.split_k = split_k; args.kb_per_split = kb_per_split;
+  args.desc_variant = g_desc_variant;
+  args.epi.flags = epi->flags;
+  args.epi.alpha = epi->alpha;
+  args.epi.bias = epi->bias;
+  args.epi.resid = reinterpret_cast<const bf16*>(epi->resid);
+  args.epi.ld_resid = epi->ld_resid;
+  args.epi.aux_in = reinterpret_cast<const bf16*>(epi->aux_in);
+  args.epi.aux_out = reinterpret_cast<bf16*>(epi->aux_out);
+  args.epi.ld_aux = epi->ld_aux;
+  args.epi.rowadd = epi->rowadd;
+  args.epi.rowidx = epi->rowidx;
+  args.epi.rowadd_rows = epi->rowadd_rows;
+
+  const int num_tiles = m_tiles * n_tiles * split_k;
+  const int grid = num_tiles < sms ? num_tiles : sms;
+  const int key = a_major * 2 + b_major;
+  if (BN == 256) {
+    if (key == 0) return launch_gemm<MAJOR_K, MAJOR_K, 256>(ta, tb, args, grid, stream);
+    if (key == 1) return launch_gemm<MAJOR_K, MAJOR_MN, 256>(ta, tb, args, grid, stream);
+    return launch_gemm<MAJOR_MN, MAJOR_MN, 256>(ta, tb, args, grid, stream);
+  } else {
+    if (key == 0) return launch_gemm<MAJOR_K, MAJOR_K, 128>(ta, tb, args, grid, stream);
+    if (key == 1) return launch_gemm<MAJOR_K, MAJOR_MN, 128>(ta, tb, args, grid, stream);
+    return launch_gemm<MAJOR_MN, MAJOR_MN, 128>(ta, tb, args, grid, stream);
+  }
+}

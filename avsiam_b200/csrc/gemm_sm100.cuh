@@ -1,0 +1,366 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> smem ring -> tcgen05.mma (TMEM accumulators,
+// double-buffered) -> tcgen05.ld epilogue with fused bias / GELU / dGELU / row-table add / residual.
+//
+//   D[M,N] = epilogue( sum_k A(m,k) * B(n,k) )
+//
+// Operand "major" selects how the operand sits in global memory (row-major tensors in all cases):
+//   A  MAJOR_K : A is [M, K]  (reduction contiguous)       MAJOR_MN : A is [K, M]  (M contiguous)
+//   B  MAJOR_K : B is [N, K]                                MAJOR_MN : B is [K, N]
+// Forward Linear = (K,K) with B = weight[N,K]; dgrad = (K,MN) with B = weight[N_out,K_in] read as [K_red, N];
+// wgrad = (MN,MN) with A = dY[tokens, N_out], B = X[tokens, K_in] -> no transposes anywhere in backward.
+//
+// Replaces the cuBLAS calls behind nn.Linear / Conv2d(k=s=16) in the reference
+// (src/models/cav_mae_base.py:51,55,96,311,334-335 and timm Mlp fc1/fc2).
+#pragma once
+#include "common.cuh"
+
+namespace avs {
+
+enum { MAJOR_K = 0, MAJOR_MN = 1 };
+
+// epilogue flags
+enum {
+  EPI_GELU = 1,        // v = gelu(v)            (aux_out, if set, receives the pre-activation)
+  EPI_DGELU = 2,       // v = v * gelu'(aux_in)
+  EPI_OUT_F32 = 4,     // C is fp32 (else bf16)
+  EPI_OUT_ATOMIC = 8,  // C is fp32 and accumulated with red.global.add (split-K / grad accumulation)
+};
+
+struct GemmEpilogue {
+  int flags;
+  float alpha;          // final scale (before the residual add)
+  const float* bias;    // [N] fp32 or null
+  const bf16* resid;    // [M, ld_resid] or null
+  long long ld_resid;
+  const bf16* aux_in;   // [M, ld_aux]
+  bf16* aux_out;        // [M, ld_aux]
+  long long ld_aux;
+  const float* rowadd;  // [rowadd_rows, N] fp32 table or null  (positional embedding)
+  const int* rowidx;    // [M] int32 row index into rowadd, or null => m % rowadd_rows
+  int rowadd_rows;
+};
+
+struct GemmArgs {
+  int M, N, K;          // K = reduction length
+  void* C;
+  long long ldc;
+  int split_k;          // >=1; >1 requires EPI_OUT_ATOMIC
+  int kb_per_split;     // k-blocks (of 64) per split
+  int desc_variant;     // debug: 1 swaps LBO/SBO of MN-major descriptors (probe only)
+  GemmEpilogue epi;
+};
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
+constexpr int GEMM_UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256 : 512;
+};
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_major, int b_major) {
+  return (1u << 4)                      // C format F32
+         | (1u << 7)                    // A format BF16
+         | (1u << 10)                   // B format BF16
+         | ((uint32_t)a_major << 15)    // A major (0 = K, 1 = MN)
+         | ((uint32_t)b_major << 16)    // B major
+         | ((uint32_t)(n >> 3) << 17)   // N / 8
+         | ((uint32_t)(m >> 4) << 24);  // M / 16
+}
+
+__device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int A_MAJOR, int B_MAJOR, int BLOCK_N>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const GemmArgs args) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (args.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int n_tiles = (args.N + BLOCK_N - 1) / BLOCK_N;
+  const int total_kb = (args.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  const int num_tiles = m_tiles * n_tiles * args.split_k;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int ks = t % args.split_k;
+        const int mn = t / args.split_k;
+        const int m0 = (mn / n_tiles) * GEMM_BLOCK_M;
+        const int n0 = (mn % n_tiles) * BLOCK_N;
+        const int kb0 = ks * args.kb_per_split;
+        const int kb1 = min(total_kb, kb0 + args.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
+          uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
+          const int k0 = kb * GEMM_BLOCK_K;
+          if (A_MAJOR == MAJOR_K) {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < GEMM_BLOCK_M / 64; ++j)
+              tma_load_2d(sa + j * (GEMM_BLOCK_K * 128), &tma_a, &full_bar[stage], m0 + j * 64, k0);
+          }
+          if (B_MAJOR == MAJOR_K) {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(sb + j * (GEMM_BLOCK_K * 128), &tma_b, &full_bar[stage], n0 + j * 64, k0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, BLOCK_N, A_MAJOR, B_MAJOR);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int ks = t % args.split_k;
+        const int kb0 = ks * args.kb_per_split;
+        const int kb1 = min(total_kb, kb0 + args.kb_per_split);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * Cfg::A_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
+            // K-major: step 16 elements (32 B) inside the 128 B swizzle row; 8-row groups 1024 B apart.
+            // MN-major: step 16 reduction rows (2 swizzle atoms = 2048 B); atoms along MN are
+            //           BLOCK_K*128 B apart (LBO), 8-row K groups 1024 B apart (SBO).
+            const uint32_t mn_lbo = args.desc_variant ? 1024 : GEMM_BLOCK_K * 128;
+            const uint32_t mn_sbo = args.desc_variant ? GEMM_BLOCK_K * 128 : 1024;
+            const uint64_t da = (A_MAJOR == MAJOR_K) ? make_smem_desc(sa + k * 32, 0, 1024)
+                                                     : make_smem_desc(sa + k * 2048, mn_lbo, mn_sbo);
+            const uint64_t db = (B_MAJOR == MAJOR_K) ? make_smem_desc(sb + k * 32, 0, 1024)
+                                                     : make_smem_desc(sb + k * 2048, mn_lbo, mn_sbo);
+            umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ============================ epilogue (4 warps, 32 TMEM lanes each) ============================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const GemmEpilogue& ep = args.epi;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int ks = t % args.split_k;
+      const int mn = t / args.split_k;
+      const int m0 = (mn / n_tiles) * GEMM_BLOCK_M;
+      const int n0 = (mn % n_tiles) * BLOCK_N;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < args.M;
+      const float* rowadd_ptr = nullptr;
+      if (ep.rowadd != nullptr && row_ok) {
+        const int ri = ep.rowidx ? ep.rowidx[row] : (row % ep.rowadd_rows);
+        rowadd_ptr = ep.rowadd + (long long)ri * args.N;
+      }
+      const bool lead_split = (ks == 0);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32);
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_wait();
+        const int nc = n0 + c * 32;
+        if (row_ok && nc < args.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const bool full = (nc + 32 <= args.N);
+          if (ep.bias != nullptr && lead_split) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (full || nc + j < args.N) {
+                const float4 b = *reinterpret_cast<const float4*>(ep.bias + nc + j);
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+          }
+          if (rowadd_ptr != nullptr && lead_split) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (full || nc + j < args.N) {
+                const float4 b = *reinterpret_cast<const float4*>(rowadd_ptr + nc + j);
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+          }
+          if (ep.flags & EPI_GELU) {
+            if (ep.aux_out != nullptr) {
+              bf16* ap = ep.aux_out + (long long)row * ep.ld_aux + nc;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (full || nc + j < args.N) {
+                  uint4 o;
+                  o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                  o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                  *reinterpret_cast<uint4*>(ap + j) = o;
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          if (ep.flags & EPI_DGELU) {
+            const bf16* ap = ep.aux_in + (long long)row * ep.ld_aux + nc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (full || nc + j < args.N) {
+                const uint4 a = *reinterpret_cast<const uint4*>(ap + j);
+                float2 f;
+                f = unpack_bf16x2(a.x); v[j] *= dgelu_erf(f.x); v[j + 1] *= dgelu_erf(f.y);
+                f = unpack_bf16x2(a.y); v[j + 2] *= dgelu_erf(f.x); v[j + 3] *= dgelu_erf(f.y);
+                f = unpack_bf16x2(a.z); v[j + 4] *= dgelu_erf(f.x); v[j + 5] *= dgelu_erf(f.y);
+                f = unpack_bf16x2(a.w); v[j + 6] *= dgelu_erf(f.x); v[j + 7] *= dgelu_erf(f.y);
+              }
+            }
+          }
+          if (ep.alpha != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+          }
+          if (ep.resid != nullptr && lead_split) {
+            const bf16* rp = ep.resid + (long long)row * ep.ld_resid + nc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (full || nc + j < args.N) {
+                const uint4 a = *reinterpret_cast<const uint4*>(rp + j);
+                float2 f;
+                f = unpack_bf16x2(a.x); v[j] += f.x; v[j + 1] += f.y;
+                f = unpack_bf16x2(a.y); v[j + 2] += f.x; v[j + 3] += f.y;
+                f = unpack_bf16x2(a.z); v[j + 4] += f.x; v[j + 5] += f.y;
+                f = unpack_bf16x2(a.w); v[j + 6] += f.x; v[j + 7] += f.y;
+              }
+            }
+          }
+          if (ep.flags & EPI_OUT_ATOMIC) {
+            float* cp = reinterpret_cast<float*>(args.C) + (long long)row * args.ldc + nc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (full || nc + j < args.N) red_add_f32x4(cp + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else if (ep.flags & EPI_OUT_F32) {
+            float* cp = reinterpret_cast<float*>(args.C) + (long long)row * args.ldc + nc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (full || nc + j < args.N)
+                *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            bf16* cp = reinterpret_cast<bf16*>(args.C) + (long long)row * args.ldc + nc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (full || nc + j < args.N) {
+                uint4 o;
+                o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(cp + j) = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace avs
