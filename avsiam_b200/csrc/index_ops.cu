@@ -1,0 +1,342 @@
+// Bit-exact index kernels: random-mask argsort, kept-row gather, patch extraction (im2col-free, fused with the
+// kept-token gather), decoder restore (mask-token fill + un-shuffle + pos/modality add) and its backward.
+// All are HBM-bound: 128-bit accesses, one pass over the data.
+#include "../../include/avsiam_b200.h"
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+// avs_mask_argsort: per-row stable ascending argsort of noise[N,L] (ties -> lower index first) producing
+// ids_shuffle, ids_restore (its inverse) and the binary mask (0 keep / 1 remove).
+// Replaces the two torch.argsort + gather at cav_mae_base.py:377-388 / :426-437.
+// One CTA per row; bitonic sort of (key,index) pairs in shared memory (L <= 2048).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void mask_argsort_kernel(const float* __restrict__ noise, int L, int Lp2, int len_keep,
+                                    int* __restrict__ ids_shuffle, int* __restrict__ ids_restore,
+                                    float* __restrict__ mask) {
+  extern __shared__ unsigned long long skeys[];  // (orderable float bits << 32) | index
+  const int row = blockIdx.x;
+  const float* nrow = noise + (size_t)row * L;
+  for (int i = threadIdx.x; i < Lp2; i += blockDim.x) {
+    unsigned long long key;
+    if (i < L) {
+      unsigned int u = __float_as_uint(nrow[i]);
+      u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // total order on floats
+      key = ((unsigned long long)u << 32) | (unsigned int)i;
+    } else {
+      key = ~0ull;
+    }
+    skeys[i] = key;
+  }
+  __syncthreads();
+  for (int k = 2; k <= Lp2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < Lp2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = skeys[i], b = skeys[ixj];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) {
+            skeys[i] = b;
+            skeys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const int src = (int)(skeys[i] & 0xffffffffu);
+    ids_shuffle[(size_t)row * L + i] = src;
+    ids_restore[(size_t)row * L + src] = i;
+    mask[(size_t)row * L + src] = (i >= len_keep) ? 1.0f : 0.0f;
+  }
+}
+
+extern "C" int avs_mask_argsort(const float* noise, int N, int L, int len_keep, int32_t* ids_shuffle,
+                                int32_t* ids_restore, float* mask, void* stream) {
+  AVS_REQUIRE(noise && ids_shuffle && ids_restore && mask, "avs_mask_argsort: null pointer");
+  AVS_REQUIRE(N >= 0 && L > 0 && L <= 2048 && len_keep >= 0 && len_keep <= L, "avs_mask_argsort: bad shape N=%d L=%d",
+              N, L);
+  if (N == 0) return 0;
+  int Lp2 = 1;
+  while (Lp2 < L) Lp2 <<= 1;
+  mask_argsort_kernel<<<N, 256, Lp2 * sizeof(unsigned long long), (cudaStream_t)stream>>>(
+      noise, L, Lp2, len_keep, ids_shuffle, ids_restore, mask);
+  return avs_check_launch("mask_argsort_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// avs_gather_rows: out[n, i, :] = x[n, ids[n, i], :] for i < keep — byte-exact row copies (16-byte vectors).
+// Replaces torch.gather(x, 1, ids_keep.unsqueeze(-1).repeat(1,1,D)) at cav_mae_base.py:382,431.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const uint4* __restrict__ x, const int* __restrict__ ids, uint4* __restrict__ out,
+                                   int L, int keep, int ids_ld, int row_vec, long long total_vec) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total_vec;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(g % row_vec);
+    const long long r = g / row_vec;  // output row = n*keep + i
+    const int n = (int)(r / keep), i = (int)(r % keep);
+    const int src = ids[(size_t)n * ids_ld + i];
+    out[g] = x[((size_t)n * L + src) * row_vec + c];
+  }
+}
+
+extern "C" int avs_gather_rows(const void* x, const int32_t* ids, void* out, int N, int L, int keep, int ids_ld,
+                               int row_bytes, void* stream) {
+  if (N == 0 || keep == 0) return 0;  // empty selection: nothing to copy
+  AVS_REQUIRE(x && ids && out, "avs_gather_rows: null pointer");
+  AVS_REQUIRE(row_bytes > 0 && row_bytes % 16 == 0, "avs_gather_rows: row_bytes must be a multiple of 16");
+  AVS_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0, "avs_gather_rows: 16-byte alignment");
+  AVS_REQUIRE(keep >= 0 && keep <= L && ids_ld >= keep, "avs_gather_rows: bad keep/ids_ld");
+  const long long total = (long long)N * keep * (row_bytes / 16);
+  if (total == 0) return 0;
+  const int blocks = (int)min((long long)avs_num_sms() * 8, ceil_div_ll(total, 256));
+  gather_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, ids, (uint4*)out, L, keep, ids_ld,
+                                                               row_bytes / 16, total);
+  return avs_check_launch("gather_rows_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Patch extraction fused with the kept-token gather (only kept patches are ever materialised):
+//   audio [B, T, F] fp32 -> rows [B*keep, p*p] bf16, token = f*ta + t, vector order (pf, pt)
+//     (PatchEmbed on a.unsqueeze(1).transpose(2,3), cav_mae_base.py:444-448; SURVEY §8a identity 3)
+//   video [B, C, H, W] fp32 -> rows [B*keep, C*p*p] bf16, token = h*g + w, vector order (c, p, q)  (identity 4)
+// ids == NULL => all tokens in natural order (keep == number of tokens).
+// sample_idx (int32 [B], optional): output sample b reads input sample sample_idx[b] (the chunk permutation of
+// forward_encoder_mmixed, cav_mae_base.py:533-549) — B is the number of OUTPUT samples.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void patchify_audio_kernel(const float* __restrict__ audio, const int* __restrict__ ids,
+                                      const int* __restrict__ sample_idx, bf16* __restrict__ out, int T, int F, int p, int ta, int keep, int ids_ld,
+                                      int ld_out, long long total8) {
+  const int vec = p * p;  // elements per patch
+  const int per_row = vec / 8;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total8;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(g % per_row);
+    const long long r = g / per_row;
+    const int bl = (int)(r / keep), i = (int)(r % keep);
+    const int tok = ids ? ids[(size_t)bl * ids_ld + i] : i;
+    const int b = sample_idx ? sample_idx[bl] : bl;
+    const int f = tok / ta, t = tok % ta;
+    const int e0 = c8 * 8;
+    const int pf = e0 / p, pt0 = e0 % p;  // p is a multiple of 8 => the 8 elements share pf
+    const float* src = audio + ((size_t)b * T + (size_t)t * p + pt0) * F + f * p + pf;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (size_t)j * F);
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + (size_t)r * ld_out + e0) = o;
+  }
+}
+
+__global__ void patchify_video_kernel(const float* __restrict__ img, const int* __restrict__ ids,
+                                      const int* __restrict__ sample_idx, bf16* __restrict__ out, int C, int H, int W, int p, int gw, int keep,
+                                      int ids_ld, int ld_out, long long total8) {
+  const int vec = C * p * p;
+  const int per_row = vec / 8;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total8;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(g % per_row);
+    const long long r = g / per_row;
+    const int bl = (int)(r / keep), i = (int)(r % keep);
+    const int tok = ids ? ids[(size_t)bl * ids_ld + i] : i;
+    const int b = sample_idx ? sample_idx[bl] : bl;
+    const int h = tok / gw, w = tok % gw;
+    const int e0 = c8 * 8;
+    const int c = e0 / (p * p), pp = (e0 / p) % p, q0 = e0 % p;
+    const float* src = img + (((size_t)b * C + c) * H + (size_t)h * p + pp) * W + (size_t)w * p + q0;
+    float v[8];
+    if ((((uintptr_t)src) & 15) == 0) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = d.x; v[5] = d.y; v[6] = d.z; v[7] = d.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldg(src + j);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + (size_t)r * ld_out + e0) = o;
+  }
+}
+
+extern "C" int avs_patchify_audio(const float* audio, const int32_t* ids, const int32_t* sample_idx, void* out, int B, int T, int F, int patch,
+                                  int keep, int ids_ld, int ld_out, void* stream) {
+  AVS_REQUIRE(audio && out, "avs_patchify_audio: null pointer");
+  AVS_REQUIRE(patch % 8 == 0 && T % patch == 0 && F % patch == 0, "avs_patchify_audio: patch must divide T,F and be a multiple of 8");
+  AVS_REQUIRE(ld_out >= patch * patch && ld_out % 8 == 0 && ((uintptr_t)out & 15) == 0, "avs_patchify_audio: bad ld_out/alignment");
+  const int ntok = (T / patch) * (F / patch);
+  AVS_REQUIRE(keep > 0 && keep <= ntok && (ids != nullptr || keep == ntok), "avs_patchify_audio: bad keep");
+  const long long total8 = (long long)B * keep * (patch * patch / 8);
+  if (total8 == 0) return 0;
+  const int blocks = (int)min((long long)avs_num_sms() * 8, ceil_div_ll(total8, 256));
+  patchify_audio_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(audio, ids, sample_idx, (bf16*)out, T, F, patch, T / patch, keep,
+                                                                  ids_ld, ld_out, total8);
+  return avs_check_launch("patchify_audio_kernel");
+}
+
+extern "C" int avs_patchify_video(const float* img, const int32_t* ids, const int32_t* sample_idx, void* out, int B, int C, int H, int W,
+                                  int patch, int keep, int ids_ld, int ld_out, void* stream) {
+  AVS_REQUIRE(img && out, "avs_patchify_video: null pointer");
+  AVS_REQUIRE(patch % 8 == 0 && H % patch == 0 && W % patch == 0, "avs_patchify_video: patch must divide H,W and be a multiple of 8");
+  AVS_REQUIRE(ld_out >= C * patch * patch && ld_out % 8 == 0 && ((uintptr_t)out & 15) == 0, "avs_patchify_video: bad ld_out/alignment");
+  const int ntok = (H / patch) * (W / patch);
+  AVS_REQUIRE(keep > 0 && keep <= ntok && (ids != nullptr || keep == ntok), "avs_patchify_video: bad keep");
+  const long long total8 = (long long)B * keep * (C * patch * patch / 8);
+  if (total8 == 0) return 0;
+  const int blocks = (int)min((long long)avs_num_sms() * 8, ceil_div_ll(total8, 256));
+  patchify_video_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(img, ids, sample_idx, (bf16*)out, C, H, W, patch, W / patch, keep,
+                                                                  ids_ld, ld_out, total8);
+  return avs_check_launch("patchify_video_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Decoder restore (cav_mae_base.py:604-626), one launch, no host sync:
+//   out[b, j]      = (ira[b,j] < ka ? x[b, ira[b,j]]      : mask_token) + pos_a[j] + mod_a      j in [0,Ta)
+//   out[b, Ta + j] = (irv[b,j] < kv ? x[b, ka + irv[b,j]] : mask_token) + pos_v[j] + mod_v      j in [0,Tv)
+// x: bf16 [B, ka+kv, D] (decoder_embed output), out: bf16 [B, Ta+Tv, D]; fp32 parameters.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void decoder_restore_fwd_kernel(const bf16* __restrict__ x, const int* __restrict__ ira,
+                                           const int* __restrict__ irv, const float* __restrict__ mask_token,
+                                           const float* __restrict__ pos_a, const float* __restrict__ pos_v,
+                                           const float* __restrict__ mod_a, const float* __restrict__ mod_v,
+                                           bf16* __restrict__ out, int Ta, int Tv, int ka, int kv, int D,
+                                           long long total8) {
+  const int per_row = D / 8;
+  const int S = Ta + Tv, K = ka + kv;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total8;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(g % per_row) * 8;
+    const long long r = g / per_row;
+    const int b = (int)(r / S), j = (int)(r % S);
+    const bool is_a = j < Ta;
+    const int jj = is_a ? j : j - Ta;
+    const int src = is_a ? ira[(size_t)b * Ta + jj] : irv[(size_t)b * Tv + jj];
+    const int keep = is_a ? ka : kv;
+    const float* pos = (is_a ? pos_a : pos_v) + (size_t)jj * D + c;
+    const float* mod = (is_a ? mod_a : mod_v) + c;
+    float v[8];
+    if (src < keep) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + ((size_t)b * K + (is_a ? 0 : ka) + src) * D + c);
+      float2 f;
+      f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+      f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+      f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+      f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = mask_token[c + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += pos[i] + mod[i];
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + (size_t)r * D + c) = o;
+  }
+}
+
+extern "C" int avs_decoder_restore_fwd(const void* x, const int32_t* ids_restore_a, const int32_t* ids_restore_v,
+                                       const float* mask_token, const float* pos_a, const float* pos_v,
+                                       const float* mod_a, const float* mod_v, void* out, int B, int Ta, int Tv,
+                                       int keep_a, int keep_v, int D, void* stream) {
+  AVS_REQUIRE(x && ids_restore_a && ids_restore_v && mask_token && pos_a && pos_v && mod_a && mod_v && out,
+              "avs_decoder_restore_fwd: null pointer");
+  AVS_REQUIRE(D % 8 == 0, "avs_decoder_restore_fwd: D must be a multiple of 8");
+  const long long total8 = (long long)B * (Ta + Tv) * (D / 8);
+  if (total8 == 0) return 0;
+  const int blocks = (int)min((long long)avs_num_sms() * 8, ceil_div_ll(total8, 256));
+  decoder_restore_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, ids_restore_a, ids_restore_v, mask_token, pos_a, pos_v, mod_a, mod_v, (bf16*)out, Ta, Tv, keep_a,
+      keep_v, D, total8);
+  return avs_check_launch("decoder_restore_fwd_kernel");
+}
+
+// Backward of the restore. One CTA per position j (grid = Ta+Tv), looping over the batch:
+//   dx[b, src]   = dout[b, j]                     where src = ids_restore[b,j] < keep     (pure scatter, unique)
+//   dpos[j]     += sum_b dout[b,j]                (deterministic, no atomics)
+//   dmask_token += sum over masked (b,j)          (fp32 atomics, one per CTA per column)
+//   dmod_{a,v}  += sum over (b,j) of the modality (fp32 atomics)
+__global__ void decoder_restore_bwd_kernel(const bf16* __restrict__ dout, const int* __restrict__ ira,
+                                           const int* __restrict__ irv, bf16* __restrict__ dx,
+                                           float* __restrict__ dmask_token, float* __restrict__ dpos_a,
+                                           float* __restrict__ dpos_v, float* __restrict__ dmod_a,
+                                           float* __restrict__ dmod_v, int B, int Ta, int Tv, int ka, int kv, int D) {
+  const int j = blockIdx.x;
+  const int S = Ta + Tv, K = ka + kv;
+  const bool is_a = j < Ta;
+  const int jj = is_a ? j : j - Ta;
+  const int keep = is_a ? ka : kv;
+  const int* ir = is_a ? ira + jj : irv + jj;
+  const int irs = is_a ? Ta : Tv;
+  for (int c = threadIdx.x * 2; c < D; c += blockDim.x * 2) {
+    float sp0 = 0.f, sp1 = 0.f, sm0 = 0.f, sm1 = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const uint32_t u = *reinterpret_cast<const uint32_t*>(dout + ((size_t)b * S + j) * D + c);
+      const float2 f = unpack_bf16x2(u);
+      sp0 += f.x; sp1 += f.y;
+      const int src = ir[(size_t)b * irs];
+      if (src < keep) {
+        *reinterpret_cast<uint32_t*>(dx + ((size_t)b * K + (is_a ? 0 : ka) + src) * D + c) = u;
+      } else {
+        sm0 += f.x; sm1 += f.y;
+      }
+    }
+    float* dpos = (is_a ? dpos_a : dpos_v) + (size_t)jj * D + c;
+    dpos[0] += sp0; dpos[1] += sp1;
+    float* dmod = (is_a ? dmod_a : dmod_v) + c;
+    atomicAdd(dmod, sp0); atomicAdd(dmod + 1, sp1);
+    atomicAdd(dmask_token + c, sm0); atomicAdd(dmask_token + c + 1, sm1);
+  }
+}
+
+extern "C" int avs_decoder_restore_bwd(const void* dout, const int32_t* ids_restore_a, const int32_t* ids_restore_v,
+                                       void* dx, float* dmask_token, float* dpos_a, float* dpos_v, float* dmod_a,
+                                       float* dmod_v, int B, int Ta, int Tv, int keep_a, int keep_v, int D,
+                                       void* stream) {
+  AVS_REQUIRE(dout && ids_restore_a && ids_restore_v && dx && dmask_token && dpos_a && dpos_v && dmod_a && dmod_v,
+              "avs_decoder_restore_bwd: null pointer");
+  AVS_REQUIRE(D % 2 == 0, "avs_decoder_restore_bwd: D must be even");
+  if (B == 0 || Ta + Tv == 0) return 0;
+  decoder_restore_bwd_kernel<<<Ta + Tv, 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dout, ids_restore_a, ids_restore_v, (bf16*)dx, dmask_token, dpos_a, dpos_v, dmod_a, dmod_v, B, Ta,
+      Tv, keep_a, keep_v, D);
+  return avs_check_launch("decoder_restore_bwd_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// avs_scatter_add_rows: table[idx[m], :] += alpha * dy[m, :]   (fp32 red.global.add; pos-embed gradient of the
+// fused patch-embed epilogue, cav_mae_base.py:449-450,454-455).   idx == NULL => m % table_rows.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void scatter_add_rows_kernel(const bf16* __restrict__ dy, const int* __restrict__ idx,
+                                        float* __restrict__ table, int D, int table_rows, float alpha,
+                                        long long total4) {
+  const int per_row = D / 4;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total4;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(g % per_row) * 4;
+    const long long m = g / per_row;
+    const int t = idx ? idx[m] : (int)(m % table_rows);
+    const uint2 u = *reinterpret_cast<const uint2*>(dy + (size_t)m * D + c);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    float* dst = table + (size_t)t * D + c;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(dst), "f"(a.x * alpha), "f"(a.y * alpha),
+                 "f"(b.x * alpha), "f"(b.y * alpha)
+                 : "memory");
+  }
+}
+
+extern "C" int avs_scatter_add_rows(const void* dy, const int32_t* idx, float* table, int M, int D, int table_rows,
+                                    float alpha, void* stream) {
+  AVS_REQUIRE(dy && table, "avs_scatter_add_rows: null pointer");
+  AVS_REQUIRE(D % 4 == 0 && ((uintptr_t)table & 15) == 0, "avs_scatter_add_rows: D %% 4 and 16-byte table alignment");
+  const long long total4 = (long long)M * (D / 4);
+  if (total4 == 0) return 0;
+  const int blocks = (int)min((long long)avs_num_sms() * 8, ceil_div_ll(total4, 256));
+  scatter_add_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, idx, table, D, table_rows, alpha,
+                                                                    total4);
+  return avs_check_launch("scatter_add_rows_kernel");
+}

@@ -1,0 +1,144 @@
+// Flat-buffer optimizer and parameter plumbing kernels (HBM-bound, 128-bit accesses):
+//   fused Adam / AdamW step over one contiguous fp32 parameter arena (+ bf16 shadow write, + GradScaler unscale /
+//   inf-check), fp32->bf16 cast, bias-gradient column sums, and an inf/nan scan.
+// Replaces torch.optim.Adam.step + GradScaler.unscale_ (traintest_cavmae_base.py:64-66,138-140,149-152).
+#include "../../include/avsiam_b200.h"
+#include "common.cuh"
+
+// torch.optim.Adam semantics (non-amsgrad): coupled L2 (g += wd*p) or decoupled (AdamW: p *= 1 - lr*wd).
+// found_inf (optional, device int/float flag != 0) => skip the whole step (GradScaler.step behaviour).
+// inv_scale (optional, device float) multiplies every gradient first (GradScaler.unscale_).
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v,
+                                                   bf16* __restrict__ shadow, long long n, float lr, float beta1,
+                                                   float beta2, float eps, float wd, float bc1, float bc2_sqrt,
+                                                   int decoupled, const float* __restrict__ inv_scale,
+                                                   const float* __restrict__ found_inf) {
+  if (found_inf != nullptr && *found_inf != 0.f) return;
+  const float gs = inv_scale ? *inv_scale : 1.0f;
+  const long long n4 = n / 4;
+  const float step_size = lr / bc1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ga[4] = {gg.x * gs, gg.y * gs, gg.z * gs, gg.w * gs};
+    float ma[4] = {mm.x, mm.y, mm.z, mm.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gj = ga[j];
+      if (decoupled) pa[j] *= 1.0f - lr * wd;
+      else gj += wd * pa[j];
+      ma[j] = beta1 * ma[j] + (1.0f - beta1) * gj;
+      va[j] = beta2 * va[j] + (1.0f - beta2) * gj * gj;
+      const float denom = sqrtf(va[j]) / bc2_sqrt + eps;
+      pa[j] -= step_size * (ma[j] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
+    if (shadow != nullptr) {
+      uint2 o;
+      o.x = pack_bf16x2(pa[0], pa[1]);
+      o.y = pack_bf16x2(pa[2], pa[3]);
+      reinterpret_cast<uint2*>(shadow)[i] = o;
+    }
+  }
+}
+
+extern "C" int avs_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
+                             const float* inv_scale, const float* found_inf, void* stream) {
+  AVS_REQUIRE(p && g && m && v, "avs_adam_step: null pointer");
+  AVS_REQUIRE(n % 4 == 0, "avs_adam_step: n must be a multiple of 4 (pad the arena)");
+  AVS_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "avs_adam_step: 16-byte alignment");
+  AVS_REQUIRE(step >= 1, "avs_adam_step: step must be >= 1");
+  if (n == 0) return 0;
+  const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+  const int blocks = (int)min((long long)avs_num_sms() * 16, ceil_div_ll(n / 4, 256));
+  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)shadow_bf16, n, lr, beta1, beta2, eps,
+                                                        weight_decay, (float)bc1, (float)sqrt(bc2), decoupled,
+                                                        inv_scale, found_inf);
+  return avs_check_launch("adam_kernel");
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long n8 = n / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * i], b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(dst)[i] = o;
+  }
+  for (long long i = n8 * 8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16(src[i]);
+}
+
+extern "C" int avs_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
+  AVS_REQUIRE(src && dst, "avs_cast_f32_to_bf16: null pointer");
+  AVS_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "avs_cast_f32_to_bf16: 16-byte alignment");
+  if (n == 0) return 0;
+  const int blocks = (int)min((long long)avs_num_sms() * 16, ceil_div_ll(n / 8 + 1, 256));
+  cast_f32_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  return avs_check_launch("cast_f32_bf16_kernel");
+}
+
+// out[n] += alpha * sum_m dy[m, n]  (bias gradients).  Each CTA owns 64 columns x a strip of rows; 8 warps stride the rows,
+// lanes read 2 adjacent bf16 (coalesced 128 B per warp-row); smem reduce; one fp32 atomic per column per CTA.
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ out, int M,
+                                                     int N, long long ld, int rows_per_cta, float alpha) {
+  const int c0 = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
+  const int warp = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(M, r0 + rows_per_cta);
+  float a0 = 0.f, a1 = 0.f;
+  if (c0 < N) {
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dy + (size_t)r * ld + c0));
+      a0 += f.x; a1 += f.y;
+    }
+  }
+  __shared__ float s[8][64];
+  s[warp][(threadIdx.x & 31) * 2] = a0;
+  s[warp][(threadIdx.x & 31) * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s[w][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < N) atomicAdd(out + c, t * alpha);
+  }
+}
+
+extern "C" int avs_colsum_bf16(const void* dy, long long ld, float* out, int M, int N, float alpha, void* stream) {
+  AVS_REQUIRE(dy && out, "avs_colsum_bf16: null pointer");
+  AVS_REQUIRE(N % 2 == 0 && ld % 2 == 0, "avs_colsum_bf16: N and ld must be even");
+  if (M == 0 || N == 0) return 0;
+  const int col_blocks = ceil_div(N, 64);
+  int row_blocks = max(1, (avs_num_sms() * 4) / col_blocks);
+  int rows_per_cta = max(64, ceil_div(M, row_blocks));
+  row_blocks = ceil_div(M, rows_per_cta);
+  dim3 grid(col_blocks, row_blocks);
+  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, out, M, N, ld, rows_per_cta, alpha);
+  return avs_check_launch("colsum_kernel");
+}
+
+// flag = 1.0 if any element is inf/nan (GradScaler found_inf); caller zeroes the flag first.
+__global__ void found_inf_kernel(const float* __restrict__ g, long long n, float* __restrict__ flag) {
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    bad |= !isfinite(g[i]);
+  if (__syncthreads_or(bad) && threadIdx.x == 0) *flag = 1.0f;
+}
+
+extern "C" int avs_found_inf(const float* g, long long n, float* flag, void* stream) {
+  AVS_REQUIRE(g && flag, "avs_found_inf: null pointer");
+  if (n == 0) return 0;
+  const int blocks = (int)min((long long)avs_num_sms() * 16, ceil_div_ll(n, 256));
+  found_inf_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, n, flag);
+  return avs_check_launch("found_inf_kernel");
+}

@@ -60,6 +60,112 @@ typedef struct {
 int avs_gemm_bf16(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major, void* C,
                   long long ldc, int M, int N, int K, const avs_gemm_epilogue_t* epi, int split_k, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Random masking (bit-exact index work).  cav_mae_base.py:365-390 (unstructured), :392-439 (structured; the
+ * host builds the noise, the device sorts it).  Stable ascending argsort (ties -> lower index):
+ *   ids_shuffle[n,:] = argsort(noise[n,:]); ids_restore = argsort(ids_shuffle); mask[n,j] = ids_restore[n,j] >= len_keep
+ * ---------------------------------------------------------------------------------------------- */
+int avs_mask_argsort(const float* noise, int N, int L, int len_keep, int32_t* ids_shuffle, int32_t* ids_restore,
+                     float* mask, void* stream);
+/* out[n,i,:] = x[n, ids[n,i], :], i < keep; byte-exact (replaces torch.gather at cav_mae_base.py:382,431). */
+int avs_gather_rows(const void* x, const int32_t* ids, void* out, int N, int L, int keep, int ids_ld, int row_bytes,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Patch extraction fused with the kept-token gather (A operand of the patch-embed GEMM, bf16).
+ *   audio fp32 [B,T,F] -> [B*keep, ld_out], token f*(T/p)+t, vector (pf,pt)   cav_mae_base.py:444-448
+ *   video fp32 [B,C,H,W] -> [B*keep, ld_out], token h*(W/p)+w, vector (c,p,q)  cav_mae_base.py:453
+ * ids (int32 [B, ids_ld], first `keep` columns used) may be NULL => all tokens in order.
+ * sample_idx (int32 [B], may be NULL): output sample b reads input sample sample_idx[b] (chunk permutation of
+ * forward_encoder_mmixed, cav_mae_base.py:533-549).
+ * ---------------------------------------------------------------------------------------------- */
+int avs_patchify_audio(const float* audio, const int32_t* ids, const int32_t* sample_idx, void* out, int B, int T, int F, int patch, int keep,
+                       int ids_ld, int ld_out, void* stream);
+int avs_patchify_video(const float* img, const int32_t* ids, const int32_t* sample_idx, void* out, int B, int C, int H, int W, int patch,
+                       int keep, int ids_ld, int ld_out, void* stream);
+/* table[idx[m],:] += alpha*dy[m,:]  (pos-embed gradient; idx NULL => m % table_rows) */
+int avs_scatter_add_rows(const void* dy, const int32_t* idx, float* table, int M, int D, int table_rows, float alpha,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decoder restore: mask-token fill + un-shuffle + positional + modality embeddings in one pass, and its backward.
+ * cav_mae_base.py:604-626 (removes the two int(mask[0].sum()) host syncs).
+ *   x bf16 [B, keep_a+keep_v, D]  ->  out bf16 [B, Ta+Tv, D]
+ * ---------------------------------------------------------------------------------------------- */
+int avs_decoder_restore_fwd(const void* x, const int32_t* ids_restore_a, const int32_t* ids_restore_v,
+                            const float* mask_token, const float* pos_a, const float* pos_v, const float* mod_a,
+                            const float* mod_v, void* out, int B, int Ta, int Tv, int keep_a, int keep_v, int D,
+                            void* stream);
+/* dx is fully written; the five fp32 parameter gradients are ACCUMULATED. */
+int avs_decoder_restore_bwd(const void* dout, const int32_t* ids_restore_a, const int32_t* ids_restore_v, void* dx,
+                            float* dmask_token, float* dpos_a, float* dpos_v, float* dmod_a, float* dmod_v, int B,
+                            int Ta, int Tv, int keep_a, int keep_v, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm (bf16 activations, fp32 affine + statistics).  Block norms eps 1e-5 (cav_mae_base.py:116,151-152),
+ * final norm/norm_a eps 1e-6 (:492-495,:563-566), decoder_norm (:631).
+ * Row maps (per-sample concatenation, torch.cat at :503 / slicing at :634-635), one for the x/dx/resid side and
+ * one for the y/dy side; stride 0 => identity:
+ *   row(r) = (seq_len && stride) ? (r/seq_len)*stride + off + r%seq_len : r
+ * bwd: dx = [resid +] LN'(dy_eff), dy_eff = dy[y_row] (+ dpool[r/seq_len]*pool_scale — gradient of the token mean);
+ *      dgamma/dbeta are ACCUMULATED (fp32 atomics).
+ * ---------------------------------------------------------------------------------------------- */
+int avs_layernorm_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y, float* mean,
+                      float* rstd, int M, int D, int seq_len, int x_seq_stride, int x_off, int y_seq_stride, int y_off,
+                      void* stream);
+int avs_layernorm_bwd(const void* dy, const float* dpool, float pool_scale, const void* x, const float* mean,
+                      const float* rstd, const float* gamma, const void* resid, void* dx, float* dgamma, float* dbeta,
+                      int M, int D, int seq_len, int x_seq_stride, int x_off, int y_seq_stride, int y_off,
+                      void* stream);
+/* out fp32 [n_seq, D] = mean over the seq_len tokens of each sequence (.mean(dim=1), cav_mae_base.py:563-566,729) */
+int avs_seq_mean_fwd(const void* y, float* out, int n_seq, int seq_len, int D, int y_seq_stride, int y_off,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused attention (flash-style), packed QKV in / O out.  Attention.forward, cav_mae_base.py:58-77.
+ *   qkv bf16 [n_seq*S, ld_qkv] = [q | k | v], each H*head_dim wide; out bf16 [n_seq*S, ld_o];
+ *   lse2 fp32 [n_seq, H, S] (log2-domain logsumexp, saved for backward); delta: scratch [n_seq, H, S].
+ * ---------------------------------------------------------------------------------------------- */
+int avs_attention_fwd(const void* qkv, long long ld_qkv, void* out, long long ld_o, float* lse2, int n_seq, int S,
+                      int H, int head_dim, void* stream);
+int avs_attention_bwd(const void* qkv, long long ld_qkv, const void* out, const void* dout, long long ld_o,
+                      const float* lse2, float* delta, void* dqkv, int n_seq, int S, int H, int head_dim, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Masked-MSE reconstruction loss, target read from the raw input (patchify + forward_mae_loss,
+ * cav_mae_base.py:343-351,663-683).  kind 0 = audio [B,d0=T,d1=F], kind 1 = video [B,C,d0=H,d1=W].
+ *   fwd: *loss_accum += sum_masked mean_e (pred-target)^2 / n_masked      (caller zeroes loss_accum)
+ *   bwd: dpred = mask * 2 (pred-target) / (P*n_masked) * (*upstream)      (upstream NULL => 1)
+ * ---------------------------------------------------------------------------------------------- */
+int avs_mae_loss_fwd(const void* pred, const float* input, const float* mask, int kind, int B, int patch, int C,
+                     int d0, int d1, float n_masked, float* loss_accum, void* stream);
+int avs_mae_loss_bwd(const void* pred, const float* input, const float* mask, int kind, int B, int patch, int C,
+                     int d0, int d1, float n_masked, const float* upstream, void* dpred, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * InfoNCE over L2-normalised embeddings (forward_contrastive, cav_mae_base.py:641-661), fp32.
+ *   ea, ev fp32 [N, D] (global batch); temperature 0.05; bidirect => mean of both directions.
+ *   bwd returns gradients for rows [row0,row0+rows) only (this rank's slice); `weight` multiplies the loss
+ *   (contrast_loss_weight x world-size factor of GatherLayer.backward, gather_layer.py:34-37).
+ * ---------------------------------------------------------------------------------------------- */
+size_t avs_infonce_workspace_bytes(int N, int D);
+int avs_infonce_fwd(const float* ea, const float* ev, int N, int D, float temperature, int bidirect, float* workspace,
+                    float* loss_out, float* acc_out, void* stream);
+int avs_infonce_bwd(int N, int D, float temperature, int bidirect, float weight, const float* upstream,
+                    float* workspace, int row0, int rows, float* scratch /* 2*rows*D */, float* d_ea, float* d_ev,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Flat-arena optimizer plumbing.  torch.optim.Adam(lr, betas=(0.95,0.999), eps=1e-8, weight_decay=5e-7) +
+ * GradScaler unscale/inf-skip (traintest_cavmae_base.py:64-66,138-140).  decoupled=1 => AdamW.
+ * ---------------------------------------------------------------------------------------------- */
+int avs_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16 /* or NULL */, long long n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
+                  const float* inv_scale /* or NULL */, const float* found_inf /* or NULL */, void* stream);
+int avs_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+int avs_colsum_bf16(const void* dy, long long ld, float* out_accum, int M, int N, float alpha, void* stream);
+int avs_found_inf(const float* g, long long n, float* flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

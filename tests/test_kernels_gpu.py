@@ -1,0 +1,326 @@
+"""Per-kernel parity tests (B200): every C-ABI entry against the oracle / a plain fp32 torch statement of the op.
+Index work is bit-exact; floating point within the tolerance written beside each assert (bf16 operands)."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from avsiam_b200 import ops  # noqa: E402
+from oracle import avsiam_oracle as O  # noqa: E402
+
+DEV = "cuda"
+
+
+def rnd(*shape, scale=1.0, dtype=torch.float32, seed=None):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed if seed is not None else (hash(shape) % 1000) + 1)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def rel_err(a, b):
+    return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(354, 768, 768), (1000, 2304, 768), (256, 128, 200), (45, 512, 3072)])
+def test_gemm_fwd_bias_gelu_resid(M, N, K):
+    a, w = rnd(M, K, dtype=torch.bfloat16), rnd(N, K, scale=K ** -0.5, dtype=torch.bfloat16)
+    bias, res = rnd(N), rnd(M, N, dtype=torch.bfloat16)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    pre = torch.empty_like(out)
+    ops.gemm(a, w, out, M, N, K, bias=bias, gelu=True, aux_out=pre, resid=res)
+    ref_pre = a.float() @ w.float().t() + bias
+    ref = F.gelu(ref_pre) + res.float()
+    assert rel_err(pre, ref_pre) < 6e-3      # bf16 output rounding (2^-9) dominates
+    assert rel_err(out, ref) < 6e-3
+
+
+def test_gemm_rowadd_alpha_patch_embed_epilogue():
+    M, N, K, T = 300, 768, 256, 64
+    a, w, bias, pos = rnd(M, K, dtype=torch.bfloat16), rnd(N, K, scale=K ** -0.5, dtype=torch.bfloat16), rnd(N), rnd(T, N)
+    idx = torch.randint(0, T, (M,), device=DEV, dtype=torch.int32)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(a, w, out, M, N, K, bias=bias, rowadd=pos, rowidx=idx, alpha=2.0)
+    ref = 2.0 * (a.float() @ w.float().t() + bias + pos[idx.long()])
+    assert rel_err(out, ref) < 6e-3
+    ops.gemm(a, w, out, M, N, K, bias=bias, rowadd=pos, alpha=2.0)  # implicit m % T
+    ref = 2.0 * (a.float() @ w.float().t() + bias + pos[torch.arange(M, device=DEV) % T])
+    assert rel_err(out, ref) < 6e-3
+
+
+def test_gemm_dgrad_dgelu_and_wgrad_accumulate():
+    M, N, K = 708, 3072, 768  # y = x W^T, W [N,K]
+    x, w, dy = rnd(M, K, dtype=torch.bfloat16), rnd(N, K, scale=K ** -0.5, dtype=torch.bfloat16), rnd(M, N, dtype=torch.bfloat16)
+    # dgrad: dx[M,K] = dy[M,N] @ W[N,K]  -> reduction N; B operand = W read MN-major
+    dx = torch.empty(M, K, dtype=torch.bfloat16, device=DEV)
+    pre = rnd(M, K, dtype=torch.bfloat16)
+    ops.gemm(dy, w, dx, M, K, N, b_major=ops.MAJOR_MN, dgelu_aux=pre)
+    xr = pre.float().requires_grad_(True)
+    F.gelu(xr).backward(dy.float() @ w.float())
+    assert rel_err(dx, xr.grad) < 6e-3
+    # wgrad: dW[N,K] += dy^T @ x  -> reduction over M; both operands MN-major; fp32 accumulate with split-K
+    dw = torch.ones(N, K, dtype=torch.float32, device=DEV)
+    ops.gemm(dy, x, dw, N, K, M, a_major=ops.MAJOR_MN, b_major=ops.MAJOR_MN, accumulate=True, split_k=0)
+    ref = 1.0 + dy.float().t() @ x.float()
+    assert rel_err(dw, ref) < 1e-4           # fp32 accumulate of exact bf16 products
+
+
+def test_gemm_rejects_bad_input():
+    a = rnd(8, 60, dtype=torch.bfloat16)  # pitch 60 not a multiple of 8
+    w = rnd(16, 60, dtype=torch.bfloat16)
+    out = torch.empty(8, 16, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, w, out, 8, 16, 60)
+
+
+# ------------------------------------------------------------------------------------------------ masking
+@pytest.mark.parametrize("N,L,ratio", [(7, 512, 0.75), (5, 196, 0.75), (3, 657, 0.4), (2, 40, 0.0), (4, 1, 0.0)])
+def test_mask_argsort_bit_exact(N, L, ratio):
+    noise = torch.rand(N, L, device=DEV)
+    noise[0, : L // 2] = 1.1  # ties, as produced by structured masking (cav_mae_base.py:408,413)
+    keep = O.len_keep_of(L, ratio)
+    ids, ids_restore, mask = ops.mask_argsort(noise, keep)
+    ref_ids = torch.argsort(noise.cpu(), dim=1, stable=True)
+    assert torch.equal(ids.cpu().long(), ref_ids)
+    x = torch.randn(N, L, 8)
+    _, ref_mask, ref_restore = O.apply_masking(x, ref_ids, keep)
+    assert torch.equal(ids_restore.cpu().long(), ref_restore)
+    assert torch.equal(mask.cpu(), ref_mask)
+
+
+def test_gather_rows_bit_exact_and_golden(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "masking_unstructured.pt"), weights_only=False)
+    x, ids = g["x"].to(DEV), g["ids_shuffle"].to(DEV).int()
+    keep = O.len_keep_of(x.shape[1], g["mask_ratio"])
+    out = ops.gather_rows(x, ids, keep)
+    assert torch.equal(out.cpu(), g["x_masked"])          # reference's own torch.gather output
+    ids2, ids_restore, mask = ops.mask_from_ids(ids, keep)
+    assert torch.equal(ids2, ids)
+    assert torch.equal(ids_restore.cpu().long(), g["ids_restore"])
+    assert torch.equal(mask.cpu(), g["mask"])
+    xb = torch.randn(9, 512, 768, device=DEV).to(torch.bfloat16)
+    idb = torch.argsort(torch.rand(9, 512, device=DEV), dim=1).int()
+    ob = ops.gather_rows(xb, idb, 128)
+    ref = torch.gather(xb, 1, idb[:, :128].long().unsqueeze(-1).expand(-1, -1, 768))
+    assert torch.equal(ob, ref)
+    assert ops.gather_rows(xb, idb, 0).shape == (9, 0, 768)  # empty keep
+
+
+def test_patchify_matches_patch_embed_order():
+    d = O.VIT_B
+    B = 3
+    audio, img = rnd(B, d.audio_len, d.mel), rnd(B, 3, d.img, d.img)
+    ids_a = torch.argsort(torch.rand(B, d.Ta, device=DEV), dim=1).int()
+    ids_v = torch.argsort(torch.rand(B, d.Tv, device=DEV), dim=1).int()
+    ka, kv = 128, 49
+    pa = torch.empty(B * ka, 256, dtype=torch.bfloat16, device=DEV)
+    pv = torch.empty(B * kv, 768, dtype=torch.bfloat16, device=DEV)
+    ops.patchify_audio(audio, ids_a, ka, 16, pa)
+    ops.patchify_video(img, ids_v, kv, 16, pv)
+    eye_a = torch.eye(256).reshape(256, 1, 16, 16)
+    eye_v = torch.eye(768).reshape(768, 3, 16, 16)
+    ref_a = O.patch_embed_audio(audio.cpu(), eye_a, torch.zeros(256), d)   # identity weights expose the vector order
+    ref_v = O.patch_embed_video(img.cpu(), eye_v, torch.zeros(768), d)
+    ref_a = torch.gather(ref_a, 1, ids_a[:, :ka].cpu().long().unsqueeze(-1).expand(-1, -1, 256)).reshape(B * ka, 256)
+    ref_v = torch.gather(ref_v, 1, ids_v[:, :kv].cpu().long().unsqueeze(-1).expand(-1, -1, 768)).reshape(B * kv, 768)
+    assert torch.equal(pa.cpu(), ref_a.to(torch.bfloat16))
+    assert torch.equal(pv.cpu(), ref_v.to(torch.bfloat16))
+    full = torch.empty(B * d.Ta, 256, dtype=torch.bfloat16, device=DEV)
+    ops.patchify_audio(audio, None, d.Ta, 16, full)
+    assert torch.equal(full.cpu(), O.patch_embed_audio(audio.cpu(), eye_a, torch.zeros(256), d).reshape(-1, 256).to(torch.bfloat16))
+
+
+def test_decoder_restore_fwd_bwd():
+    B, Ta, Tv, ka, kv, D = 3, 64, 36, 16, 9, 64
+    x = rnd(B, ka + kv, D, dtype=torch.bfloat16)
+    ira = torch.argsort(torch.argsort(torch.rand(B, Ta, device=DEV), dim=1), dim=1).int()
+    irv = torch.argsort(torch.argsort(torch.rand(B, Tv, device=DEV), dim=1), dim=1).int()
+    mt, pos_a, pos_v, mod_a, mod_v = rnd(D), rnd(Ta, D), rnd(Tv, D), rnd(D), rnd(D)
+    out = torch.empty(B, Ta + Tv, D, dtype=torch.bfloat16, device=DEV)
+    ops.decoder_restore_fwd(x, ira, irv, mt, pos_a, pos_v, mod_a, mod_v, out, B, Ta, Tv, ka, kv, D)
+    leaves = [t.clone().float().requires_grad_(True) for t in (x, mt, pos_a, pos_v, mod_a, mod_v)]
+    xr, mtr, par, pvr, mar, mvr = leaves
+    a_ = torch.cat([xr[:, :ka], mtr.expand(B, Ta - ka, D)], 1)
+    a_ = torch.gather(a_, 1, ira.long().unsqueeze(-1).expand(-1, -1, D)) + par + mar
+    v_ = torch.cat([xr[:, ka:], mtr.expand(B, Tv - kv, D)], 1)
+    v_ = torch.gather(v_, 1, irv.long().unsqueeze(-1).expand(-1, -1, D)) + pvr + mvr
+    ref = torch.cat([a_, v_], 1)
+    assert torch.equal(out, ref.to(torch.bfloat16))       # pure index work + one rounding
+    dout = rnd(B, Ta + Tv, D, dtype=torch.bfloat16)
+    ref.backward(dout.float())
+    dx = torch.full_like(x, float("nan"))
+    grads = [torch.zeros_like(t) for t in (mt, pos_a, pos_v, mod_a, mod_v)]
+    ops.decoder_restore_bwd(dout, ira, irv, dx, *grads, B, Ta, Tv, ka, kv, D)
+    assert torch.equal(dx.float(), xr.grad)
+    for g, l in zip(grads, leaves[1:]):
+        assert torch.allclose(g, l.grad, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("M,D,eps", [(177 * 3, 768, 1e-5), (708 * 2, 512, 1e-5), (98, 1280, 1e-6), (40, 64, 1e-5)])
+def test_layernorm_fwd_bwd(M, D, eps):
+    x = rnd(M, D, scale=2.0, dtype=torch.bfloat16)
+    gamma, beta = 1 + 0.1 * rnd(D), 0.1 * rnd(D)
+    y = torch.empty_like(x)
+    mean, rstd = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    ops.layernorm_fwd(x, gamma, beta, eps, y, mean, rstd, M, D)
+    xr, gr, br = x.float().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (D,), gr, br, eps)
+    assert rel_err(y, ref) < 4e-3
+    dy, res = rnd(M, D, dtype=torch.bfloat16), rnd(M, D, dtype=torch.bfloat16)
+    ref.backward(dy.float())
+    dx = torch.empty_like(x)
+    dg, db = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, dg, db, M, D, resid=res)
+    assert rel_err(dx, xr.grad + res.float()) < 5e-3
+    assert rel_err(dg, gr.grad) < 1e-3 and rel_err(db, br.grad) < 1e-3
+
+
+def test_layernorm_rowmap_and_pool_grad():
+    n_seq, S, D, stride, off = 4, 5, 128, 12, 7
+    M = n_seq * S
+    x = rnd(M, D, dtype=torch.bfloat16)
+    gamma, beta = 1 + 0.1 * rnd(D), 0.1 * rnd(D)
+    ycat = torch.zeros(n_seq * stride, D, dtype=torch.bfloat16, device=DEV)
+    mean, rstd = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    ops.layernorm_fwd(x, gamma, beta, 1e-6, ycat, mean, rstd, M, D, seq_len=S, y_seq_stride=stride, y_off=off)
+    xr = x.float().requires_grad_(True)
+    ref = F.layer_norm(xr, (D,), gamma, beta, 1e-6).reshape(n_seq, S, D)
+    got = ycat.reshape(n_seq, stride, D)[:, off:off + S]
+    assert rel_err(got, ref) < 4e-3
+    pooled = torch.empty(n_seq, D, device=DEV)
+    ops.seq_mean_fwd(ycat, pooled, n_seq, S, D, y_seq_stride=stride, y_off=off)
+    assert torch.allclose(pooled, got.float().mean(1), rtol=1e-5, atol=1e-5)
+    dycat = rnd(n_seq * stride, D, dtype=torch.bfloat16)
+    dpool = rnd(n_seq, D)
+    (ref * dycat.reshape(n_seq, stride, D)[:, off:off + S].float()).sum().backward(retain_graph=True)
+    (ref.mean(1) * dpool).sum().backward()
+    dx = torch.empty_like(x)
+    dg, db = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    ops.layernorm_bwd(dycat, x, mean, rstd, gamma, dx, dg, db, M, D, dpool=dpool, pool_scale=1.0 / S, seq_len=S,
+                      y_seq_stride=stride, y_off=off)
+    assert rel_err(dx, xr.grad) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("n_seq,S,H,hd", [(3, 49, 12, 64), (2, 128, 12, 64), (2, 177, 12, 64), (2, 708, 16, 32),
+                                          (1, 64, 2, 32), (2, 1, 2, 64)])
+def test_attention_fwd_bwd(n_seq, S, H, hd):
+    D = H * hd
+    qkv = rnd(n_seq * S, 3 * D, dtype=torch.bfloat16)
+    out = torch.empty(n_seq * S, D, dtype=torch.bfloat16, device=DEV)
+    lse2 = torch.empty(n_seq, H, S, device=DEV)
+    ops.attention_fwd(qkv, out, lse2, n_seq, S, H, hd)
+    q5 = qkv.float().reshape(n_seq, S, 3, H, hd).permute(2, 0, 3, 1, 4).detach().requires_grad_(True)
+    q, k, v = q5[0], q5[1], q5[2]
+    att = (q @ k.transpose(-2, -1)) * hd ** -0.5
+    ref = (att.softmax(-1) @ v).transpose(1, 2).reshape(n_seq * S, D)
+    assert rel_err(out, ref) < 8e-3
+    ref_lse2 = torch.logsumexp(att, -1) / math.log(2)
+    assert torch.allclose(lse2, ref_lse2, rtol=1e-4, atol=1e-3)
+    dout = rnd(n_seq * S, D, dtype=torch.bfloat16)
+    ref.backward(dout.float())
+    ref_dqkv = q5.grad.permute(1, 3, 0, 2, 4).reshape(n_seq * S, 3 * D)
+    dqkv = torch.full_like(qkv, float("nan"))
+    delta = torch.empty(n_seq, H, S, device=DEV)
+    ops.attention_bwd(qkv, out, dout, lse2, delta, dqkv, n_seq, S, H, hd)
+    for i, name in enumerate("qkv"):
+        e = rel_err(dqkv[:, i * D:(i + 1) * D], ref_dqkv[:, i * D:(i + 1) * D])
+        assert e < 2e-2, (name, e)   # bf16 P / dS operands in the tensor-core products
+
+
+# ------------------------------------------------------------------------------------------------ losses
+def test_mae_loss_fwd_bwd():
+    d = O.VIT_B
+    B = 2
+    audio, img = rnd(B, d.audio_len, d.mel), rnd(B, 3, d.img, d.img)
+    pa, pv = rnd(B * d.Ta, 256, dtype=torch.bfloat16), rnd(B * d.Tv, 768, dtype=torch.bfloat16)
+    ma = (torch.rand(B, d.Ta, device=DEV) < 0.75).float()
+    mv = (torch.rand(B, d.Tv, device=DEV) < 0.75).float()
+    loss = torch.zeros(2, device=DEV)
+    ops.mae_loss_fwd(pa, audio, ma, 0, B, 16, 1, d.audio_len, d.mel, float(ma.sum()), loss[0:1])
+    ops.mae_loss_fwd(pv, img, mv, 1, B, 16, 3, d.img, d.img, float(mv.sum()), loss[1:2])
+    par = pa.float().cpu().reshape(B, d.Ta, 256).requires_grad_(True)
+    pvr = pv.float().cpu().reshape(B, d.Tv, 768).requires_grad_(True)
+    ra = O.mae_loss(O.patchify_target_audio(audio.cpu(), d), par, ma.cpu())
+    rv = O.mae_loss(O.patchify_target_video(img.cpu(), d), pvr, mv.cpu())
+    assert float(loss[0]) == pytest.approx(float(ra), rel=1e-4)
+    assert float(loss[1]) == pytest.approx(float(rv), rel=1e-4)
+    up = torch.tensor([3.0], device=DEV)
+    (3.0 * ra).backward(); (3.0 * rv).backward()
+    dpa, dpv = torch.empty_like(pa), torch.empty_like(pv)
+    ops.mae_loss_bwd(pa, audio, ma, 0, B, 16, 1, d.audio_len, d.mel, float(ma.sum()), up, dpa)
+    ops.mae_loss_bwd(pv, img, mv, 1, B, 16, 3, d.img, d.img, float(mv.sum()), up, dpv)
+    assert rel_err(dpa.cpu(), par.grad.reshape(-1, 256)) < 4e-3
+    assert rel_err(dpv.cpu(), pvr.grad.reshape(-1, 768)) < 4e-3
+
+
+@pytest.mark.parametrize("N,D,bidirect", [(10, 768, True), (300, 128, True), (64, 768, False)])
+def test_infonce_fwd_bwd(N, D, bidirect):
+    ea, ev = rnd(N, D, seed=3), rnd(N, D, seed=4)
+    ev = ev + 0.5 * ea  # correlated pairs => non-trivial accuracy
+    ws = ops.infonce_workspace(N, D, DEV)
+    res = torch.zeros(2, device=DEV)
+    ops.infonce_fwd(ea, ev, 0.05, bidirect, ws, res[0:1], res[1:2])
+    ar, vr = ea.cpu().requires_grad_(True), ev.cpu().requires_grad_(True)
+    loss, acc = O.contrastive(ar, vr, bidirect=bidirect)
+    assert float(res[0]) == pytest.approx(float(loss), rel=1e-4, abs=1e-5)   # fp32 path: 1e-4
+    assert float(res[1]) == pytest.approx(float(acc), abs=1e-6)
+    (0.7 * 2.0 * loss).backward()
+    row0, rows = N // 3, N - N // 3 - 1
+    d_ea, d_ev = torch.empty(rows, D, device=DEV), torch.empty(rows, D, device=DEV)
+    scratch = torch.empty(2 * rows * D, device=DEV)
+    up = torch.tensor([2.0], device=DEV)
+    ops.infonce_bwd(N, D, 0.05, bidirect, 0.7, up, ws, row0, rows, scratch, d_ea, d_ev)
+    assert rel_err(d_ea.cpu(), ar.grad[row0:row0 + rows]) < 1e-3
+    assert rel_err(d_ev.cpu(), vr.grad[row0:row0 + rows]) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ optimizer
+def test_adam_matches_torch_optim():
+    n = 4096 * 5
+    p0, g1, g2 = rnd(n, seed=1), rnd(n, seed=2), rnd(n, seed=3)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref_p], lr=2e-4, weight_decay=5e-7, betas=(0.95, 0.999))
+    p, m, v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    shadow = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    for step, g in enumerate((g1, g2), 1):
+        ref_p.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g, m, v, shadow, 2e-4, 0.95, 0.999, 1e-8, 5e-7, step)
+    assert torch.allclose(p, ref_p.data, rtol=1e-5, atol=1e-7)
+    assert torch.equal(shadow, p.to(torch.bfloat16))
+    # found_inf skips the step; inv_scale unscales
+    flag = torch.ones(1, device=DEV)
+    before = p.clone()
+    ops.adam_step(p, g1, m, v, None, 2e-4, 0.95, 0.999, 1e-8, 5e-7, 3, found_inf=flag)
+    assert torch.equal(p, before)
+    flag.zero_()
+    bad = g1.clone(); bad[7] = float("inf")
+    ops.found_inf(bad, flag)
+    assert float(flag) == 1.0
+
+
+def test_colsum_and_cast():
+    M, N = 1234, 2304
+    dy = rnd(M, N, dtype=torch.bfloat16)
+    out = torch.ones(N, device=DEV)
+    ops.colsum(dy, out, M, N)
+    assert torch.allclose(out, 1 + dy.float().sum(0), rtol=1e-4, atol=1e-3)
+    src = rnd(100003)
+    dst = torch.empty(100003, dtype=torch.bfloat16, device=DEV)
+    ops.cast_f32_to_bf16(src, dst)
+    assert torch.equal(dst, src.to(torch.bfloat16))
+    table = torch.zeros(16, 64, device=DEV)
+    idx = torch.randint(0, 16, (200,), device=DEV, dtype=torch.int32)
+    d2 = rnd(200, 64, dtype=torch.bfloat16)
+    ops.scatter_add_rows(d2, idx, table, 2.0)
+    ref = torch.zeros(16, 64, device=DEV).index_add_(0, idx.long(), 2.0 * d2.float())
+    assert torch.allclose(table, ref, rtol=1e-5, atol=1e-5)
