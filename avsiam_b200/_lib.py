@@ -56,7 +56,7 @@ SIGNATURES = {
     "avs_infonce_workspace_bytes": [_I, _I],
     "avs_infonce_fwd": [_P, _P, _I, _I, _F, _I, _P, _P, _P, _P],
     "avs_infonce_bwd": [_I, _I, _F, _I, _F, _P, _P, _I, _I, _P, _P, _P, _P],
-    "avs_adam_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _I, _P, _P, _P],
+    "avs_adam_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _I, _P, _P, _P, _P],
     "avs_cast_f32_to_bf16": [_P, _P, _L, _P],
     "avs_colsum_bf16": [_P, _L, _P, _I, _I, _F, _P],
     "avs_found_inf": [_P, _L, _P, _P],

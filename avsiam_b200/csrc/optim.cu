@@ -8,17 +8,21 @@
 // torch.optim.Adam semantics (non-amsgrad): coupled L2 (g += wd*p) or decoupled (AdamW: p *= 1 - lr*wd).
 // found_inf (optional, device int/float flag != 0) => skip the whole step (GradScaler.step behaviour).
 // inv_scale (optional, device float) multiplies every gradient first (GradScaler.unscale_).
+// active (optional, one byte per 64-element chunk of the arena): 0 => the chunk belongs to a parameter whose
+// .grad is None in the reference (torch.optim skips those entirely — no weight decay, no moment update).
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v,
                                                    bf16* __restrict__ shadow, long long n, float lr, float beta1,
                                                    float beta2, float eps, float wd, float bc1, float bc2_sqrt,
                                                    int decoupled, const float* __restrict__ inv_scale,
-                                                   const float* __restrict__ found_inf) {
+                                                   const float* __restrict__ found_inf,
+                                                   const uint8_t* __restrict__ active) {
   if (found_inf != nullptr && *found_inf != 0.f) return;
   const float gs = inv_scale ? *inv_scale : 1.0f;
   const long long n4 = n / 4;
   const float step_size = lr / bc1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    if (active != nullptr && active[i >> 4] == 0) continue;  // parameter received no gradient: Adam skips it
     float4 pp = reinterpret_cast<float4*>(p)[i];
     const float4 gg = reinterpret_cast<const float4*>(g)[i];
     float4 mm = reinterpret_cast<float4*>(m)[i];
@@ -49,7 +53,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 
 extern "C" int avs_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr,
                              float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
-                             const float* inv_scale, const float* found_inf, void* stream) {
+                             const float* inv_scale, const float* found_inf, const uint8_t* active_chunks,
+                             void* stream) {
   AVS_REQUIRE(p && g && m && v, "avs_adam_step: null pointer");
   AVS_REQUIRE(n % 4 == 0, "avs_adam_step: n must be a multiple of 4 (pad the arena)");
   AVS_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "avs_adam_step: 16-byte alignment");
@@ -59,7 +64,7 @@ extern "C" int avs_adam_step(float* p, const float* g, float* m, float* v, void*
   const int blocks = (int)min((long long)avs_num_sms() * 16, ceil_div_ll(n / 4, 256));
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)shadow_bf16, n, lr, beta1, beta2, eps,
                                                         weight_decay, (float)bc1, (float)sqrt(bc2), decoupled,
-                                                        inv_scale, found_inf);
+                                                        inv_scale, found_inf, active_chunks);
   return avs_check_launch("adam_kernel");
 }
 

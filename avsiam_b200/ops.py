@@ -275,14 +275,18 @@ def infonce_bwd(N, D, temperature, bidirect, weight, upstream, workspace, row0, 
 
 # --------------------------------------------------------------------------------------------- optimizer plumbing
 def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, decoupled=False, inv_scale=None,
-              found_inf=None):
+              found_inf=None, active=None):
     for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
         _chk(t, F32, "adam." + n)
     if shadow is not None:
         _chk(shadow, BF16, "adam.shadow")
+    if active is not None:
+        _chk(active, torch.uint8, "adam.active")
+        if active.numel() * 64 < p.numel():
+            raise RuntimeError("adam.active: one byte per 64 parameters required")
     _lib.check(_lib.lib().avs_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(shadow), p.numel(),
                                         lr, beta1, beta2, eps, weight_decay, step, int(decoupled), _p(inv_scale),
-                                        _p(found_inf), _stream()), "avs_adam_step")
+                                        _p(found_inf), _p(active), _stream()), "avs_adam_step")
 
 
 def cast_f32_to_bf16(src, dst):
@@ -308,3 +312,97 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     _lib.lib().avs_reset_launch_count()
+
+
+# --------------------------------------------------------------------------------------------- per-family timing
+class KernelTimer:
+    """CUDA-event timing of every C-ABI call, grouped by kernel family (bench.py's roofline leg).
+
+    `with KernelTimer() as t: step()` brackets each wrapper call with two events recorded on the CURRENT stream
+    (the stream the kernels are launched on); `t.summary()` synchronises and returns
+    {family: {"ms": total, "calls": n, "work": algorithmic flops or bytes}}. Off by default: the wrappers
+    pay one `is None` test when no timer is installed."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _TIMER
+        _TIMER = self
+        return self
+
+    def __exit__(self, *exc):
+        global _TIMER
+        _TIMER = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for fam, s, e, work in self.records:
+            d = out.setdefault(fam, {"ms": 0.0, "calls": 0, "work": 0.0})
+            d["ms"] += s.elapsed_time(e)
+            d["calls"] += 1
+            d["work"] += work
+        return out
+
+
+_TIMER: Optional[KernelTimer] = None
+
+
+def _nbytes(*ts):
+    return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
+
+
+def _work_gemm(a, b, out, M, N, K, **kw):
+    return 2.0 * M * N * K
+
+
+def _work_attn_fwd(qkv, out, lse2, n_seq, S, H, hd):
+    return 4.0 * n_seq * H * S * S * hd
+
+
+def _work_attn_bwd(qkv, out, dout, lse2, delta, dqkv, n_seq, S, H, hd):
+    return 10.0 * n_seq * H * S * S * hd       # 5 S x S x hd products (QK^T, dO V^T, P^T dO, dS^T Q, dS K)
+
+
+def _instrument(family, fn, work_fn):
+    def wrapped(*a, **k):
+        t = _TIMER
+        if t is None:
+            return fn(*a, **k)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = fn(*a, **k)
+        e.record()
+        t.records.append((family, s, e, work_fn(*a, **k)))
+        return r
+    wrapped.__name__ = fn.__name__
+    wrapped.__doc__ = fn.__doc__
+    return wrapped
+
+
+gemm = _instrument("gemm", gemm, _work_gemm)
+attention_fwd = _instrument("attention_fwd", attention_fwd, _work_attn_fwd)
+attention_bwd = _instrument("attention_bwd", attention_bwd, _work_attn_bwd)
+layernorm_fwd = _instrument("layernorm_fwd", layernorm_fwd,
+                            lambda x, gamma, beta, eps, y, mean, rstd, M, D, **k: 4.0 * M * D)
+layernorm_bwd = _instrument("layernorm_bwd", layernorm_bwd,
+                            lambda dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, **k:
+                            (8.0 if k.get("resid") is not None else 6.0) * M * D)
+colsum = _instrument("colsum", colsum, lambda dy, out, M, N, alpha=1.0: 2.0 * M * N)
+adam_step = _instrument("adam", adam_step, lambda p, g, m, v, shadow, *a, **k: 28.0 * p.numel() + (2.0 * p.numel() if shadow is not None else 0.0))
+cast_f32_to_bf16 = _instrument("cast", cast_f32_to_bf16, lambda src, dst: 6.0 * src.numel())
+patchify_audio = _instrument("patchify", patchify_audio, lambda audio, ids, keep, patch, out, sample_idx=None: 3.0 * out.numel())
+patchify_video = _instrument("patchify", patchify_video, lambda img, ids, keep, patch, out, sample_idx=None: 3.0 * out.numel())
+decoder_restore_fwd = _instrument("decoder_restore", decoder_restore_fwd,
+                                  lambda x, ira, irv, mt, pa, pv, ma, mv, out, *a: _nbytes(x, out))
+decoder_restore_bwd = _instrument("decoder_restore", decoder_restore_bwd,
+                                  lambda dout, ira, irv, dx, *a: _nbytes(dout, dx))
+mae_loss_fwd = _instrument("mae_loss", mae_loss_fwd, lambda pred, inp, mask, *a: _nbytes(pred, inp))
+mae_loss_bwd = _instrument("mae_loss", mae_loss_bwd, lambda pred, inp, mask, *a: 2.0 * _nbytes(pred) + _nbytes(inp))
+infonce_fwd = _instrument("infonce", infonce_fwd, lambda ea, ev, *a: 2.0 * ea.shape[0] * ea.shape[0] * ea.shape[1])
+infonce_bwd = _instrument("infonce", infonce_bwd, lambda N, D, *a: 4.0 * N * N * D)
+mask_argsort = _instrument("mask_argsort", mask_argsort, lambda noise, keep: 16.0 * noise.numel())
+gather_rows = _instrument("gather_rows", gather_rows, lambda x, ids, keep: 2.0 * x.shape[0] * keep * x.shape[2] * x.element_size())
+scatter_add_rows = _instrument("scatter_add", scatter_add_rows, lambda dy, idx, table, alpha: _nbytes(dy) * 3.0)
+seq_mean_fwd = _instrument("seq_mean", seq_mean_fwd, lambda y, out, n_seq, seq_len, D, **k: 2.0 * n_seq * seq_len * D)

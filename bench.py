@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the AVSiam ViT-B/16 pretraining step (BASELINE.json config 2) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl avsiam_b200|reference] [--batch 256]
+                    [--arrangement single_pass|two_pass]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one optimisation step over a per-GPU batch of synthetic AudioSet-shaped samples (randn fbank
+[B,1024,128] + one randn frame [B,3,224,224], 75 % random mask): forward (shared ViT-B/16 encoder over both
+modalities, fusion blocks + MAE decoder + masked-MSE, global-batch InfoNCE), hand-written reverse pass, bucketed
+gradient all-reduce (N>1) and the fused Adam step. `value` = samples/s over all ranks with inputs resident in
+HBM; `e2e` = the same through the public nn.Module call with HOST inputs (pinned H2D copy + loss read-back inside
+the timed region). `--impl reference` times the reference algorithm's CPU restatement (oracle/, "port": the
+reference itself is a pure-Python research dump that cannot travel to the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "AV pretrain samples/sec"
+UNIT = "samples/s"
+TRAIN_GFLOP_PER_SAMPLE = {"single_pass": 242.0, "two_pass": 474.0}   # BASELINE.md §4 (3 x forward)
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}  # B200_PROFILING.md
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return {k: float(d[k]) for k in FALLBACK_PEAKS}, "measured"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+# ----------------------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.sm_max = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_step_fn(arrangement: str, B: int):
+    """The reference algorithm's CPU restatement (oracle/avsiam_oracle.py, pinned to the unmodified reference by
+    tests/golden): literal train-step body of traintest_cavmae_base.py:131-152 minus autocast/GradScaler, fp32."""
+    from oracle import avsiam_oracle as O
+    d = O.VIT_B
+    sd = O.init_state(d, seed=0, skip_heads=True)
+    params = {k: v.requires_grad_(True) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(87)
+    audio = torch.randn(B, d.audio_len, d.mel, generator=g)
+    imgs = torch.randn(B, d.in_chans, d.img, d.img, generator=g)
+    plist = list(params.values())
+    opt1 = torch.optim.Adam(plist, 2e-4, weight_decay=5e-7, betas=(0.95, 0.999))
+    opt2 = torch.optim.Adam(plist, 2e-4, weight_decay=5e-7, betas=(0.95, 0.999))
+    counter = [0]
+
+    def step():
+        counter[0] += 1
+        plan = O.make_mask_plan(B, d, 1234 + counter[0], two_pass=(arrangement == "two_pass"))
+        if arrangement == "single_pass":
+            out = O.forward_single_pass(audio, imgs, params, d, plan, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+            opt1.zero_grad(set_to_none=True)
+            out[0].backward()
+            opt1.step()
+        else:
+            out = O.forward(audio, imgs, params, d, plan, mae_loss_weight=0, contrast_loss_weight=1)
+            opt1.zero_grad(set_to_none=True)
+            out[0].backward()
+            opt1.step()
+            out = O.forward(audio, imgs, params, d, plan, mae_loss_weight=1, contrast_loss_weight=0)
+            opt2.zero_grad(set_to_none=True)
+            out[0].backward()
+            opt2.step()
+        return float(out[0])
+
+    return step
+
+
+def time_cpu(arrangement: str, B: int, steps: int, warmup: int):
+    step = cpu_reference_step_fn(arrangement, B)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = step()
+    dt = time.perf_counter() - t0
+    assert loss == loss, "CPU reference produced NaN"
+    return B * steps / dt, dt / steps
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.cpu_batch
+    cores = torch.get_num_threads()
+    sps, s_per_step = time_cpu(args.arrangement, B, args.steps, args.warmup)
+    sample = (f"{args.steps} steps x batch {B} of the ViT-B/16 {args.arrangement} step (fp32, torch CPU kernels, "
+              f"{cores} threads)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, B, 1),
+        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, per_gpu_batch: int, world: int):
+    return {"workload": f"ViT-B/16 AVSiam pretrain step ({args.arrangement}), 1024x128 fbank + 1x224x224 frame, "
+                        f"mask 0.75, MAE + global-batch InfoNCE, Adam",
+            "arrangement": args.arrangement, "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * world,
+            "parallelism": f"dp{world}", "l2": "inputs (288 MB/step) and activations (>40 GB/step) exceed the 126 MB L2"}
+
+
+# ----------------------------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    import avsiam_b200
+    from avsiam_b200 import B200DDP, CAVMAE_BASE, FusedAdam, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — avsiam_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+
+    torch.manual_seed(0)                      # identical random-init weights on every rank
+    model = CAVMAE_BASE(audio_length=1024, norm_pix_loss=False, modality_specific_depth=23, tr_pos=False,
+                        arrangement=args.arrangement).to(dev)
+    with torch.no_grad():                     # the reference zero-inits these (cav_mae_base.py:312-337); any value works
+        for n in ("mask_token", "decoder_pos_embed_a", "decoder_pos_embed_v", "decoder_modality_a", "decoder_modality_v"):
+            getattr(model, n).normal_(std=0.02)
+    model.direct_grads = True
+    net = B200DDP(model) if world > 1 else model
+    adam_kw = dict(lr=2e-4, weight_decay=5e-7, betas=(0.95, 0.999))      # traintest_cavmae_base.py:64-66
+    opt1 = FusedAdam(model.parameters(), model=model, **adam_kw)
+    opt2 = FusedAdam(model.parameters(), model=model, **adam_kw) if args.arrangement == "two_pass" else None
+
+    torch.manual_seed(87 + rank)              # run_cavmae_pretrain_base.py:113
+    n_host = 2
+    host_a = [torch.randn(B, 1024, 128).pin_memory() for _ in range(n_host)]
+    host_v = [torch.randn(B, 3, 224, 224).pin_memory() for _ in range(n_host)]
+    dev_a = [t.to(dev) for t in host_a]
+    dev_v = [t.to(dev) for t in host_v]
+    h2d_bytes = host_a[0].numel() * 4 + host_v[0].numel() * 4
+
+    def train_step(a, v):
+        if args.arrangement == "single_pass":
+            out = net(a, v, 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+            opt1.zero_grad()
+            out[0].backward()
+            opt1.step()
+        else:                                 # literal two-pass body, traintest_cavmae_base.py:131-152
+            out = net(a, v, 0.75, 0.75, mae_loss_weight=0, contrast_loss_weight=1)
+            opt1.zero_grad()
+            out[0].backward()
+            opt1.step()
+            out = net(a, v, 0.75, 0.75, mae_loss_weight=1, contrast_loss_weight=0)
+            opt2.zero_grad()
+            out[0].backward()
+            opt2.step()
+        return out[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # ---- (1) device-resident inputs: `value`
+    for i in range(args.warmup):
+        train_step(dev_a[i % n_host], dev_v[i % n_host])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ops.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = train_step(dev_a[i % n_host], dev_v[i % n_host])
+    e1.record()
+    barrier()
+    launches = ops.launch_count()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    loss_val = float(loss)
+    if loss_val != loss_val:
+        raise SystemExit("bench.py: loss is NaN")
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- (2) end to end through the public module call with HOST inputs (double-buffered pinned H2D + loss D2H)
+    copy_stream = torch.cuda.Stream()
+    stage_a = [torch.empty_like(dev_a[0]) for _ in range(2)]
+    stage_v = [torch.empty_like(dev_v[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.zeros(args.steps + args.warmup, dtype=torch.float32).pin_memory()
+
+    def prefetch(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            stage_a[s].copy_(host_a[i % n_host], non_blocking=True)
+            stage_v[s].copy_(host_v[i % n_host], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_loop(n, base):
+        prefetch(0)
+        for i in range(n):
+            if i + 1 < n:
+                prefetch(i + 1)
+            s = i % 2
+            torch.cuda.current_stream().wait_event(ready[s])
+            l = train_step(stage_a[s], stage_v[s])
+            consumed[s].record()
+            loss_host[base + i].copy_(l.detach(), non_blocking=True)
+
+    for s in range(2):
+        consumed[s].record()
+    e2e_loop(args.warmup, 0)
+    barrier()
+    e0.record()
+    e2e_loop(args.steps, args.warmup)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    assert bool(torch.isfinite(loss_host).all()), "e2e: non-finite loss"
+
+    # ---- (3) per-family device time of one more step (roofline of the dominant kernel family)
+    peaks, peaks_src = load_peaks()
+    with ops.KernelTimer() as kt:
+        train_step(dev_a[0], dev_v[0])
+    fam = kt.summary()
+    fam_total = sum(f["ms"] for f in fam.values())
+    gemm = fam.get("gemm", {"ms": 0.0, "work": 0.0, "calls": 0})
+    gemm_tflops = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
+    roofline = {
+        "kernel": "avs::gemm_bf16_kernel (tcgen05.mma + TMEM + TMA, all Linear / patch-embed fwd, dgrad, wgrad)",
+        "bound": "tensor", "achieved": gemm_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+        "frac": gemm_tflops / peaks["bf16_tflops_sustained"], "peak_source": f"{peaks_src} (sustained cuBLAS bf16)",
+        "traffic": None, "launches_per_step": gemm["calls"], "ms_per_step": gemm["ms"],
+        "share_of_kernel_time": gemm["ms"] / fam_total if fam_total else None,
+    }
+    families = {k: {"ms": round(v["ms"], 3), "calls": v["calls"],
+                    "rate": (v["work"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None)}
+                for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    step_util = (value / world) * TRAIN_GFLOP_PER_SAMPLE[args.arrangement] * 1e9 / (peaks["bf16_tflops"] * 1e12)
+
+    # ---- (4) CPU baseline (rank 0, N=1 only): bounded sample of the same step on the host cores
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = torch.get_num_threads()
+        sps, _ = time_cpu(args.arrangement, args.cpu_batch, 3, 1)
+        cpu_baseline = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"3 steps x batch {args.cpu_batch} (1 warm-up) of the same ViT-B/16 "
+                                  f"{args.arrangement} step, fp32 torch CPU, oracle/avsiam_oracle.py"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, B, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "tensor_pipe_util_vs_burst_peak": step_util,
+            "train_gflop_per_sample": TRAIN_GFLOP_PER_SAMPLE[args.arrangement],
+            "kernel_families_ms": families,
+            "loss": loss_val,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="avsiam_b200", choices=["avsiam_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE.json config 2: 256)")
+    ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the CPU reference sample (config 1: 2)")
+    ap.add_argument("--arrangement", default="single_pass", choices=["single_pass", "two_pass"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != "reference":
+        args.warmup = 3                       # timing rule: W >= 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

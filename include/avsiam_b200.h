@@ -161,7 +161,10 @@ int avs_infonce_bwd(int N, int D, float temperature, int bidirect, float weight,
  * ---------------------------------------------------------------------------------------------- */
 int avs_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16 /* or NULL */, long long n, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
-                  const float* inv_scale /* or NULL */, const float* found_inf /* or NULL */, void* stream);
+                  const float* inv_scale /* or NULL */, const float* found_inf /* or NULL */,
+                  const uint8_t* active_chunks /* or NULL: one byte per 64 elements, 0 = parameter had no gradient
+                                                  (torch.optim.Adam skips grad-None parameters) */,
+                  void* stream);
 int avs_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 int avs_colsum_bf16(const void* dy, long long ld, float* out_accum, int M, int N, float alpha, void* stream);
 int avs_found_inf(const float* g, long long n, float* flag, void* stream);

@@ -232,7 +232,11 @@ def test_attention_fwd_bwd(n_seq, S, H, hd):
     delta = torch.empty(n_seq, H, S, device=DEV)
     ops.attention_bwd(qkv, out, dout, lse2, delta, dqkv, n_seq, S, H, hd)
     for i, name in enumerate("qkv"):
-        e = rel_err(dqkv[:, i * D:(i + 1) * D], ref_dqkv[:, i * D:(i + 1) * D])
+        got, want = dqkv[:, i * D:(i + 1) * D].float(), ref_dqkv[:, i * D:(i + 1) * D]
+        if S == 1 and name in "qk":   # softmax over one key is constant: dQ = dK = 0 exactly in the reference
+            assert float(got.abs().max()) < 2e-2 * float(dout.float().abs().max()), name
+            continue
+        e = rel_err(got, want)
         assert e < 2e-2, (name, e)   # bf16 P / dS operands in the tensor-core products
 
 

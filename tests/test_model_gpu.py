@@ -1,0 +1,221 @@
+"""Whole-path parity (B200): the drop-in CAVMAE_BASE running on libavsiam_b200.so against
+  (1) the golden fixtures recorded from the UNMODIFIED reference model file (tests/golden, ViT-B/16), and
+  (2) the CPU oracle executed live on identical weights, inputs and supplied mask indices.
+Tolerances are BASELINE.json's: masks bit-exact; losses 2e-2 relative (bf16 mode); per-parameter gradient
+cosine >= 0.999."""
+import dataclasses
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+import avsiam_b200  # noqa: E402
+from avsiam_b200 import CAVMAE_BASE, Dims, FusedAdam  # noqa: E402
+from oracle import avsiam_oracle as O  # noqa: E402
+from oracle.make_golden import synth_inputs  # noqa: E402
+
+DEV = "cuda"
+LOSS_RTOL_BF16 = 2e-2      # BASELINE.json north_star: "within 2e-2 in bf16"
+GRAD_COS_MIN = 0.999       # "per-parameter gradients match at cosine >= 0.999"
+
+
+def make_model(d: O.Dims, arrangement="two_pass", seed=0, **kw):
+    model = CAVMAE_BASE(dims=Dims(**dataclasses.asdict(d)), arrangement=arrangement, **kw)
+    sd = O.with_aliases(O.init_state(d, seed=seed))
+    model.load_state_dict(sd, strict=True)
+    return model.to(DEV), sd
+
+
+def cos(a, b):
+    return float(torch.nn.functional.cosine_similarity(a.flatten().double().cpu(), b.flatten().double().cpu(), dim=0))
+
+
+def check_losses(out, ref, names=("loss", "loss_mae", "loss_mae_a", "loss_mae_v", "loss_c")):
+    for i, n in enumerate(names):
+        r = float(ref[i]) if not isinstance(ref, dict) else ref[n]
+        assert float(out[i]) == pytest.approx(r, rel=LOSS_RTOL_BF16, abs=1e-4), (n, float(out[i]), r)
+
+
+# ------------------------------------------------------------------------------------------------ golden (ViT-B/16)
+@pytest.fixture(scope="module")
+def vitb():
+    model, sd = make_model(O.VIT_B)
+    return model
+
+
+@pytest.fixture(scope="module")
+def golden_cases(golden_dir):
+    return torch.load(os.path.join(golden_dir, "cavmae_base_forward.pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_vitb_against_reference_golden(vitb, golden_cases, idx):
+    c = golden_cases[idx]
+    d = O.VIT_B
+    audio, imgs = synth_inputs(c["B"], d, c["seed_in"])
+    vitb.mask_plan = O.make_mask_plan(c["B"], d, c["seed_mask"], two_pass=True)
+    vitb.zero_grad(set_to_none=True)
+    out = vitb(audio.to(DEV), imgs.to(DEV), 0.75, 0.75, mae_loss_weight=c["mae_w"], contrast_loss_weight=c["c_w"])
+    check_losses(out, c)
+    assert float(out[7]) == pytest.approx(c["c_acc"], abs=0.11)   # argmax hits can flip on near-ties at B<=5
+    if c["mask_a"] is not None:
+        assert torch.equal(out[5].cpu().to(torch.uint8), c["mask_a"])      # bit-exact masks
+        assert torch.equal(out[6].cpu().to(torch.uint8), c["mask_v"])
+    out[0].backward()
+    named = dict(vitb.named_parameters())
+    got = {k for k, p in named.items() if p.grad is not None}
+    want = {k for k in c["grad_norm"] if ".head." not in k}
+    assert got == want, (sorted(got - want)[:5], sorted(want - got)[:5])
+    for k, gref in c["grad_full"].items():
+        assert cos(named[k].grad, gref) >= GRAD_COS_MIN, (k, cos(named[k].grad, gref))
+    bad = []
+    for k in want:
+        n = float(named[k].grad.double().norm())
+        if abs(n - c["grad_norm"][k]) > 0.06 * c["grad_norm"][k] + 1e-6:
+            bad.append((k, n, c["grad_norm"][k]))
+    assert not bad, bad[:8]
+
+
+# ------------------------------------------------------------------------------------------------ live oracle (TINY)
+def run_oracle(fn, audio, imgs, sd, d, plan, **kw):
+    state = {k: v.clone().requires_grad_(True) for k, v in sd.items() if not k.startswith("my_blocks.")}
+    out = fn(audio, imgs, state, d, plan, **kw)
+    out[0].backward()
+    return out, state
+
+
+@pytest.mark.parametrize("arrangement,B,mae_w,c_w", [("two_pass", 4, 1.0, 0.0), ("two_pass", 7, 0.0, 1.0),
+                                                      ("two_pass", 5, 1.0, 0.01), ("single_pass", 6, 1.0, 0.01),
+                                                      ("single_pass", 3, 0.0, 1.0), ("single_pass", 1, 1.0, 0.0)])
+def test_tiny_against_oracle_all_grads(arrangement, B, mae_w, c_w):
+    d = O.TINY
+    model, sd = make_model(d, arrangement)
+    audio, imgs = synth_inputs(B, d, 100 + B)
+    plan = O.make_mask_plan(B, d, 200 + B, two_pass=True)
+    fn = O.forward if arrangement == "two_pass" else O.forward_single_pass
+    ref, state = run_oracle(fn, audio, imgs, sd, d, plan, mae_loss_weight=mae_w, contrast_loss_weight=c_w)
+    model.mask_plan = plan
+    out = model(audio.to(DEV), imgs.to(DEV), 0.75, 0.75, mae_loss_weight=mae_w, contrast_loss_weight=c_w)
+    check_losses(out, ref)
+    if mae_w != 0:
+        assert torch.equal(out[5].cpu(), ref[5]) and torch.equal(out[6].cpu(), ref[6])
+    out[0].backward()
+    named = dict(model.named_parameters())
+    got = {k for k, p in named.items() if p.grad is not None}
+    want = {k for k, v in state.items() if v.grad is not None}
+    assert got == want, (sorted(got - want)[:5], sorted(want - got)[:5])
+    low = [(k, cos(named[k].grad, state[k].grad)) for k in want if float(state[k].grad.norm()) > 1e-9]
+    low = [(k, c) for k, c in low if c < GRAD_COS_MIN]
+    assert not low, low[:8]
+
+
+def test_vitb_single_pass_against_oracle(vitb):
+    """The north-star arrangement at full ViT-B/16 geometry, every parameter's gradient checked."""
+    d = O.VIT_B
+    B = 2
+    sd = O.init_state(d, seed=0, skip_heads=True)
+    audio, imgs = synth_inputs(B, d, 31)
+    plan = O.make_mask_plan(B, d, 32, two_pass=False)
+    ref, state = run_oracle(O.forward_single_pass, audio, imgs, sd, d, plan, mae_loss_weight=1.0,
+                            contrast_loss_weight=0.01)
+    vitb.arrangement = "single_pass"
+    try:
+        vitb.mask_plan = plan
+        vitb.zero_grad(set_to_none=True)
+        out = vitb(audio.to(DEV), imgs.to(DEV), 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+        check_losses(out, ref)
+        assert torch.equal(out[5].cpu(), ref[5]) and torch.equal(out[6].cpu(), ref[6])
+        out[0].backward()
+    finally:
+        vitb.arrangement = "two_pass"
+    named = dict(vitb.named_parameters())
+    want = {k for k, v in state.items() if v.grad is not None}
+    got = {k for k, p in named.items() if p.grad is not None}
+    assert got == want, (sorted(got - want)[:5], sorted(want - got)[:5])
+    low = [(k, cos(named[k].grad, state[k].grad)) for k in want]
+    low = [(k, c) for k, c in low if c < GRAD_COS_MIN]
+    assert not low, low[:8]
+
+
+# ------------------------------------------------------------------------------------------------ API behaviour
+def test_internal_rng_masks_and_eval_mode():
+    d = O.TINY
+    model, _ = make_model(d, "single_pass")
+    audio, imgs = synth_inputs(4, d, 5)
+    with torch.no_grad():
+        out = model(audio.to(DEV), imgs.to(DEV), 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+    assert len(out) == 8 and out[0].dim() == 0 and not out[0].requires_grad
+    ma, mv = out[5], out[6]
+    assert ma.shape == (4, d.Ta) and mv.shape == (4, d.Tv) and ma.dtype == torch.float32
+    assert torch.all(ma.sum(1) == d.Ta - O.len_keep_of(d.Ta, 0.75))
+    assert torch.all(mv.sum(1) == d.Tv - O.len_keep_of(d.Tv, 0.75))
+    out2 = model(audio.to(DEV), imgs.to(DEV), 0.5, 0.5, mae_loss_weight=1.0, contrast_loss_weight=0.0,
+                 mask_mode="tf")   # structured audio mask (cav_mae_base.py:392-439)
+    assert torch.all(out2[5].sum(1) == d.Ta - O.len_keep_of(d.Ta, 0.5))
+    assert float(out2[4]) == 0.0 and float(out2[7]) == 0.0
+
+
+def test_cpu_input_is_rejected():
+    model, _ = make_model(O.TINY)
+    a, v = synth_inputs(2, O.TINY, 1)
+    with pytest.raises(RuntimeError):
+        model(a, v)
+
+
+def test_fused_adam_step_matches_oracle_adam():
+    """Literal train-step body (traintest_cavmae_base.py:131-152 minus autocast/GradScaler) on the fast route:
+    gradients stay in the arena, one fused Adam launch; compared with torch.optim.Adam on the oracle's gradients."""
+    d = O.TINY
+    B = 4
+    model, sd = make_model(d, "single_pass")
+    model.direct_grads = True
+    opt = FusedAdam(model.parameters(), lr=2e-4, weight_decay=5e-7, betas=(0.95, 0.999), model=model)
+    audio, imgs = synth_inputs(B, d, 9)
+    plan = O.make_mask_plan(B, d, 10, two_pass=False)
+    ref, state = run_oracle(O.forward_single_pass, audio, imgs, sd, d, plan, mae_loss_weight=1.0,
+                            contrast_loss_weight=0.01)
+    ref_params = [state[k] for k in state if state[k].grad is not None]
+    ref_opt = torch.optim.Adam(ref_params, lr=2e-4, weight_decay=5e-7, betas=(0.95, 0.999))
+    ref_opt.step()
+    model.mask_plan = plan
+    out = model(audio.to(DEV), imgs.to(DEV), 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+    opt.zero_grad()
+    out[0].backward()
+    opt.step()
+    named = dict(model.named_parameters())
+    # Adam's first step moves every touched weight by ~lr*sign(g): compare the update direction
+    worst = 1.0
+    for k, v in state.items():
+        if v.grad is None or float(v.grad.abs().max()) < 1e-7:
+            continue
+        upd = named[k].detach().cpu() - sd[k]
+        ref_upd = v.detach() - sd[k]
+        big = v.grad.abs() > 10 * v.grad.abs().mean() * 0.1   # ignore the sign-ambiguous near-zero gradients
+        if big.sum() == 0:
+            continue
+        worst = min(worst, cos(upd[big], ref_upd[big]))
+    assert worst > 0.98, worst
+    # the bf16 shadow the next forward consumes was refreshed by the same launch
+    k = "vit_base.blocks.0.attn.qkv.weight"
+    assert torch.equal(model.arena.bf16(k), named[k].detach().to(torch.bfloat16))
+
+
+def test_state_dict_round_trip_keeps_arena_binding():
+    d = O.TINY
+    model, sd = make_model(d)
+    audio, imgs = synth_inputs(2, d, 3)
+    model.mask_plan = O.make_mask_plan(2, d, 4)
+    with torch.no_grad():
+        l0 = float(model(audio.to(DEV), imgs.to(DEV), mae_loss_weight=1.0, contrast_loss_weight=0.0)[0])
+        saved = {k: v.clone() for k, v in model.state_dict().items()}
+        assert set(saved) == set(O.state_dict_keys(d))
+        model.load_state_dict(O.with_aliases(O.init_state(d, seed=1)))
+        l1 = float(model(audio.to(DEV), imgs.to(DEV), mae_loss_weight=1.0, contrast_loss_weight=0.0)[0])
+        model.load_state_dict(saved)
+        l2 = float(model(audio.to(DEV), imgs.to(DEV), mae_loss_weight=1.0, contrast_loss_weight=0.0)[0])
+    assert l0 != l1 and l0 == l2
