@@ -1,22 +1,29 @@
 // Fused (flash-style) multi-head self-attention forward + backward for the short sequences of the AVSiam
 // encoder / MAE decoder (S = 49..708, head_dim 32 or 64).  Reads q,k,v straight out of the packed QKV GEMM
 // output [tokens, 3*D] and writes O as [tokens, D] / dQKV as [tokens, 3*D], so there are no permute copies on
-// either side.  Online softmax in fp32 (exp2 domain), bf16 mma.sync.m16n8k16 tensor-core tiles, never
-// materialises the [S,S] score matrix in HBM.
+// either side, and never materialises the [S,S] score matrix in HBM.
 //
 // Replaces F.scaled_dot_product_attention + the reshape/permute/transpose around it in Attention.forward
 // (cav_mae_base.py:58-77): scale = head_dim^-0.5, no mask, dropout 0.
 //
-// Round-1 note: this kernel uses the legacy mma.sync path (HMMA); attention is ~11 % of the step FLOPs. A
-// tcgen05/TMEM version is the next optimisation.
+// Design (round 1, v2).  At head_dim 32 (the decoder: 54 % of the MAE FLOPs) attention is bound by the softmax
+// exponentials (MUFU, 16/clk/SM), not by the tensor pipe: a 128x128 score block costs 256 tensor cycles on
+// tcgen05 but 1024 MUFU cycles.  So the kernel is organised around keeping the SFU/FMA pipes busy:
+//   * one CTA per (sequence, head); the WHOLE head's K and V (<= 90 KB) are brought into shared memory once with
+//     cp.async (XOR-swizzled 16-byte chunks, conflict-free for ldmatrix) and reused by every query tile — no
+//     per-tile reloads, no barriers inside the main loop;
+//   * 8 warps, each owning 16-query tiles round-robin; scores / probabilities live in registers
+//     (mma.sync.m16n8k16 bf16, fp32 accumulate), B fragments come from ldmatrix.x4 (1 LDSM per 2 MMAs);
+//   * online softmax in the exp2 domain with fp32 statistics.
+// Backward = delta pre-pass + a dK/dV kernel (warp owns 16 keys, the head's Q and dO resident in smem) + a dQ
+// kernel (warp owns 16 queries, K and V resident), each recomputing P from the saved log-sum-exp.
 #include "../../include/avsiam_b200.h"
 #include "common.cuh"
 
 namespace {
 
-constexpr int BM = 64;  // query rows per CTA (4 warps x 16)
-constexpr int BN = 64;  // keys per inner tile
-constexpr int ATT_THREADS = 128;
+constexpr int ATT_WARPS = 8;
+constexpr int ATT_THREADS = ATT_WARPS * 32;
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -24,80 +31,101 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, const void* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n"
-               : "=r"(r0), "=r"(r1)
-               : "r"(smem_u32(p)));
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// A head tile in shared memory: rows of HD bf16 (HD*2 bytes, no padding), 16-byte chunks XOR-swizzled by row so
+// that the 8 row addresses of an ldmatrix 8x8 fetch hit 8 distinct bank groups.
+template <int HD>
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
+  constexpr int CPR = HD / 8;  // 16-byte chunks per row (4 or 8)
+  const int sw = (CPR == 8) ? (row & 7) : ((row >> 1) & 3);
+  return (uint32_t)(row * (HD * 2) + ((chunk ^ sw) << 4));
 }
 
+// Whole-head load: rows [0,S) of a [*, ld] bf16 matrix (HD columns starting at src) -> swizzled smem tile; rows
+// [S, S_pad) are zero-filled.  Asynchronous (cp.async); caller waits + __syncthreads.
 template <int HD>
-struct Tile {
-  static constexpr int LDS = HD + 8;  // padded row pitch (elements): conflict-free fragment loads
-  bf16 d[BM][LDS];
-};
-
-// cooperative load of a [64 x HD] tile; rows >= valid_rows are zero-filled
-template <int HD>
-__device__ __forceinline__ void load_tile(Tile<HD>& t, const bf16* __restrict__ src, long long ld, int valid_rows) {
-  constexpr int VPR = HD / 8;  // 16-byte vectors per row
-  for (int i = threadIdx.x; i < BM * VPR; i += ATT_THREADS) {
-    const int r = i / VPR, c = (i % VPR) * 8;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < valid_rows) v = *reinterpret_cast<const uint4*>(src + (long long)r * ld + c);
-    *reinterpret_cast<uint4*>(&t.d[r][c]) = v;
+__device__ __forceinline__ void load_head_async(uint32_t tile, const bf16* __restrict__ src, long long ld, int S,
+                                                int S_pad) {
+  constexpr int CPR = HD / 8;
+  for (int i = threadIdx.x; i < S_pad * CPR; i += ATT_THREADS) {
+    const int r = i / CPR, c = i % CPR;
+    const uint32_t dst = tile + tile_off<HD>(r, c);
+    if (r < S) cp_async16(dst, src + (long long)r * ld + c * 8);
+    else asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};\n" ::"r"(dst), "r"(0u) : "memory");
   }
 }
 
-// A fragments (16 rows of this warp x HD) from a smem tile
+// A-operand fragments of 16 rows (row0 + lane/4, +8) x HD straight from global memory; rows >= S read as zero.
 template <int HD>
-__device__ __forceinline__ void load_a_frags(uint32_t (&a)[HD / 16][4], const Tile<HD>& t, int warp, int lane) {
-  const int r = warp * 16 + (lane >> 2), c = (lane & 3) * 2;
+__device__ __forceinline__ void load_a_frags_global(uint32_t (&a)[HD / 16][4], const bf16* __restrict__ base,
+                                                    long long ld, int row0, int S, int lane) {
+  const int r0 = row0 + (lane >> 2), r1 = r0 + 8, c = (lane & 3) * 2;
+  const bf16* p0 = base + (long long)r0 * ld + c;
+  const bf16* p1 = base + (long long)r1 * ld + c;
 #pragma unroll
   for (int ks = 0; ks < HD / 16; ++ks) {
-    a[ks][0] = *reinterpret_cast<const uint32_t*>(&t.d[r][ks * 16 + c]);
-    a[ks][1] = *reinterpret_cast<const uint32_t*>(&t.d[r + 8][ks * 16 + c]);
-    a[ks][2] = *reinterpret_cast<const uint32_t*>(&t.d[r][ks * 16 + c + 8]);
-    a[ks][3] = *reinterpret_cast<const uint32_t*>(&t.d[r + 8][ks * 16 + c + 8]);
+    a[ks][0] = r0 < S ? *reinterpret_cast<const uint32_t*>(p0 + ks * 16) : 0u;
+    a[ks][1] = r1 < S ? *reinterpret_cast<const uint32_t*>(p1 + ks * 16) : 0u;
+    a[ks][2] = r0 < S ? *reinterpret_cast<const uint32_t*>(p0 + ks * 16 + 8) : 0u;
+    a[ks][3] = r1 < S ? *reinterpret_cast<const uint32_t*>(p1 + ks * 16 + 8) : 0u;
   }
 }
 
-// acc[nt] (16 x 64 over 8 n-tiles) = A(16 x HD) * T^T, T = [64 x HD] row-major tile ("col-major B")
-template <int HD>
-__device__ __forceinline__ void gemm_a_tT(float (&acc)[8][4], const uint32_t (&a)[HD / 16][4], const Tile<HD>& t,
-                                          int lane) {
+// acc[nt] (16 x 8*NT) = A(16 x HD) * T[row0 .. row0+8*NT)^T     (T rows are the n index: "col-major B")
+template <int HD, int NT>
+__device__ __forceinline__ void gemm_a_tT(float (&acc)[NT][4], const uint32_t (&a)[HD / 16][4], uint32_t tile,
+                                          int row0, int lane) {
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
+  for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
-    const int n = nt * 8 + (lane >> 2), c = (lane & 3) * 2;
+    const int row = row0 + nt * 8 + (lane & 7);
 #pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks) {
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&t.d[n][ks * 16 + c]);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&t.d[n][ks * 16 + c + 8]);
-      mma16816(acc[nt], a[ks], b0, b1);
+    for (int half = 0; half < HD / 32; ++half) {
+      uint32_t b[4];
+      ldsm_x4(b, tile + tile_off<HD>(row, half * 4 + (lane >> 3)));
+      mma16816(acc[nt], a[2 * half], b[0], b[1]);
+      mma16816(acc[nt], a[2 * half + 1], b[2], b[3]);
     }
   }
 }
 
-// out[dn] (16 x HD) += P(16 x 64, packed bf16 A-frags) * T,  T = [64 x HD] row-major (B via ldmatrix.trans)
-template <int HD>
-__device__ __forceinline__ void gemm_p_t(float (&out)[HD / 8][4], const uint32_t (&p)[4][4], const Tile<HD>& t,
+// out[dn] (16 x HD) += P(16 x 16*KK, packed bf16 A-frags) * T[row0 .. row0+16*KK)     (T rows are the k index)
+template <int HD, int KK>
+__device__ __forceinline__ void gemm_p_t(float (&out)[HD / 8][4], const uint32_t (&p)[KK][4], uint32_t tile, int row0,
                                          int lane) {
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
+  for (int kk = 0; kk < KK; ++kk) {
+    const int row = row0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
-    for (int dn = 0; dn < HD / 8; ++dn) {
-      uint32_t b0, b1;
-      ldsm_x2_trans(b0, b1, &t.d[kk * 16 + (lane & 15)][dn * 8]);
-      mma16816(out[dn], p[kk], b0, b1);
+    for (int dp = 0; dp < HD / 16; ++dp) {
+      uint32_t b[4];
+      ldsm_x4_trans(b, tile + tile_off<HD>(row, dp * 2 + (lane >> 4)));
+      mma16816(out[2 * dp], p[kk], b[0], b[1]);
+      mma16816(out[2 * dp + 1], p[kk], b[2], b[3]);
     }
   }
 }
 
-// pack a 16x64 fp32 C-fragment set into bf16 A-fragments (the FA2 register trick)
-__device__ __forceinline__ void pack_c_to_a(uint32_t (&p)[4][4], const float (&s)[8][4]) {
+// pack a 16 x 8*NT fp32 C-fragment set into bf16 A-fragments (the FA2 register trick)
+template <int NT>
+__device__ __forceinline__ void pack_c_to_a(uint32_t (&p)[NT / 2][4], const float (&s)[NT][4]) {
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
+  for (int kk = 0; kk < NT / 2; ++kk) {
     p[kk][0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
     p[kk][1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
     p[kk][2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
@@ -106,100 +134,100 @@ __device__ __forceinline__ void pack_c_to_a(uint32_t (&p)[4][4], const float (&s
 }
 
 struct AttnArgs {
-  const bf16* qkv;   // [rows, ld_qkv]: q | k | v, each D wide, head h at h*HD
-  bf16* out;         // fwd: O [rows, ld_o]
-  float* lse2;       // [n_seq, H, S] log2-domain logsumexp
-  const bf16* dout;  // bwd: dO [rows, ld_o]
+  const bf16* qkv;     // [rows, ld_qkv]: q | k | v, each D wide, head h at h*HD
+  bf16* out;           // fwd: O [rows, ld_o]
+  float* lse2;         // [n_seq, H, S] log2-domain logsumexp
+  const bf16* dout;    // bwd: dO [rows, ld_o]
   const float* delta;  // bwd: [n_seq, H, S]  rowsum(dO * O)
-  bf16* dqkv;        // bwd: [rows, ld_qkv]
+  bf16* dqkv;          // bwd: [rows, ld_qkv]
   long long ld_qkv, ld_o;
-  int S, H, D;
-  float scale_log2;  // scale * log2(e)
+  int S, S_pad, H, D;
+  float scale_log2;    // scale * log2(e)
   float scale;
 };
 
 // ------------------------------------------------ forward ------------------------------------------------
 template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnArgs a) {
-  __shared__ __align__(16) Tile<HD> sQ, sK, sV;
+__global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const AttnArgs a) {
+  constexpr int NT = 8;  // 64 keys per inner block
+  extern __shared__ __align__(128) uint8_t att_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BM, h = blockIdx.y, seq = blockIdx.z;
-  const long long row0 = (long long)seq * a.S;
-  const bf16* qb = a.qkv + row0 * a.ld_qkv + h * HD;
-  const bf16* kb = qb + a.D;
-  const bf16* vb = qb + 2 * a.D;
-
-  load_tile<HD>(sQ, qb + (long long)q0 * a.ld_qkv, a.ld_qkv, min(BM, a.S - q0));
+  const int h = blockIdx.x, seq = blockIdx.y;
+  const int S = a.S, S_pad = a.S_pad;
+  const long long row_base = (long long)seq * S;
+  const bf16* qb = a.qkv + row_base * a.ld_qkv + h * HD;
+  const uint32_t sK = smem_u32(att_smem), sV = sK + S_pad * HD * 2;
+  load_head_async<HD>(sK, qb + a.D, a.ld_qkv, S, S_pad);
+  load_head_async<HD>(sV, qb + 2 * a.D, a.ld_qkv, S, S_pad);
+  cp_async_wait_all();
   __syncthreads();
-  uint32_t qf[HD / 16][4];
-  load_a_frags<HD>(qf, sQ, warp, lane);
 
-  float o[HD / 8][4];
+  bf16* ob = a.out + row_base * a.ld_o + h * HD;
+  float* lp = a.lse2 + ((long long)seq * a.H + h) * S;
+  const int n_qt = (S + 15) >> 4;
+  for (int qt = warp; qt < n_qt; qt += ATT_WARPS) {
+    uint32_t qf[HD / 16][4];
+    load_a_frags_global<HD>(qf, qb, a.ld_qkv, qt * 16, S, lane);
+    float o[HD / 8][4];
 #pragma unroll
-  for (int i = 0; i < HD / 8; ++i)
+    for (int i = 0; i < HD / 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+      for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-  for (int kv0 = 0; kv0 < a.S; kv0 += BN) {
-    __syncthreads();  // previous tile fully consumed
-    const int valid = min(BN, a.S - kv0);
-    load_tile<HD>(sK, kb + (long long)kv0 * a.ld_qkv, a.ld_qkv, valid);
-    load_tile<HD>(sV, vb + (long long)kv0 * a.ld_qkv, a.ld_qkv, valid);
-    __syncthreads();
-    float s[8][4];
-    gemm_a_tT<HD>(s, qf, sK, lane);
-    float mx0 = -INFINITY, mx1 = -INFINITY;
+    for (int kv0 = 0; kv0 < S_pad; kv0 += 8 * NT) {
+      float s[NT][4];
+      gemm_a_tT<HD, NT>(s, qf, sK, kv0, lane);
+      const bool tail = kv0 + 8 * NT > S;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int c = nt * 8 + (lane & 3) * 2;
+      for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool ok = (c + (j & 1)) < valid;
-        s[nt][j] = ok ? s[nt][j] * a.scale_log2 : -INFINITY;
+        for (int j = 0; j < 4; ++j) {
+          s[nt][j] *= a.scale_log2;
+          if (tail && (kv0 + nt * 8 + (lane & 3) * 2 + (j & 1)) >= S) s[nt][j] = -INFINITY;
+        }
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
       }
-      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float nm0 = fmaxf(m0, mx0), nm1 = fmaxf(m1, mx1);
-    const float corr0 = exp2f(m0 - nm0), corr1 = exp2f(m1 - nm1);
-    m0 = nm0; m1 = nm1;
-    float rs0 = 0.f, rs1 = 0.f;
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float nm0 = fmaxf(m0, mx0), nm1 = fmaxf(m1, mx1);
+      const float corr0 = exp2f(m0 - nm0), corr1 = exp2f(m1 - nm1);
+      m0 = nm0; m1 = nm1;
+      float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = exp2f(s[nt][0] - m0); s[nt][1] = exp2f(s[nt][1] - m0);
-      s[nt][2] = exp2f(s[nt][2] - m1); s[nt][3] = exp2f(s[nt][3] - m1);
-      rs0 += s[nt][0] + s[nt][1];
-      rs1 += s[nt][2] + s[nt][3];
+      for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = exp2f(s[nt][0] - m0); s[nt][1] = exp2f(s[nt][1] - m0);
+        s[nt][2] = exp2f(s[nt][2] - m1); s[nt][3] = exp2f(s[nt][3] - m1);
+        rs0 += s[nt][0] + s[nt][1];
+        rs1 += s[nt][2] + s[nt][3];
+      }
+      l0 = l0 * corr0 + rs0;
+      l1 = l1 * corr1 + rs1;
+#pragma unroll
+      for (int dn = 0; dn < HD / 8; ++dn) {
+        o[dn][0] *= corr0; o[dn][1] *= corr0;
+        o[dn][2] *= corr1; o[dn][3] *= corr1;
+      }
+      uint32_t p[NT / 2][4];
+      pack_c_to_a<NT>(p, s);
+      gemm_p_t<HD, NT / 2>(o, p, sV, kv0, lane);
     }
-    l0 = l0 * corr0 + rs0;
-    l1 = l1 * corr1 + rs1;
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    const int r0 = qt * 16 + (lane >> 2), r1 = r0 + 8;
 #pragma unroll
     for (int dn = 0; dn < HD / 8; ++dn) {
-      o[dn][0] *= corr0; o[dn][1] *= corr0;
-      o[dn][2] *= corr1; o[dn][3] *= corr1;
+      const int c = dn * 8 + (lane & 3) * 2;
+      if (r0 < S) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * a.ld_o + c) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
+      if (r1 < S) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * a.ld_o + c) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
     }
-    uint32_t p[4][4];
-    pack_c_to_a(p, s);
-    gemm_p_t<HD>(o, p, sV, lane);
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
-  const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
-  bf16* ob = a.out + row0 * a.ld_o + h * HD;
-#pragma unroll
-  for (int dn = 0; dn < HD / 8; ++dn) {
-    const int c = dn * 8 + (lane & 3) * 2;
-    if (r0 < a.S) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * a.ld_o + c) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
-    if (r1 < a.S) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * a.ld_o + c) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
-  }
-  if ((lane & 3) == 0) {
-    float* lp = a.lse2 + ((long long)seq * a.H + h) * a.S;
-    if (r0 < a.S) lp[r0] = m0 + log2f(l0);
-    if (r1 < a.S) lp[r1] = m1 + log2f(l1);
+    if ((lane & 3) == 0) {
+      if (r0 < S) lp[r0] = m0 + log2f(l0);
+      if (r1 < S) lp[r1] = m1 + log2f(l1);
+    }
   }
 }
 
@@ -223,152 +251,163 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __rest
 }
 
 // ------------------------------------------------ backward: dQ ------------------------------------------------
+// warp owns 16 queries; K and V of the head resident in smem; dQ = sum_blocks dS * K
 template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnArgs a) {
-  __shared__ __align__(16) Tile<HD> sQ, sK, sV;  // sQ is reused for dO
+__global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_dq_kernel(const AttnArgs a) {
+  constexpr int NT = (HD == 64) ? 4 : 8;  // keys per inner block / 8 (register budget: 128/thread)
+  extern __shared__ __align__(128) uint8_t att_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BM, h = blockIdx.y, seq = blockIdx.z;
-  const long long row0 = (long long)seq * a.S;
-  const bf16* qb = a.qkv + row0 * a.ld_qkv + h * HD;
-  const bf16* kb = qb + a.D;
-  const bf16* vb = qb + 2 * a.D;
-  const int vq = min(BM, a.S - q0);
-
-  uint32_t qf[HD / 16][4], dof[HD / 16][4];
-  load_tile<HD>(sQ, qb + (long long)q0 * a.ld_qkv, a.ld_qkv, vq);
+  const int h = blockIdx.x, seq = blockIdx.y;
+  const int S = a.S, S_pad = a.S_pad;
+  const long long row_base = (long long)seq * S;
+  const bf16* qb = a.qkv + row_base * a.ld_qkv + h * HD;
+  const bf16* dob = a.dout + row_base * a.ld_o + h * HD;
+  const uint32_t sK = smem_u32(att_smem), sV = sK + S_pad * HD * 2;
+  load_head_async<HD>(sK, qb + a.D, a.ld_qkv, S, S_pad);
+  load_head_async<HD>(sV, qb + 2 * a.D, a.ld_qkv, S, S_pad);
+  cp_async_wait_all();
   __syncthreads();
-  load_a_frags<HD>(qf, sQ, warp, lane);
-  __syncthreads();
-  load_tile<HD>(sQ, a.dout + (row0 + q0) * a.ld_o + h * HD, a.ld_o, vq);
-  __syncthreads();
-  load_a_frags<HD>(dof, sQ, warp, lane);
 
-  const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
-  const long long sb = ((long long)seq * a.H + h) * a.S;
-  const float lse0 = r0 < a.S ? a.lse2[sb + r0] : 0.f, lse1 = r1 < a.S ? a.lse2[sb + r1] : 0.f;
-  const float dl0 = r0 < a.S ? a.delta[sb + r0] : 0.f, dl1 = r1 < a.S ? a.delta[sb + r1] : 0.f;
+  const long long sb = ((long long)seq * a.H + h) * S;
+  bf16* dqb = a.dqkv + row_base * a.ld_qkv + h * HD;
+  const int n_qt = (S + 15) >> 4;
+  for (int qt = warp; qt < n_qt; qt += ATT_WARPS) {
+    uint32_t qf[HD / 16][4], dof[HD / 16][4];
+    load_a_frags_global<HD>(qf, qb, a.ld_qkv, qt * 16, S, lane);
+    load_a_frags_global<HD>(dof, dob, a.ld_o, qt * 16, S, lane);
+    const int r0 = qt * 16 + (lane >> 2), r1 = r0 + 8;
+    const float lse0 = r0 < S ? a.lse2[sb + r0] : 0.f, lse1 = r1 < S ? a.lse2[sb + r1] : 0.f;
+    const float dl0 = r0 < S ? a.delta[sb + r0] : 0.f, dl1 = r1 < S ? a.delta[sb + r1] : 0.f;
+    float dq[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
 
-  float dq[HD / 8][4];
+    for (int kv0 = 0; kv0 < S_pad; kv0 += 8 * NT) {
+      float s[NT][4], dp[NT][4];
+      gemm_a_tT<HD, NT>(s, qf, sK, kv0, lane);
+      gemm_a_tT<HD, NT>(dp, dof, sV, kv0, lane);
+      const bool tail = kv0 + 8 * NT > S;
 #pragma unroll
-  for (int i = 0; i < HD / 8; ++i)
+      for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
-
-  for (int kv0 = 0; kv0 < a.S; kv0 += BN) {
-    __syncthreads();
-    const int valid = min(BN, a.S - kv0);
-    load_tile<HD>(sK, kb + (long long)kv0 * a.ld_qkv, a.ld_qkv, valid);
-    load_tile<HD>(sV, vb + (long long)kv0 * a.ld_qkv, a.ld_qkv, valid);
-    __syncthreads();
-    float s[8][4], dp[8][4];
-    gemm_a_tT<HD>(s, qf, sK, lane);
-    gemm_a_tT<HD>(dp, dof, sV, lane);
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int c = nt * 8 + (lane & 3) * 2;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool ok = (c + (j & 1)) < valid;
-        const float lse = (j < 2) ? lse0 : lse1, dl = (j < 2) ? dl0 : dl1;
-        const float p = ok ? exp2f(s[nt][j] * a.scale_log2 - lse) : 0.f;
-        s[nt][j] = p * (dp[nt][j] - dl) * a.scale;  // dS * scale
+        for (int j = 0; j < 4; ++j) {
+          const float lse = (j < 2) ? lse0 : lse1, dl = (j < 2) ? dl0 : dl1;
+          float p = exp2f(s[nt][j] * a.scale_log2 - lse);
+          if (tail && (kv0 + nt * 8 + (lane & 3) * 2 + (j & 1)) >= S) p = 0.f;
+          s[nt][j] = p * (dp[nt][j] - dl) * a.scale;  // dS * scale
+        }
       }
+      uint32_t ds[NT / 2][4];
+      pack_c_to_a<NT>(ds, s);
+      gemm_p_t<HD, NT / 2>(dq, ds, sK, kv0, lane);
     }
-    uint32_t ds[4][4];
-    pack_c_to_a(ds, s);
-    gemm_p_t<HD>(dq, ds, sK, lane);
-  }
-  bf16* dqb = a.dqkv + row0 * a.ld_qkv + h * HD;
 #pragma unroll
-  for (int dn = 0; dn < HD / 8; ++dn) {
-    const int c = dn * 8 + (lane & 3) * 2;
-    if (r0 < a.S) *reinterpret_cast<uint32_t*>(dqb + (long long)r0 * a.ld_qkv + c) = pack_bf16x2(dq[dn][0], dq[dn][1]);
-    if (r1 < a.S) *reinterpret_cast<uint32_t*>(dqb + (long long)r1 * a.ld_qkv + c) = pack_bf16x2(dq[dn][2], dq[dn][3]);
+    for (int dn = 0; dn < HD / 8; ++dn) {
+      const int c = dn * 8 + (lane & 3) * 2;
+      if (r0 < S) *reinterpret_cast<uint32_t*>(dqb + (long long)r0 * a.ld_qkv + c) = pack_bf16x2(dq[dn][0], dq[dn][1]);
+      if (r1 < S) *reinterpret_cast<uint32_t*>(dqb + (long long)r1 * a.ld_qkv + c) = pack_bf16x2(dq[dn][2], dq[dn][3]);
+    }
   }
 }
 
 // ------------------------------------------------ backward: dK, dV ------------------------------------------------
+// warp owns 16 keys; Q and dO of the head (+ lse, delta) resident in smem
 template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnArgs a) {
-  __shared__ __align__(16) Tile<HD> sA, sQ, sDO;  // sA stages K then V for fragment extraction
-  __shared__ float s_lse[BM], s_delta[BM];
+__global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_dkv_kernel(const AttnArgs a) {
+  constexpr int NT = (HD == 64) ? 4 : 8;  // queries per inner block / 8
+  extern __shared__ __align__(128) uint8_t att_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k0 = blockIdx.x * BN, h = blockIdx.y, seq = blockIdx.z;
-  const long long row0 = (long long)seq * a.S;
-  const bf16* qb = a.qkv + row0 * a.ld_qkv + h * HD;
-  const bf16* kb = qb + a.D;
-  const bf16* vb = qb + 2 * a.D;
-  const int vk = min(BN, a.S - k0);
+  const int h = blockIdx.x, seq = blockIdx.y;
+  const int S = a.S, S_pad = a.S_pad;
+  const long long row_base = (long long)seq * S;
+  const bf16* qb = a.qkv + row_base * a.ld_qkv + h * HD;
+  const bf16* dob = a.dout + row_base * a.ld_o + h * HD;
+  const uint32_t sQ = smem_u32(att_smem), sDO = sQ + S_pad * HD * 2;
+  float* s_lse = reinterpret_cast<float*>(att_smem + 2 * S_pad * HD * 2);
+  float* s_delta = s_lse + S_pad;
+  load_head_async<HD>(sQ, qb, a.ld_qkv, S, S_pad);
+  load_head_async<HD>(sDO, dob, a.ld_o, S, S_pad);
+  const long long sb = ((long long)seq * a.H + h) * S;
+  for (int i = threadIdx.x; i < S_pad; i += ATT_THREADS) {
+    s_lse[i] = i < S ? a.lse2[sb + i] : INFINITY;  // padded queries: p = exp2(-inf) = 0
+    s_delta[i] = i < S ? a.delta[sb + i] : 0.f;
+  }
+  cp_async_wait_all();
+  __syncthreads();
 
-  uint32_t kf[HD / 16][4], vf[HD / 16][4];
-  load_tile<HD>(sA, kb + (long long)k0 * a.ld_qkv, a.ld_qkv, vk);
-  __syncthreads();
-  load_a_frags<HD>(kf, sA, warp, lane);
-  __syncthreads();
-  load_tile<HD>(sA, vb + (long long)k0 * a.ld_qkv, a.ld_qkv, vk);
-  __syncthreads();
-  load_a_frags<HD>(vf, sA, warp, lane);
-
-  float dk[HD / 8][4], dv[HD / 8][4];
+  bf16* dkb = a.dqkv + row_base * a.ld_qkv + a.D + h * HD;
+  bf16* dvb = a.dqkv + row_base * a.ld_qkv + 2 * a.D + h * HD;
+  const int n_kt = (S + 15) >> 4;
+  for (int kt = warp; kt < n_kt; kt += ATT_WARPS) {
+    uint32_t kf[HD / 16][4], vf[HD / 16][4];
+    load_a_frags_global<HD>(kf, qb + a.D, a.ld_qkv, kt * 16, S, lane);
+    load_a_frags_global<HD>(vf, qb + 2 * a.D, a.ld_qkv, kt * 16, S, lane);
+    float dk[HD / 8][4], dv[HD / 8][4];
 #pragma unroll
-  for (int i = 0; i < HD / 8; ++i)
+    for (int i = 0; i < HD / 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) dk[i][j] = 0.f, dv[i][j] = 0.f;
-  const long long sb = ((long long)seq * a.H + h) * a.S;
+      for (int j = 0; j < 4; ++j) dk[i][j] = 0.f, dv[i][j] = 0.f;
 
-  for (int q0 = 0; q0 < a.S; q0 += BM) {
-    __syncthreads();
-    const int vq = min(BM, a.S - q0);
-    load_tile<HD>(sQ, qb + (long long)q0 * a.ld_qkv, a.ld_qkv, vq);
-    load_tile<HD>(sDO, a.dout + (row0 + q0) * a.ld_o + h * HD, a.ld_o, vq);
-    if (threadIdx.x < BM) {
-      const bool ok = threadIdx.x < vq;
-      s_lse[threadIdx.x] = ok ? a.lse2[sb + q0 + threadIdx.x] : 0.f;
-      s_delta[threadIdx.x] = ok ? a.delta[sb + q0 + threadIdx.x] : 0.f;
+    for (int q0 = 0; q0 < S_pad; q0 += 8 * NT) {
+      float st[NT][4], dpt[NT][4];
+      gemm_a_tT<HD, NT>(st, kf, sQ, q0, lane);     // S^T  [keys x q]
+      gemm_a_tT<HD, NT>(dpt, vf, sDO, q0, lane);   // dP^T [keys x q]
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int q = q0 + nt * 8 + (lane & 3) * 2;
+        const float2 ls = *reinterpret_cast<const float2*>(s_lse + q);
+        const float2 dl = *reinterpret_cast<const float2*>(s_delta + q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float p = exp2f(st[nt][j] * a.scale_log2 - ((j & 1) ? ls.y : ls.x));
+          st[nt][j] = p;
+          dpt[nt][j] = p * (dpt[nt][j] - ((j & 1) ? dl.y : dl.x)) * a.scale;  // dS^T * scale
+        }
+      }
+      uint32_t pt[NT / 2][4];
+      pack_c_to_a<NT>(pt, st);
+      gemm_p_t<HD, NT / 2>(dv, pt, sDO, q0, lane);  // dV += P^T dO
+      pack_c_to_a<NT>(pt, dpt);
+      gemm_p_t<HD, NT / 2>(dk, pt, sQ, q0, lane);   // dK += dS^T Q
     }
-    __syncthreads();
-    float st[8][4], dpt[8][4];
-    gemm_a_tT<HD>(st, kf, sQ, lane);     // S^T  [keys x q]
-    gemm_a_tT<HD>(dpt, vf, sDO, lane);   // dP^T [keys x q]
-    uint32_t pt[4][4];
+    const int r0 = kt * 16 + (lane >> 2), r1 = r0 + 8;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int c = nt * 8 + (lane & 3) * 2;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int q = c + (j & 1);
-        const float p = (q < vq) ? exp2f(st[nt][j] * a.scale_log2 - s_lse[q]) : 0.f;
-        st[nt][j] = p;
-        dpt[nt][j] = p * (dpt[nt][j] - s_delta[q]) * a.scale;  // dS^T * scale
+    for (int dn = 0; dn < HD / 8; ++dn) {
+      const int c = dn * 8 + (lane & 3) * 2;
+      if (r0 < S) {
+        *reinterpret_cast<uint32_t*>(dkb + (long long)r0 * a.ld_qkv + c) = pack_bf16x2(dk[dn][0], dk[dn][1]);
+        *reinterpret_cast<uint32_t*>(dvb + (long long)r0 * a.ld_qkv + c) = pack_bf16x2(dv[dn][0], dv[dn][1]);
+      }
+      if (r1 < S) {
+        *reinterpret_cast<uint32_t*>(dkb + (long long)r1 * a.ld_qkv + c) = pack_bf16x2(dk[dn][2], dk[dn][3]);
+        *reinterpret_cast<uint32_t*>(dvb + (long long)r1 * a.ld_qkv + c) = pack_bf16x2(dv[dn][2], dv[dn][3]);
       }
     }
-    pack_c_to_a(pt, st);
-    gemm_p_t<HD>(dv, pt, sDO, lane);  // dV += P^T dO
-    pack_c_to_a(pt, dpt);
-    gemm_p_t<HD>(dk, pt, sQ, lane);   // dK += dS^T Q
   }
-  const int r0 = k0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
-  bf16* dkb = a.dqkv + row0 * a.ld_qkv + a.D + h * HD;
-  bf16* dvb = a.dqkv + row0 * a.ld_qkv + 2 * a.D + h * HD;
-#pragma unroll
-  for (int dn = 0; dn < HD / 8; ++dn) {
-    const int c = dn * 8 + (lane & 3) * 2;
-    if (r0 < a.S) {
-      *reinterpret_cast<uint32_t*>(dkb + (long long)r0 * a.ld_qkv + c) = pack_bf16x2(dk[dn][0], dk[dn][1]);
-      *reinterpret_cast<uint32_t*>(dvb + (long long)r0 * a.ld_qkv + c) = pack_bf16x2(dv[dn][0], dv[dn][1]);
-    }
-    if (r1 < a.S) {
-      *reinterpret_cast<uint32_t*>(dkb + (long long)r1 * a.ld_qkv + c) = pack_bf16x2(dk[dn][2], dk[dn][3]);
-      *reinterpret_cast<uint32_t*>(dvb + (long long)r1 * a.ld_qkv + c) = pack_bf16x2(dv[dn][2], dv[dn][3]);
-    }
+}
+
+constexpr int ATT_SMEM_MAX = 227 * 1024;
+
+template <typename K>
+int set_smem(K kernel, int bytes, const char* who) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    avs_set_error("%s: cudaFuncSetAttribute(smem=%d): %s", who, bytes, cudaGetErrorString(e));
+    return (int)e;
   }
+  return 0;
 }
 
 int check_common(const void* qkv, long long ld_qkv, long long ld_o, int n_seq, int S, int H, int HD, const char* who) {
   AVS_REQUIRE(qkv != nullptr, "%s: null pointer", who);
   AVS_REQUIRE(HD == 32 || HD == 64, "%s: head_dim must be 32 or 64 (got %d)", who, HD);
-  AVS_REQUIRE(S > 0 && H > 0 && n_seq >= 0 && n_seq <= 65535 && H <= 65535, "%s: bad shape", who);
+  AVS_REQUIRE(S > 0 && H > 0 && n_seq >= 0 && n_seq <= 65535, "%s: bad shape", who);
   AVS_REQUIRE(ld_qkv % 8 == 0 && ld_o % 8 == 0 && ((uintptr_t)qkv & 15) == 0, "%s: 16-byte alignment", who);
+  const int S_pad = (S + 63) & ~63;
+  AVS_REQUIRE(2 * S_pad * HD * 2 + 8 * S_pad <= ATT_SMEM_MAX,
+              "%s: sequence too long for the head-resident kernel (S=%d, head_dim=%d)", who, S, HD);
   return 0;
 }
 
@@ -381,12 +420,19 @@ extern "C" int avs_attention_fwd(const void* qkv, long long ld_qkv, void* out, l
   if (n_seq == 0) return 0;
   AttnArgs a = {};
   a.qkv = (const bf16*)qkv; a.out = (bf16*)out; a.lse2 = lse2;
-  a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.S = S; a.H = H; a.D = H * head_dim;
+  a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.S = S; a.S_pad = (S + 63) & ~63; a.H = H; a.D = H * head_dim;
   a.scale = rsqrtf((float)head_dim);
   a.scale_log2 = a.scale * 1.4426950408889634f;
-  dim3 grid(ceil_div(S, BM), H, n_seq);
-  if (head_dim == 64) attn_fwd_kernel<64><<<grid, ATT_THREADS, 0, (cudaStream_t)stream>>>(a);
-  else attn_fwd_kernel<32><<<grid, ATT_THREADS, 0, (cudaStream_t)stream>>>(a);
+  const int smem = 2 * a.S_pad * head_dim * 2;
+  dim3 grid(H, n_seq);
+  int rc;
+  if (head_dim == 64) {
+    if ((rc = set_smem(attn_fwd_kernel<64>, smem, "avs_attention_fwd"))) return rc;
+    attn_fwd_kernel<64><<<grid, ATT_THREADS, smem, (cudaStream_t)stream>>>(a);
+  } else {
+    if ((rc = set_smem(attn_fwd_kernel<32>, smem, "avs_attention_fwd"))) return rc;
+    attn_fwd_kernel<32><<<grid, ATT_THREADS, smem, (cudaStream_t)stream>>>(a);
+  }
   return avs_check_launch("attn_fwd_kernel");
 }
 
@@ -401,7 +447,7 @@ extern "C" int avs_attention_bwd(const void* qkv, long long ld_qkv, const void* 
   AttnArgs a = {};
   a.qkv = (const bf16*)qkv; a.dout = (const bf16*)dout; a.lse2 = const_cast<float*>(lse2); a.delta = delta;
   a.dqkv = (bf16*)dqkv;
-  a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.S = S; a.H = H; a.D = H * head_dim;
+  a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.S = S; a.S_pad = (S + 63) & ~63; a.H = H; a.D = H * head_dim;
   a.scale = rsqrtf((float)head_dim);
   a.scale_log2 = a.scale * 1.4426950408889634f;
   const long long total = (long long)n_seq * S * H;
@@ -410,15 +456,21 @@ extern "C" int avs_attention_bwd(const void* qkv, long long ld_qkv, const void* 
                                                  total);
   int rc = avs_check_launch("attn_delta_kernel");
   if (rc) return rc;
-  dim3 grid(ceil_div(S, BM), H, n_seq);
+  const int smem_dq = 2 * a.S_pad * head_dim * 2;
+  const int smem_dkv = smem_dq + 2 * a.S_pad * 4;
+  dim3 grid(H, n_seq);
   if (head_dim == 64) {
-    attn_bwd_dkv_kernel<64><<<grid, ATT_THREADS, 0, stream>>>(a);
+    if ((rc = set_smem(attn_bwd_dkv_kernel<64>, smem_dkv, "avs_attention_bwd"))) return rc;
+    if ((rc = set_smem(attn_bwd_dq_kernel<64>, smem_dq, "avs_attention_bwd"))) return rc;
+    attn_bwd_dkv_kernel<64><<<grid, ATT_THREADS, smem_dkv, stream>>>(a);
     if ((rc = avs_check_launch("attn_bwd_dkv_kernel"))) return rc;
-    attn_bwd_dq_kernel<64><<<grid, ATT_THREADS, 0, stream>>>(a);
+    attn_bwd_dq_kernel<64><<<grid, ATT_THREADS, smem_dq, stream>>>(a);
   } else {
-    attn_bwd_dkv_kernel<32><<<grid, ATT_THREADS, 0, stream>>>(a);
+    if ((rc = set_smem(attn_bwd_dkv_kernel<32>, smem_dkv, "avs_attention_bwd"))) return rc;
+    if ((rc = set_smem(attn_bwd_dq_kernel<32>, smem_dq, "avs_attention_bwd"))) return rc;
+    attn_bwd_dkv_kernel<32><<<grid, ATT_THREADS, smem_dkv, stream>>>(a);
     if ((rc = avs_check_launch("attn_bwd_dkv_kernel"))) return rc;
-    attn_bwd_dq_kernel<32><<<grid, ATT_THREADS, 0, stream>>>(a);
+    attn_bwd_dq_kernel<32><<<grid, ATT_THREADS, smem_dq, stream>>>(a);
   }
   return avs_check_launch("attn_bwd_dq_kernel");
 }

@@ -323,8 +323,9 @@ class KernelTimer:
     {family: {"ms": total, "calls": n, "work": algorithmic flops or bytes}}. Off by default: the wrappers
     pay one `is None` test when no timer is installed."""
 
-    def __init__(self):
+    def __init__(self, detail: bool = False):
         self.records = []
+        self.detail = detail     # True: GEMM / attention records are keyed by shape as well
 
     def __enter__(self):
         global _TIMER
@@ -365,7 +366,21 @@ def _work_attn_bwd(qkv, out, dout, lse2, delta, dqkv, n_seq, S, H, hd):
     return 10.0 * n_seq * H * S * S * hd       # 5 S x S x hd products (QK^T, dO V^T, P^T dO, dS^T Q, dS K)
 
 
-def _instrument(family, fn, work_fn):
+def _detail_gemm(a, b, out, M, N, K, **kw):
+    tag = "".join(c for c, f in (("b", kw.get("bias") is not None), ("g", kw.get("gelu")), ("r", kw.get("resid") is not None),
+                                  ("d", kw.get("dgelu_aux") is not None), ("p", kw.get("rowadd") is not None),
+                                  ("A", kw.get("accumulate"))) if f)
+    return f"gemm M={M} N={N} K={K} maj={kw.get('a_major', 0)}{kw.get('b_major', 0)} {tag}"
+
+
+def _detail_attn(name):
+    def f(*a):
+        n_seq, S, H, hd = a[-4:]
+        return f"{name} n_seq={n_seq} S={S} H={H} hd={hd}"
+    return f
+
+
+def _instrument(family, fn, work_fn, detail_fn=None):
     def wrapped(*a, **k):
         t = _TIMER
         if t is None:
@@ -374,16 +389,17 @@ def _instrument(family, fn, work_fn):
         s.record()
         r = fn(*a, **k)
         e.record()
-        t.records.append((family, s, e, work_fn(*a, **k)))
+        key = detail_fn(*a, **k) if (t.detail and detail_fn is not None) else family
+        t.records.append((key, s, e, work_fn(*a, **k)))
         return r
     wrapped.__name__ = fn.__name__
     wrapped.__doc__ = fn.__doc__
     return wrapped
 
 
-gemm = _instrument("gemm", gemm, _work_gemm)
-attention_fwd = _instrument("attention_fwd", attention_fwd, _work_attn_fwd)
-attention_bwd = _instrument("attention_bwd", attention_bwd, _work_attn_bwd)
+gemm = _instrument("gemm", gemm, _work_gemm, _detail_gemm)
+attention_fwd = _instrument("attention_fwd", attention_fwd, _work_attn_fwd, _detail_attn("attention_fwd"))
+attention_bwd = _instrument("attention_bwd", attention_bwd, _work_attn_bwd, _detail_attn("attention_bwd"))
 layernorm_fwd = _instrument("layernorm_fwd", layernorm_fwd,
                             lambda x, gamma, beta, eps, y, mean, rstd, M, D, **k: 4.0 * M * D)
 layernorm_bwd = _instrument("layernorm_bwd", layernorm_bwd,

@@ -265,6 +265,21 @@ def run_gpu_arm(args):
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
 
+    if args.detail:      # developer aid: per-shape device time of one step, printed to stderr
+        with ops.KernelTimer(detail=True) as kt:
+            train_step(dev_a[0], dev_v[0])
+        rows = sorted(kt.summary().items(), key=lambda kv: -kv[1]["ms"])
+        for k, v in rows:
+            rate = v["work"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0
+            print(f"[detail] {v['ms']:9.3f} ms  {v['calls']:4d} calls  {rate:8.1f} T/s  {k}", file=sys.stderr)
+    if args.kernel_only:  # ncu runs: stop after the device-resident timed region
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_per_step,
+                              "gpu_launches": int(launches), "note": "kernel-only run (profiling aid)"}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- (2) end to end through the public module call with HOST inputs (double-buffered pinned H2D + loss D2H)
     copy_stream = torch.cuda.Stream()
     stage_a = [torch.empty_like(dev_a[0]) for _ in range(2)]
@@ -365,6 +380,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the CPU reference sample (config 1: 2)")
     ap.add_argument("--arrangement", default="single_pass", choices=["single_pass", "two_pass"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--detail", action="store_true", help="print a per-shape kernel time table to stderr")
+    ap.add_argument("--kernel-only", action="store_true", help="stop after the device-resident timed region (ncu aid)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3                       # timing rule: W >= 3
