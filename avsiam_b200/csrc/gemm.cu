@@ -1,5 +1,6 @@
 // Host side of the tcgen05 GEMM: TMA descriptor encoding, tile/split-K selection, C-ABI entry.
 #include <cudaTypedefs.h>
+#include <cstring>
 #include <mutex>
 
 #include "../../include/avsiam_b200.h"
@@ -26,7 +27,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // 2-D bf16 row-major tensor [rows, cols] with pitch ld (elements); box = {box_cols (inner), box_rows}, 128B swizzle.
 static int make_tmap_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld,
-                        int box_cols, int box_rows) {
+                        int box_cols, int box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   auto fn = get_encode_fn();
   AVS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   AVS_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA: base pointer must be 16-byte aligned");
@@ -36,28 +37,34 @@ static int make_tmap_2d(CUtensorMap* map, const void* ptr, long long rows, long 
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   AVS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld cols=%lld ld=%lld", (int)r,
               rows, cols, ld);
   return 0;
 }
 
+struct GemmMaps {
+  CUtensorMap a, b, c, in, aux;
+};
+
 template <int AM, int BM, int BN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int grid,
-                       cudaStream_t stream) {
+static int launch_gemm(const GemmMaps& tm, GemmArgs& args, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;  // idempotent; benign race
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<AM, BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
+                                         GEMM_SMEM_LIMIT);
     if (e != cudaSuccess) {
-      avs_set_error("cudaFuncSetAttribute(gemm smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      avs_set_error("cudaFuncSetAttribute(gemm smem=%d): %s", GEMM_SMEM_LIMIT, cudaGetErrorString(e));
       return (int)e;
     }
     attr_set = true;
   }
-  gemm_bf16_kernel<AM, BM, BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, args);
+  const int epw = Cfg::epi_bytes_per_warp(args.tma_epi, args.has_in, args.has_aux_out);
+  args.stages = Cfg::pick_stages(epw);
+  const int smem = Cfg::smem_bytes(args.stages, epw);
+  gemm_bf16_kernel<AM, BM, BN><<<grid, GEMM_THREADS, smem, stream>>>(tm.a, tm.b, tm.c, tm.in, tm.aux, args);
   return avs_check_launch("gemm_bf16_kernel");
 }
 
@@ -95,20 +102,43 @@ extern "C" int avs_gemm_bf16(const void* A, long long lda, int a_major, const vo
   const int kb_per_split = ceil_div(total_kb, split_k);
   split_k = ceil_div(total_kb, kb_per_split);
 
-  CUtensorMap ta, tb;
+  GemmMaps tm;
+  memset(&tm, 0, sizeof(tm));
   int rc;
-  if (a_major == 0) rc = make_tmap_2d(&ta, A, M, K, lda, GEMM_BLOCK_K, GEMM_BLOCK_M);
-  else rc = make_tmap_2d(&ta, A, K, M, lda, 64, GEMM_BLOCK_K);
+  if (a_major == 0) rc = make_tmap_2d(&tm.a, A, M, K, lda, GEMM_BLOCK_K, GEMM_BLOCK_M);
+  else rc = make_tmap_2d(&tm.a, A, K, M, lda, 64, GEMM_BLOCK_K);
   if (rc) return rc;
-  if (b_major == 0) rc = make_tmap_2d(&tb, B, N, K, ldb, GEMM_BLOCK_K, BN);
-  else rc = make_tmap_2d(&tb, B, K, N, ldb, 64, GEMM_BLOCK_K);
+  if (b_major == 0) rc = make_tmap_2d(&tm.b, B, N, K, ldb, GEMM_BLOCK_K, BN);
+  else rc = make_tmap_2d(&tm.b, B, K, N, ldb, 64, GEMM_BLOCK_K);
   if (rc) return rc;
+  // bf16 outputs leave (and the residual / dGELU operand arrives) as [32 x 32] tiles moved by TMA, 64-byte swizzle
+  const bool tma_epi = !out_f32;
+  const void* in_ptr = nullptr;
+  long long in_ld = 0;
+  if (tma_epi) {
+    AVS_REQUIRE(!(epi->resid && (epi->flags & AVS_EPI_DGELU)), "avs_gemm_bf16: resid and DGELU cannot be combined");
+    if ((rc = make_tmap_2d(&tm.c, C, M, N, ldc, GEMM_EPI_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if (epi->flags & AVS_EPI_DGELU) { in_ptr = epi->aux_in; in_ld = epi->ld_aux; }
+    else if (epi->resid) { in_ptr = epi->resid; in_ld = epi->ld_resid; }
+    if (in_ptr && (rc = make_tmap_2d(&tm.in, in_ptr, M, N, in_ld, GEMM_EPI_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B)))
+      return rc;
+    if ((epi->flags & AVS_EPI_GELU) && epi->aux_out &&
+        (rc = make_tmap_2d(&tm.aux, epi->aux_out, M, N, epi->ld_aux, GEMM_EPI_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B)))
+      return rc;
+  } else {
+    AVS_REQUIRE(!epi->resid && !(epi->flags & (AVS_EPI_GELU | AVS_EPI_DGELU)),
+                "avs_gemm_bf16: fp32 outputs support bias / rowadd / alpha only");
+  }
 
   GemmArgs args;
   args.M = M; args.N = N; args.K = K;
   args.C = C; args.ldc = ldc;
   args.split_k = split_k; args.kb_per_split = kb_per_split;
   args.desc_variant = g_desc_variant;
+  args.stages = 0;
+  args.tma_epi = tma_epi ? 1 : 0;
+  args.has_in = in_ptr ? 1 : 0;
+  args.has_aux_out = (tma_epi && (epi->flags & AVS_EPI_GELU) && epi->aux_out) ? 1 : 0;
   args.epi.flags = epi->flags;
   args.epi.alpha = epi->alpha;
   args.epi.bias = epi->bias;
@@ -125,12 +155,12 @@ extern "C" int avs_gemm_bf16(const void* A, long long lda, int a_major, const vo
   const int grid = num_tiles < sms ? num_tiles : sms;
   const int key = a_major * 2 + b_major;
   if (BN == 256) {
-    if (key == 0) return launch_gemm<MAJOR_K, MAJOR_K, 256>(ta, tb, args, grid, stream);
-    if (key == 1) return launch_gemm<MAJOR_K, MAJOR_MN, 256>(ta, tb, args, grid, stream);
-    return launch_gemm<MAJOR_MN, MAJOR_MN, 256>(ta, tb, args, grid, stream);
+    if (key == 0) return launch_gemm<MAJOR_K, MAJOR_K, 256>(tm, args, grid, stream);
+    if (key == 1) return launch_gemm<MAJOR_K, MAJOR_MN, 256>(tm, args, grid, stream);
+    return launch_gemm<MAJOR_MN, MAJOR_MN, 256>(tm, args, grid, stream);
   } else {
-    if (key == 0) return launch_gemm<MAJOR_K, MAJOR_K, 128>(ta, tb, args, grid, stream);
-    if (key == 1) return launch_gemm<MAJOR_K, MAJOR_MN, 128>(ta, tb, args, grid, stream);
-    return launch_gemm<MAJOR_MN, MAJOR_MN, 128>(ta, tb, args, grid, stream);
+    if (key == 0) return launch_gemm<MAJOR_K, MAJOR_K, 128>(tm, args, grid, stream);
+    if (key == 1) return launch_gemm<MAJOR_K, MAJOR_MN, 128>(tm, args, grid, stream);
+    return launch_gemm<MAJOR_MN, MAJOR_MN, 128>(tm, args, grid, stream);
   }
 }

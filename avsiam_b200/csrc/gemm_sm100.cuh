@@ -47,23 +47,42 @@ struct GemmArgs {
   int split_k;          // >=1; >1 requires EPI_OUT_ATOMIC
   int kb_per_split;     // k-blocks (of 64) per split
   int desc_variant;     // debug: 1 swaps LBO/SBO of MN-major descriptors (probe only)
+  int stages;           // smem ring depth (runtime: whatever fits beside the epilogue staging buffers)
+  int tma_epi;          // 1: bf16 C (and aux_out) leave through TMA stores, resid/aux_in arrive through TMA loads
+  int has_in;           // tma_epi: a [M,N] bf16 input tile stream exists (resid or aux_in — never both)
+  int has_aux_out;      // tma_epi: the GELU pre-activation is stored as a second output stream
   GemmEpilogue epi;
 };
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int GEMM_UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int GEMM_EPI_WARPS = 8;  // two warps per TMEM lane quarter, each taking half of the tile's columns
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp0 TMA, warp1 MMA, warps2-9 epilogue
+constexpr int GEMM_MAX_STAGES = 8;
+constexpr int GEMM_EPI_CHUNK = 32;                 // columns per epilogue chunk (one tcgen05.ld 32x32b.x32)
+constexpr int GEMM_EPI_BUF = 32 * GEMM_EPI_CHUNK * 2;  // one [32 rows x 32 cols] bf16 staging tile = 2 KB
+constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 
 template <int BLOCK_N>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : 6;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr int BAR_BYTES = 512;
+  // per epilogue warp: [in x2][out][aux_out] staging tiles (only the ones the launch uses)
+  static __host__ __device__ int epi_bytes_per_warp(int tma_epi, int has_in, int has_aux_out) {
+    return tma_epi ? GEMM_EPI_BUF * (1 + (has_in ? 2 : 0) + (has_aux_out ? 1 : 0)) : 0;
+  }
+  static __host__ int pick_stages(int epi_per_warp) {
+    int s = (GEMM_SMEM_LIMIT - 1024 - BAR_BYTES - GEMM_EPI_WARPS * epi_per_warp) / STAGE_BYTES;
+    return s > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : s;
+  }
+  static __host__ int smem_bytes(int stages, int epi_per_warp) {
+    return stages * STAGE_BYTES + GEMM_EPI_WARPS * epi_per_warp + 1024 + BAR_BYTES;
+  }
 };
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1
@@ -91,22 +110,30 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// byte offset of 16-byte chunk `j` (0..3) of row `r` inside a [32 x 32] bf16 staging tile laid out the way TMA's
+// SWIZZLE_64B expects it (chunk index XOR address bits 7..8) — also conflict-free for one-row-per-lane accesses.
+__device__ __forceinline__ uint32_t epi_tile_off(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
+
 template <int A_MAJOR, int B_MAJOR, int BLOCK_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const GemmArgs args) {
+                 const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_in,
+                 const __grid_constant__ CUtensorMap tma_aux, const GemmArgs args) {
   using Cfg = GemmCfg<BLOCK_N>;
-  constexpr int STAGES = Cfg::STAGES;
+  const int STAGES = args.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full_bar = bars;                 // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const int epi_per_warp = Cfg::epi_bytes_per_warp(args.tma_epi, args.has_in, args.has_aux_out);
+  uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + GEMM_EPI_WARPS * epi_per_warp);
+  uint64_t* full_bar = bars;                               // [MAX_STAGES]
+  uint64_t* empty_bar = bars + GEMM_MAX_STAGES;            // [MAX_STAGES]
+  uint64_t* tfull_bar = bars + 2 * GEMM_MAX_STAGES;        // [2]
+  uint64_t* tempty_bar = bars + 2 * GEMM_MAX_STAGES + 2;   // [2]
+  uint64_t* in_bar = bars + 2 * GEMM_MAX_STAGES + 4;       // [EPI_WARPS][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_MAX_STAGES + 4 + 2 * GEMM_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,6 +146,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (args.tma_epi) {
+      tma_prefetch_desc(&tma_c);
+      if (args.has_in) tma_prefetch_desc(&tma_in);
+      if (args.has_aux_out) tma_prefetch_desc(&tma_aux);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -127,8 +159,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], GEMM_EPI_WARPS);
     }
+    for (int i = 0; i < 2 * GEMM_EPI_WARPS; ++i) mbar_init(&in_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -224,11 +257,40 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
     }
   } else {
-    // ============================ epilogue (4 warps, 32 TMEM lanes each) ============================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ============================ epilogue (8 warps) ============================
+    // warp w may only touch TMEM lanes 32*(w%4)..+32; the two warps sharing a quarter split the tile's columns.
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    constexpr int CH = BLOCK_N / (2 * GEMM_EPI_CHUNK);  // chunks per warp per tile
     const GemmEpilogue& ep = args.epi;
+    uint8_t* my_epi = smem_epi + ew * epi_per_warp;
+    uint8_t* in_buf = my_epi;                                        // [2][2 KB] when has_in
+    uint8_t* out_buf = my_epi + (args.has_in ? 2 * GEMM_EPI_BUF : 0);
+    uint8_t* aux_buf = out_buf + GEMM_EPI_BUF;
+    uint64_t* my_in_bar = in_bar + 2 * ew;
+    const bool tma_epi = args.tma_epi != 0;
+    const bool has_in = tma_epi && args.has_in;
+
+    // flat per-warp chunk sequence q = tile_iteration * CH + chunk; `in` tiles are prefetched two chunks ahead
+    auto issue_in = [&](int q) {
+      const int t = blockIdx.x + (q / CH) * (int)gridDim.x;
+      if (t >= num_tiles) return;
+      const int mn = t / args.split_k;
+      const int m0 = (mn / n_tiles) * GEMM_BLOCK_M;
+      const int n0 = (mn % n_tiles) * BLOCK_N;
+      const int col = n0 + half * (BLOCK_N / 2) + (q % CH) * GEMM_EPI_CHUNK;
+      mbar_arrive_expect_tx(&my_in_bar[q & 1], GEMM_EPI_BUF);
+      tma_load_2d(in_buf + (q & 1) * GEMM_EPI_BUF, &tma_in, &my_in_bar[q & 1], col, m0 + quarter * 32);
+    };
+    if (has_in && lane == 0) {
+      issue_in(0);
+      issue_in(1);
+    }
+
     int acc = 0;
     uint32_t acc_phase = 0;
+    int q = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int ks = t % args.split_k;
       const int mn = t / args.split_k;
@@ -245,114 +307,128 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
       const bool lead_split = (ks == 0);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = 0; c < CH; ++c, ++q) {
+        const int ccol = half * (BLOCK_N / 2) + c * GEMM_EPI_CHUNK;  // column offset inside the tile
         uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + ccol);
         tmem_ld_32x32b_x32(taddr, r);
         tmem_ld_wait();
-        const int nc = n0 + c * 32;
-        if (row_ok && nc < args.N) {
-          float v[32];
+        if (c == CH - 1) {  // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        const int nc = n0 + ccol;
+        const bool col_ok = nc < args.N;
+        const bool full = (nc + 32 <= args.N);
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const bool full = (nc + 32 <= args.N);
-          if (ep.bias != nullptr && lead_split) {
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (ep.bias != nullptr && lead_split && col_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (full || nc + j < args.N) {
-                const float4 b = *reinterpret_cast<const float4*>(ep.bias + nc + j);
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
+          for (int j = 0; j < 32; j += 4) {
+            if (full || nc + j < args.N) {
+              const float4 b = *reinterpret_cast<const float4*>(ep.bias + nc + j);
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
             }
           }
-          if (rowadd_ptr != nullptr && lead_split) {
+        }
+        if (rowadd_ptr != nullptr && lead_split && col_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (full || nc + j < args.N) {
-                const float4 b = *reinterpret_cast<const float4*>(rowadd_ptr + nc + j);
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
+          for (int j = 0; j < 32; j += 4) {
+            if (full || nc + j < args.N) {
+              const float4 b = *reinterpret_cast<const float4*>(rowadd_ptr + nc + j);
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
             }
           }
+        }
+        if (tma_epi) {
+          // ---------------- bf16 outputs: staged in smem, moved by TMA ----------------
+          if (lane == 0) bulk_wait_read0();  // the previous chunk's stores have finished reading the staging tiles
+          __syncwarp();
           if (ep.flags & EPI_GELU) {
-            if (ep.aux_out != nullptr) {
-              bf16* ap = ep.aux_out + (long long)row * ep.ld_aux + nc;
+            if (args.has_aux_out) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (full || nc + j < args.N) {
-                  uint4 o;
-                  o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                  o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                  *reinterpret_cast<uint4*>(ap + j) = o;
-                }
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                *reinterpret_cast<uint4*>(aux_buf + epi_tile_off(lane, j)) = o;
               }
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
           }
-          if (ep.flags & EPI_DGELU) {
-            const bf16* ap = ep.aux_in + (long long)row * ep.ld_aux + nc;
+          uint4 in4[4];
+          if (has_in) {
+            mbar_wait(&my_in_bar[q & 1], (uint32_t)((q >> 1) & 1));
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (full || nc + j < args.N) {
-                const uint4 a = *reinterpret_cast<const uint4*>(ap + j);
-                float2 f;
-                f = unpack_bf16x2(a.x); v[j] *= dgelu_erf(f.x); v[j + 1] *= dgelu_erf(f.y);
-                f = unpack_bf16x2(a.y); v[j + 2] *= dgelu_erf(f.x); v[j + 3] *= dgelu_erf(f.y);
-                f = unpack_bf16x2(a.z); v[j + 4] *= dgelu_erf(f.x); v[j + 5] *= dgelu_erf(f.y);
-                f = unpack_bf16x2(a.w); v[j + 6] *= dgelu_erf(f.x); v[j + 7] *= dgelu_erf(f.y);
-              }
+            for (int j = 0; j < 4; ++j)
+              in4[j] = *reinterpret_cast<const uint4*>(in_buf + (q & 1) * GEMM_EPI_BUF + epi_tile_off(lane, j));
+            __syncwarp();                     // every lane has read its row: the tile may be refilled
+            if (lane == 0) issue_in(q + 2);
+          }
+          if (ep.flags & EPI_DGELU) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 f;
+              f = unpack_bf16x2(in4[j].x); v[8 * j] *= dgelu_erf(f.x); v[8 * j + 1] *= dgelu_erf(f.y);
+              f = unpack_bf16x2(in4[j].y); v[8 * j + 2] *= dgelu_erf(f.x); v[8 * j + 3] *= dgelu_erf(f.y);
+              f = unpack_bf16x2(in4[j].z); v[8 * j + 4] *= dgelu_erf(f.x); v[8 * j + 5] *= dgelu_erf(f.y);
+              f = unpack_bf16x2(in4[j].w); v[8 * j + 6] *= dgelu_erf(f.x); v[8 * j + 7] *= dgelu_erf(f.y);
             }
           }
           if (ep.alpha != 1.0f) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
           }
-          if (ep.resid != nullptr && lead_split) {
-            const bf16* rp = ep.resid + (long long)row * ep.ld_resid + nc;
+          if (has_in && !(ep.flags & EPI_DGELU)) {  // residual add
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (full || nc + j < args.N) {
-                const uint4 a = *reinterpret_cast<const uint4*>(rp + j);
-                float2 f;
-                f = unpack_bf16x2(a.x); v[j] += f.x; v[j + 1] += f.y;
-                f = unpack_bf16x2(a.y); v[j + 2] += f.x; v[j + 3] += f.y;
-                f = unpack_bf16x2(a.z); v[j + 4] += f.x; v[j + 5] += f.y;
-                f = unpack_bf16x2(a.w); v[j + 6] += f.x; v[j + 7] += f.y;
-              }
+            for (int j = 0; j < 4; ++j) {
+              float2 f;
+              f = unpack_bf16x2(in4[j].x); v[8 * j] += f.x; v[8 * j + 1] += f.y;
+              f = unpack_bf16x2(in4[j].y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+              f = unpack_bf16x2(in4[j].z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+              f = unpack_bf16x2(in4[j].w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
             }
           }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            *reinterpret_cast<uint4*>(out_buf + epi_tile_off(lane, j)) = o;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && col_ok && m0 + quarter * 32 < args.M) {  // TMA clips the M / N tails of the box
+            tma_store_2d(&tma_c, out_buf, nc, m0 + quarter * 32);
+            if (args.has_aux_out) tma_store_2d(&tma_aux, aux_buf, nc, m0 + quarter * 32);
+            bulk_commit();
+          }
+        } else if (row_ok && col_ok) {
+          // ---------------- fp32 outputs (wgrad / split-K accumulation): direct stores ----------------
+          if (ep.alpha != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+          }
+          float* cp = reinterpret_cast<float*>(args.C) + (long long)row * args.ldc + nc;
           if (ep.flags & EPI_OUT_ATOMIC) {
-            float* cp = reinterpret_cast<float*>(args.C) + (long long)row * args.ldc + nc;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               if (full || nc + j < args.N) red_add_f32x4(cp + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else if (ep.flags & EPI_OUT_F32) {
-            float* cp = reinterpret_cast<float*>(args.C) + (long long)row * args.ldc + nc;
+          } else {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               if (full || nc + j < args.N)
                 *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            bf16* cp = reinterpret_cast<bf16*>(args.C) + (long long)row * args.ldc + nc;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (full || nc + j < args.N) {
-                uint4 o;
-                o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(cp + j) = o;
-              }
-            }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (tma_epi && lane == 0) bulk_wait0();  // all stores retired before the CTA exits
   }
 
   tc_fence_before();
