@@ -47,7 +47,7 @@ SIGNATURES = {
     "avs_decoder_restore_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "avs_decoder_restore_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "avs_layernorm_fwd": [_P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
-    "avs_layernorm_bwd": [_P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "avs_layernorm_bwd": [_P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "avs_seq_mean_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
     "avs_attention_fwd": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _P],
     "avs_attention_bwd": [_P, _L, _P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _P],

@@ -385,7 +385,8 @@ class CAVMAE_BASE(nn.Module):
                     rows = B * keep
                     dx = torch.empty_like(xin.t)
                     ops.layernorm_bwd(y.g, xin.t, mean, rstd, P.f32(nm + ".weight"), dx, P.grad(nm + ".weight"),
-                                      P.grad(nm + ".bias"), rows, D, seq_len=keep, y_seq_stride=S, y_off=off)
+                                      P.grad(nm + ".bias"), rows, D, seq_len=keep, y_seq_stride=S, y_off=off,
+                                      dbias=xin.take_sink())
                     xin.g = dx
             bwd.touch = ("ast_base.norm_a.", "vit_base.norm.")
             tape.append(bwd)

@@ -91,10 +91,20 @@ extern "C" int avs_gemm_bf16(const void* A, long long lda, int a_major, const vo
   if (split_k <= 0) {  // auto: only meaningful with atomic accumulation
     split_k = 1;
     if (epi->flags & AVS_EPI_OUT_ATOMIC) {
+      // wgrad: few output tiles, very long reduction.  Pick the split that wastes the least of the last wave
+      // (work items = tiles x splits over `sms` persistent CTAs), keeping >= 8 k-blocks per split.
       const int mn = m_tiles * n_tiles;
-      if (mn < 2 * sms) split_k = ceil_div(2 * sms, mn);
-      if (split_k > total_kb / 4) split_k = total_kb / 4;  // keep >= 4 k-blocks per split
-      if (split_k < 1) split_k = 1;
+      const int max_split = total_kb / 8 > 0 ? (total_kb / 8 < 64 ? total_kb / 8 : 64) : 1;
+      double best = -1.0;
+      for (int s = 1; s <= max_split; ++s) {
+        const int kbs = ceil_div(total_kb, s);
+        const int s_eff = ceil_div(total_kb, kbs);
+        const long long items = (long long)mn * s_eff;
+        const long long rounds = (items + sms - 1) / sms;
+        // time ~ rounds x (k-blocks per item + fixed per-item epilogue cost of ~6 k-block equivalents)
+        const double t = (double)rounds * (kbs + 6);
+        if (best < 0 || t < best * 0.995) { best = t; split_k = s_eff; }
+      }
     }
   }
   AVS_REQUIRE(split_k == 1 || (epi->flags & AVS_EPI_OUT_ATOMIC), "avs_gemm_bf16: split_k>1 needs AVS_EPI_OUT_ATOMIC");

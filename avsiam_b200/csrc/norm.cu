@@ -88,97 +88,157 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
   }
 }
 
-template <int NCH>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(
+// Backward.  Thread mapping chosen for memory-level parallelism at low register cost: every thread owns ONE
+// 16-byte chunk (8 columns) of a row, a row is covered by TPR = D/8 consecutive threads ("row group"), a CTA holds
+// RG row groups and each group keeps LNB_R rows in flight.  The per-column accumulators (dgamma, dbeta, and the
+// column sum of the produced dx = bias gradient of the Linear that feeds this residual stream) are therefore
+// 3 x 8 registers per thread instead of 3 x D/32, and x / dy / resid stay packed in bf16 until used.
+constexpr int LNB_R = 2;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  float2 f;
+  f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+}
+
+template <int TPR, int RG>
+__global__ void __launch_bounds__(TPR * RG, (TPR * RG > 192) ? 2 : 3) layernorm_bwd_kernel(
     const bf16* __restrict__ dy, const float* __restrict__ dpool, float pool_scale, const bf16* __restrict__ x,
     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
     const bf16* __restrict__ resid, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-    int M, int D, int S, int x_stride, int x_off, int y_stride, int y_off) {
-  extern __shared__ float sred[];  // [2*D]: dgamma partials, dbeta partials
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nchunks = D / 8;
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sred[i] = 0.f;
-  __syncthreads();
-  float ag[NCH][8], ab[NCH][8];
-#pragma unroll
-  for (int k = 0; k < NCH; ++k)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) ag[k][j] = 0.f, ab[k][j] = 0.f;
+    float* __restrict__ dbias, int M, int S, int x_stride, int x_off, int y_stride, int y_off) {
+  constexpr int NT = TPR * RG, NW = (NT + 31) / 32, D = TPR * 8;
+  constexpr int WPG = (TPR >= 32) ? TPR / 32 : 1;   // warps per row group
+  __shared__ float red[2][LNB_R][2][NW];
+  __shared__ float sacc[3][D];
+  const int t = threadIdx.x, rg = t / TPR, ci = t % TPR, warp = t >> 5, lane = t & 31;
+  for (int i = t; i < 3 * D; i += NT) (&sacc[0][0])[i] = 0.f;
 
-  for (long long r = (long long)blockIdx.x * 8 + warp; r < M; r += (long long)gridDim.x * 8) {
-    const float mean = mean_in[r], rstd = rstd_in[r];
-    const long long yr = map_row(r, S, y_stride, y_off);
-    const long long xr = map_row(r, S, x_stride, x_off);
-    const long long seq = S > 0 ? r / S : 0;
-    float xh[NCH][8], gd[NCH][8];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int ci = lane + 32 * k;
-      if (ci < nchunks) {
-        float xv[8], d[8];
-        load8(x + xr * D + ci * 8, xv);
-        if (dy != nullptr) {
-          load8(dy + yr * D + ci * 8, d);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) d[j] = 0.f;
-        }
-        if (dpool != nullptr) {
-          const float4 p0 = *reinterpret_cast<const float4*>(dpool + seq * D + ci * 8);
-          const float4 p1 = *reinterpret_cast<const float4*>(dpool + seq * D + ci * 8 + 4);
-          d[0] += p0.x * pool_scale; d[1] += p0.y * pool_scale; d[2] += p0.z * pool_scale; d[3] += p0.w * pool_scale;
-          d[4] += p1.x * pool_scale; d[5] += p1.y * pool_scale; d[6] += p1.z * pool_scale; d[7] += p1.w * pool_scale;
-        }
-        const float4 g0 = *reinterpret_cast<const float4*>(gamma + ci * 8);
-        const float4 g1 = *reinterpret_cast<const float4*>(gamma + ci * 8 + 4);
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float h = (xv[j] - mean) * rstd;
-          xh[k][j] = h;
-          ag[k][j] += d[j] * h;
-          ab[k][j] += d[j];
-          const float gdy = g[j] * d[j];
-          gd[k][j] = gdy;
-          s1 += gdy;
-          s2 += gdy * h;
-        }
-      }
-    }
-    const float c1 = warp_sum(s1) / D, c2 = warp_sum(s2) / D;
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int ci = lane + 32 * k;
-      if (ci < nchunks) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (gd[k][j] - c1 - xh[k][j] * c2);
-        if (resid != nullptr) {
-          float rr[8];
-          load8(resid + xr * D + ci * 8, rr);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += rr[j];
-        }
-        store8(dx + xr * D + ci * 8, o);
-      }
-    }
+  float g[8];
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + ci * 8);
+    const float4 g1 = *reinterpret_cast<const float4*>(gamma + ci * 8 + 4);
+    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
   }
+  float ag[8], ab[8], ad[8];
 #pragma unroll
-  for (int k = 0; k < NCH; ++k) {
-    const int ci = lane + 32 * k;
-    if (ci < nchunks) {
+  for (int j = 0; j < 8; ++j) ag[j] = ab[j] = ad[j] = 0.f;
+  const float inv_d = 1.0f / D;
+
+  int it = 0;
+  for (long long base = (long long)blockIdx.x * (RG * LNB_R); base < M; base += (long long)gridDim.x * (RG * LNB_R), ++it) {
+    uint4 xv[LNB_R], dv[LNB_R], rv[LNB_R];
+    float mean[LNB_R], rstd[LNB_R], s1[LNB_R], s2[LNB_R];
+    long long xrow[LNB_R], seq[LNB_R];
+    bool ok[LNB_R];
+#pragma unroll
+    for (int k = 0; k < LNB_R; ++k) {                 // issue every load of the LNB_R rows up front
+      const long long r = base + k * RG + rg;
+      ok[k] = r < M;
+      xv[k] = dv[k] = rv[k] = make_uint4(0, 0, 0, 0);
+      mean[k] = 0.f; rstd[k] = 0.f; xrow[k] = 0; seq[k] = 0;
+      if (ok[k]) {
+        xrow[k] = map_row(r, S, x_stride, x_off);
+        seq[k] = S > 0 ? r / S : 0;
+        xv[k] = *reinterpret_cast<const uint4*>(x + xrow[k] * D + ci * 8);
+        if (dy != nullptr) dv[k] = *reinterpret_cast<const uint4*>(dy + map_row(r, S, y_stride, y_off) * D + ci * 8);
+        if (resid != nullptr) rv[k] = *reinterpret_cast<const uint4*>(resid + xrow[k] * D + ci * 8);
+        mean[k] = mean_in[r];
+        rstd[k] = rstd_in[r];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < LNB_R; ++k) {
+      float xf[8], d[8];
+      unpack8(xv[k], xf);
+      unpack8(dv[k], d);
+      if (dpool != nullptr && ok[k]) {
+        const float4 p0 = *reinterpret_cast<const float4*>(dpool + seq[k] * D + ci * 8);
+        const float4 p1 = *reinterpret_cast<const float4*>(dpool + seq[k] * D + ci * 8 + 4);
+        d[0] += p0.x * pool_scale; d[1] += p0.y * pool_scale; d[2] += p0.z * pool_scale; d[3] += p0.w * pool_scale;
+        d[4] += p1.x * pool_scale; d[5] += p1.y * pool_scale; d[6] += p1.z * pool_scale; d[7] += p1.w * pool_scale;
+      }
+      float a1 = 0.f, a2 = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sred[ci * 8 + j], ag[k][j]);
-        atomicAdd(&sred[D + ci * 8 + j], ab[k][j]);
+        const float h = (xf[j] - mean[k]) * rstd[k];
+        const float gd = g[j] * d[j];
+        ag[j] += d[j] * h;
+        ab[j] += d[j];
+        a1 += gd;
+        a2 += gd * h;
       }
+      s1[k] = a1; s2[k] = a2;
+    }
+    // row reductions over the TPR threads of the group
+    if (TPR >= 32) {
+#pragma unroll
+      for (int k = 0; k < LNB_R; ++k) {
+        s1[k] = warp_sum(s1[k]);
+        s2[k] = warp_sum(s2[k]);
+      }
+      if (WPG > 1) {
+        const int b = it & 1;
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < LNB_R; ++k) { red[b][k][0][warp] = s1[k]; red[b][k][1][warp] = s2[k]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < LNB_R; ++k) {
+          float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+          for (int w = 0; w < WPG; ++w) { t1 += red[b][k][0][rg * WPG + w]; t2 += red[b][k][1][rg * WPG + w]; }
+          s1[k] = t1; s2[k] = t2;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < LNB_R; ++k) {
+#pragma unroll
+        for (int o = TPR / 2; o > 0; o >>= 1) {
+          s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o);
+          s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < LNB_R; ++k) {
+      if (!ok[k]) continue;
+      const float c1 = s1[k] * inv_d, c2 = s2[k] * inv_d;
+      float xf[8], d[8], rr[8], o[8];
+      unpack8(xv[k], xf);
+      unpack8(dv[k], d);
+      unpack8(rv[k], rr);
+      if (dpool != nullptr) {
+        const float4 p0 = *reinterpret_cast<const float4*>(dpool + seq[k] * D + ci * 8);
+        const float4 p1 = *reinterpret_cast<const float4*>(dpool + seq[k] * D + ci * 8 + 4);
+        d[0] += p0.x * pool_scale; d[1] += p0.y * pool_scale; d[2] += p0.z * pool_scale; d[3] += p0.w * pool_scale;
+        d[4] += p1.x * pool_scale; d[5] += p1.y * pool_scale; d[6] += p1.z * pool_scale; d[7] += p1.w * pool_scale;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float h = (xf[j] - mean[k]) * rstd[k];
+        o[j] = rstd[k] * (g[j] * d[j] - c1 - h * c2) + rr[j];
+        ad[j] += o[j];
+      }
+      store8(dx + xrow[k] * D + ci * 8, o);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    atomicAdd(dgamma + i, sred[i]);
-    atomicAdd(dbeta + i, sred[D + i]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sacc[0][ci * 8 + j], ag[j]);
+    atomicAdd(&sacc[1][ci * 8 + j], ab[j]);
+    if (dbias != nullptr) atomicAdd(&sacc[2][ci * 8 + j], ad[j]);
+  }
+  __syncthreads();
+  for (int i = t; i < D; i += NT) {
+    atomicAdd(dgamma + i, sacc[0][i]);
+    atomicAdd(dbeta + i, sacc[1][i]);
+    if (dbias != nullptr) atomicAdd(dbias + i, sacc[2][i]);
   }
 }
 
@@ -208,29 +268,44 @@ extern "C" int avs_layernorm_fwd(const void* x, const float* gamma, const float*
   return avs_check_launch("layernorm_fwd_kernel");
 }
 
+template <int TPR, int RG>
+static void launch_ln_bwd(const void* dy, const float* dpool, float pool_scale, const void* x, const float* mean,
+                          const float* rstd, const float* gamma, const void* resid, void* dx, float* dgamma,
+                          float* dbeta, float* dbias, int M, int seq_len, int x_seq_stride, int x_off,
+                          int y_seq_stride, int y_off, cudaStream_t stream) {
+  const int rows_per_cta = RG * LNB_R;
+  const int ctas_per_sm = (TPR * RG > 192) ? 2 : 3;
+  const int blocks = min(avs_num_sms() * ctas_per_sm, ceil_div(M, rows_per_cta));
+  layernorm_bwd_kernel<TPR, RG><<<blocks, TPR * RG, 0, stream>>>(
+      (const bf16*)dy, dpool, pool_scale, (const bf16*)x, mean, rstd, gamma, (const bf16*)resid, (bf16*)dx, dgamma,
+      dbeta, dbias, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off);
+}
+
 extern "C" int avs_layernorm_bwd(const void* dy, const float* dpool, float pool_scale, const void* x,
                                  const float* mean, const float* rstd, const float* gamma, const void* resid,
-                                 void* dx, float* dgamma, float* dbeta, int M, int D, int seq_len, int x_seq_stride,
-                                 int x_off, int y_seq_stride, int y_off, void* stream_) {
+                                 void* dx, float* dgamma, float* dbeta, float* dbias, int M, int D, int seq_len,
+                                 int x_seq_stride, int x_off, int y_seq_stride, int y_off, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   AVS_REQUIRE(x && mean && rstd && gamma && dx && dgamma && dbeta, "avs_layernorm_bwd: null pointer");
   AVS_REQUIRE(dy != nullptr || dpool != nullptr, "avs_layernorm_bwd: need dy and/or dpool");
   AVS_REQUIRE(dpool == nullptr || seq_len > 0, "avs_layernorm_bwd: dpool needs seq_len");
-  AVS_REQUIRE(D % 8 == 0 && D <= 2048, "avs_layernorm_bwd: D must be a multiple of 8 and <= 2048 (got %d)", D);
+  AVS_REQUIRE(((uintptr_t)gamma & 15) == 0 && (dpool == nullptr || ((uintptr_t)dpool & 15) == 0),
+              "avs_layernorm_bwd: gamma / dpool 16-byte alignment");
   if (M == 0) return 0;
-  const int blocks = min(avs_num_sms() * 2, ceil_div(M, 8));
-  const size_t smem = 2 * (size_t)D * sizeof(float);
-#define LN_BWD(N)                                                                                                  \
-  layernorm_bwd_kernel<N><<<blocks, 256, smem, stream>>>((const bf16*)dy, dpool, pool_scale, (const bf16*)x, mean, \
-                                                         rstd, gamma, (const bf16*)resid, (bf16*)dx, dgamma, dbeta, \
-                                                         M, D, seq_len, x_seq_stride, x_off, y_seq_stride, y_off)
-  switch (ln_nch(D)) {
-    case 1: LN_BWD(1); break;
-    case 2: LN_BWD(2); break;
-    case 3: LN_BWD(3); break;
-    case 4: LN_BWD(4); break;
-    case 5: LN_BWD(5); break;
-    default: LN_BWD(8); break;
+#define LN_BWD(TPR, RG)                                                                                          \
+  launch_ln_bwd<TPR, RG>(dy, dpool, pool_scale, x, mean, rstd, gamma, resid, dx, dgamma, dbeta, dbias, M, seq_len, \
+                         x_seq_stride, x_off, y_seq_stride, y_off, stream)
+  switch (D) {
+    case 64: LN_BWD(8, 32); break;
+    case 128: LN_BWD(16, 16); break;
+    case 256: LN_BWD(32, 8); break;
+    case 512: LN_BWD(64, 4); break;
+    case 768: LN_BWD(96, 2); break;
+    case 1024: LN_BWD(128, 2); break;
+    case 1280: LN_BWD(160, 1); break;
+    default:
+      avs_set_error("avs_layernorm_bwd: unsupported width D=%d (instantiated: 64,128,256,512,768,1024,1280)", D);
+      return -1;
   }
 #undef LN_BWD
   return avs_check_launch("layernorm_bwd_kernel");

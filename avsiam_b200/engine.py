@@ -130,12 +130,23 @@ class Group:
 
 
 class Act:
-    """An activation and (during backward) its gradient."""
-    __slots__ = ("t", "g")
+    """An activation and (during backward) its gradient.
+
+    `bias_sink`: fp32 gradient of the bias that was added when this activation was produced; a consumer whose
+    backward kernel can emit column sums of the gradient it writes (LayerNorm backward) accumulates them there and
+    sets `sink_done`, sparing the producer a separate column-sum pass over the gradient."""
+    __slots__ = ("t", "g", "bias_sink", "sink_done")
 
     def __init__(self, t: torch.Tensor):
         self.t = t
         self.g: Optional[torch.Tensor] = None
+        self.bias_sink: Optional[torch.Tensor] = None
+        self.sink_done = False
+
+    def take_sink(self) -> Optional[torch.Tensor]:
+        if self.bias_sink is not None:
+            self.sink_done = True
+        return self.bias_sink
 
 
 @dataclass
@@ -169,13 +180,15 @@ class Engine:
         return g.view(g.shape[0], -1)
 
     def _linear_bwd(self, dy: torch.Tensor, x_in: torch.Tensor, wname: str, bname: str, M: int, n_out: int, k_in: int,
-                    dx_out: Optional[torch.Tensor], dgelu_aux: Optional[torch.Tensor] = None, alpha: float = 1.0):
+                    dx_out: Optional[torch.Tensor], dgelu_aux: Optional[torch.Tensor] = None, alpha: float = 1.0,
+                    skip_bias: bool = False):
         """dgrad (optional), wgrad and bias-grad of y = x W^T + b. No transposes: see gemm_sm100.cuh."""
         if dx_out is not None:
             ops.gemm(dy, self._w2d(wname), dx_out, M, k_in, n_out, b_major=MAJOR_MN, dgelu_aux=dgelu_aux)
         ops.gemm(dy, x_in, self._g2d(wname), n_out, k_in, M, a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
                  split_k=0, alpha=alpha)
-        ops.colsum(dy, self.P.grad(bname), M, n_out, alpha)
+        if not skip_bias:
+            ops.colsum(dy, self.P.grad(bname), M, n_out, alpha)
 
     # -------------------------------------------------------------------------------------------- patch embed
     def embed(self, tape: Optional[list], audio: torch.Tensor, imgs: torch.Tensor, specs: Sequence[EmbedSpec],
@@ -225,13 +238,13 @@ class Engine:
             ops.layernorm_fwd(x[r0:r1], self.P.f32(f"{pfx}{which}{sfx}.weight"), self.P.f32(f"{pfx}{which}{sfx}.bias"),
                               LN_EPS_BLOCK, y[r0:r1], mean[r0:r1], rstd[r0:r1], g.rows, D)
 
-    def _ln_bwd_groups(self, dy, x, mean, rstd, dx, resid, groups, pfx, which, D):
+    def _ln_bwd_groups(self, dy, x, mean, rstd, dx, resid, groups, pfx, which, D, dbias=None):
         for g in groups:
             sfx = "" if g.mod is None else "_" + g.mod
             r0, r1 = g.row0, g.row0 + g.rows
             ops.layernorm_bwd(dy[r0:r1], x[r0:r1], mean[r0:r1], rstd[r0:r1], self.P.f32(f"{pfx}{which}{sfx}.weight"),
                               dx[r0:r1], self.P.grad(f"{pfx}{which}{sfx}.weight"),
-                              self.P.grad(f"{pfx}{which}{sfx}.bias"), g.rows, D, resid=resid[r0:r1])
+                              self.P.grad(f"{pfx}{which}{sfx}.bias"), g.rows, D, resid=resid[r0:r1], dbias=dbias)
 
     def block(self, tape: Optional[list], xin: Act, groups: Sequence[Group], pfx: str, heads: int) -> Act:
         """Block.forward (cav_mae_base.py:149-193): x += proj(attn(LN1_m x)); x += fc2(gelu(fc1(LN2_m x)))."""
@@ -257,20 +270,24 @@ class Engine:
         ops.gemm(ln2, self._w2d(pfx + "mlp.fc1.weight"), hact, M, Hid, D, bias=self.P.f32(pfx + "mlp.fc1.bias"),
                  gelu=True, aux_out=hpre)
         out = Act(self._empty(M, D))
+        out.bias_sink = self.P.grad(pfx + "mlp.fc2.bias")
         ops.gemm(hact, self._w2d(pfx + "mlp.fc2.weight"), out.t, M, D, Hid, bias=self.P.f32(pfx + "mlp.fc2.bias"),
                  resid=x1)
         if tape is not None:
             def bwd():
                 dx2 = out.g
                 dh = self._empty(M, Hid)
-                self._linear_bwd(dx2, hact, pfx + "mlp.fc2.weight", pfx + "mlp.fc2.bias", M, D, Hid, dh, dgelu_aux=hpre)
+                self._linear_bwd(dx2, hact, pfx + "mlp.fc2.weight", pfx + "mlp.fc2.bias", M, D, Hid, dh, dgelu_aux=hpre,
+                                 skip_bias=out.sink_done)
                 dln2 = self._empty(M, D)
                 self._linear_bwd(dh, ln2, pfx + "mlp.fc1.weight", pfx + "mlp.fc1.bias", M, Hid, D, dln2)
                 del dh
                 dx1 = self._empty(M, D)
-                self._ln_bwd_groups(dln2, x1, mean2, rstd2, dx1, dx2, groups, pfx, "norm2", D)
+                # LN2 backward writes dx1 = d(x1) and its column sums = gradient of proj.bias in the same pass
+                self._ln_bwd_groups(dln2, x1, mean2, rstd2, dx1, dx2, groups, pfx, "norm2", D,
+                                    dbias=self.P.grad(pfx + "attn.proj.bias"))
                 do = dln2  # reuse
-                self._linear_bwd(dx1, o, pfx + "attn.proj.weight", pfx + "attn.proj.bias", M, D, D, do)
+                self._linear_bwd(dx1, o, pfx + "attn.proj.weight", pfx + "attn.proj.bias", M, D, D, do, skip_bias=True)
                 dqkv = self._empty(M, 3 * D)
                 for g, lse in zip(groups, lses):
                     delta = self._empty(g.n_seq, heads, g.S, dtype=F32)
@@ -279,7 +296,7 @@ class Engine:
                 dln1 = do
                 self._linear_bwd(dqkv, ln1, pfx + "attn.qkv.weight", pfx + "attn.qkv.bias", M, 3 * D, D, dln1)
                 dx = self._empty(M, D)
-                self._ln_bwd_groups(dln1, x, mean1, rstd1, dx, dx1, groups, pfx, "norm1", D)
+                self._ln_bwd_groups(dln1, x, mean1, rstd1, dx, dx1, groups, pfx, "norm1", D, dbias=xin.take_sink())
                 xin.g = dx
                 out.g = None
             bwd.touch = (pfx,)
@@ -326,6 +343,7 @@ class Engine:
         if tape is not None:
             def bwd():
                 dx = self._empty(M, D)
+                sink = xin.take_sink()
                 for g, pa, (ystride, yoff) in zip(groups, pooled, maps):
                     r0, r1 = g.row0, g.row0 + g.rows
                     nm = norm_of[g.mod]
@@ -338,7 +356,7 @@ class Engine:
                         continue
                     ops.layernorm_bwd(dy, x[r0:r1], mean[r0:r1], rstd[r0:r1], self.P.f32(nm + ".weight"), dx[r0:r1],
                                       self.P.grad(nm + ".weight"), self.P.grad(nm + ".bias"), g.rows, D, dpool=dpool,
-                                      pool_scale=1.0 / g.S, seq_len=g.S, y_seq_stride=ystride, y_off=yoff)
+                                      pool_scale=1.0 / g.S, seq_len=g.S, y_seq_stride=ystride, y_off=yoff, dbias=sink)
                 xin.g = dx
             bwd.touch = tuple(norm_of[g.mod] + "." for g in groups)
             tape.append(bwd)
@@ -409,6 +427,7 @@ class Engine:
         if tape is not None:
             def bwd_heads():
                 dxdec = self._empty(B * St, Dd)
+                sink = xdec.take_sink()
                 for (off, T, wname, bname, inp, kind, mask, up, y, mean, rstd, pred, Pn, n_masked, geom) in parts:
                     rows = B * T
                     dpred = self._empty(rows, Pn)
@@ -417,7 +436,7 @@ class Engine:
                     self._linear_bwd(dpred, y, wname, bname, rows, Pn, Dd, dy)
                     ops.layernorm_bwd(dy, xdec.t, mean, rstd, P.f32("decoder_norm.weight"), dxdec,
                                       P.grad("decoder_norm.weight"), P.grad("decoder_norm.bias"), rows, Dd, seq_len=T,
-                                      x_seq_stride=St, x_off=off)
+                                      x_seq_stride=St, x_off=off, dbias=sink)
                 xdec.g = dxdec
             bwd_heads.touch = ("decoder_pred_", "decoder_norm.")
             tape.append(bwd_heads)

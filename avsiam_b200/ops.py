@@ -196,7 +196,7 @@ def layernorm_fwd(x, gamma, beta, eps, y, mean, rstd, M, D, seq_len=0, y_seq_str
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, *, resid=None, dpool=None, pool_scale=0.0,
-                  seq_len=0, y_seq_stride=0, y_off=0, x_seq_stride=0, x_off=0):
+                  seq_len=0, y_seq_stride=0, y_off=0, x_seq_stride=0, x_off=0, dbias=None):
     if dy is not None:
         _chk(dy, BF16, "ln_bwd.dy")
     if dpool is not None:
@@ -205,9 +205,11 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, *, resid=No
         _chk(resid, BF16, "ln_bwd.resid")
     _chk(x, BF16, "ln_bwd.x"); _chk(dx, BF16, "ln_bwd.dx")
     _chk(dgamma, F32, "ln_bwd.dgamma"); _chk(dbeta, F32, "ln_bwd.dbeta")
+    if dbias is not None:
+        _chk(dbias, F32, "ln_bwd.dbias")
     _lib.check(_lib.lib().avs_layernorm_bwd(_p(dy), _p(dpool), pool_scale, x.data_ptr(), mean.data_ptr(),
                                             rstd.data_ptr(), gamma.data_ptr(), _p(resid), dx.data_ptr(),
-                                            dgamma.data_ptr(), dbeta.data_ptr(), M, D, seq_len, x_seq_stride, x_off,
+                                            dgamma.data_ptr(), dbeta.data_ptr(), _p(dbias), M, D, seq_len, x_seq_stride, x_off,
                                             y_seq_stride, y_off, _stream()), "avs_layernorm_bwd")
 
 

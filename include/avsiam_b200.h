@@ -115,6 +115,8 @@ int avs_layernorm_fwd(const void* x, const float* gamma, const float* beta, floa
                       void* stream);
 int avs_layernorm_bwd(const void* dy, const float* dpool, float pool_scale, const void* x, const float* mean,
                       const float* rstd, const float* gamma, const void* resid, void* dx, float* dgamma, float* dbeta,
+                      float* dbias /* or NULL: += column sums of the produced dx (bias gradient of the Linear that
+                                      writes this residual stream) */,
                       int M, int D, int seq_len, int x_seq_stride, int x_off, int y_seq_stride, int y_off,
                       void* stream);
 /* out fp32 [n_seq, D] = mean over the seq_len tokens of each sequence (.mean(dim=1), cav_mae_base.py:563-566,729) */

@@ -164,7 +164,8 @@ def test_decoder_restore_fwd_bwd():
 
 
 # ------------------------------------------------------------------------------------------------ LayerNorm
-@pytest.mark.parametrize("M,D,eps", [(177 * 3, 768, 1e-5), (708 * 2, 512, 1e-5), (98, 1280, 1e-6), (40, 64, 1e-5)])
+@pytest.mark.parametrize("M,D,eps", [(177 * 3, 768, 1e-5), (708 * 2, 512, 1e-5), (98, 1280, 1e-6), (40, 64, 1e-5),
+                                     (1001, 128, 1e-5), (5, 1024, 1e-6), (77, 256, 1e-5)])
 def test_layernorm_fwd_bwd(M, D, eps):
     x = rnd(M, D, scale=2.0, dtype=torch.bfloat16)
     gamma, beta = 1 + 0.1 * rnd(D), 0.1 * rnd(D)
@@ -177,10 +178,12 @@ def test_layernorm_fwd_bwd(M, D, eps):
     dy, res = rnd(M, D, dtype=torch.bfloat16), rnd(M, D, dtype=torch.bfloat16)
     ref.backward(dy.float())
     dx = torch.empty_like(x)
-    dg, db = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
-    ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, dg, db, M, D, resid=res)
+    dg, db, dbias = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV), torch.ones(D, device=DEV)
+    ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, dg, db, M, D, resid=res, dbias=dbias)
     assert rel_err(dx, xr.grad + res.float()) < 5e-3
     assert rel_err(dg, gr.grad) < 1e-3 and rel_err(db, br.grad) < 1e-3
+    # column sums of the produced dx (bias gradient of the upstream Linear), accumulated in place
+    assert torch.allclose(dbias, 1.0 + (xr.grad + res.float()).sum(0), rtol=2e-3, atol=2e-2 * math.sqrt(M))
 
 
 def test_layernorm_rowmap_and_pool_grad():
