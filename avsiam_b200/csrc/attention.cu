@@ -231,22 +231,39 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const AttnArgs
   }
 }
 
-// delta[seq,h,t] = sum_d dO * O   — one warp per (token, head)
-__global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
-                                  long long ld_o, int S, int H, int HD, long long total) {
-  const int lane = threadIdx.x & 31;
-  for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total;
-       w += ((long long)gridDim.x * blockDim.x) >> 5) {
-    const long long row = w / H;
-    const int h = (int)(w % H);
+// delta[seq,h,t] = sum_d dO * O.  HBM-bound pre-pass: each thread takes one 16-byte chunk (8 columns) of O and dO,
+// HD/8 adjacent lanes reduce with shuffles; fully coalesced 128-bit loads.
+template <int HD>
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout,
+                                                         float* __restrict__ delta, long long ld_o, int S, int H,
+                                                         long long rows) {
+  constexpr int LPH = HD / 8;                       // lanes per head (4 or 8)
+  const int cpr = H * LPH;                          // 16-byte chunks per row
+  const long long total = rows * cpr;
+  // total is a multiple of LPH and the stride is a multiple of 32, so all lanes of a shuffle group stay together
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((total + 31) & ~31LL);
+       i += (long long)gridDim.x * blockDim.x) {
     float acc = 0.f;
-    for (int c = lane * 2; c < HD; c += 64) {
-      const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + row * ld_o + h * HD + c));
-      const float2 y = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dout + row * ld_o + h * HD + c));
-      acc += x.x * y.x + x.y * y.y;
+    const bool ok = i < total;
+    long long row = 0;
+    int c = 0;
+    if (ok) {
+      row = i / cpr;
+      c = (int)(i % cpr);
+      const uint4 x = *reinterpret_cast<const uint4*>(o + row * ld_o + c * 8);
+      const uint4 y = *reinterpret_cast<const uint4*>(dout + row * ld_o + c * 8);
+      float2 a, b;
+      a = unpack_bf16x2(x.x); b = unpack_bf16x2(y.x); acc += a.x * b.x + a.y * b.y;
+      a = unpack_bf16x2(x.y); b = unpack_bf16x2(y.y); acc += a.x * b.x + a.y * b.y;
+      a = unpack_bf16x2(x.z); b = unpack_bf16x2(y.z); acc += a.x * b.x + a.y * b.y;
+      a = unpack_bf16x2(x.w); b = unpack_bf16x2(y.w); acc += a.x * b.x + a.y * b.y;
     }
-    acc = warp_sum(acc);
-    if (lane == 0) delta[((row / S) * H + h) * S + (row % S)] = acc;
+#pragma unroll
+    for (int off = LPH / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (ok && (c % LPH) == 0) {
+      const int h = c / LPH;
+      delta[((row / S) * H + h) * S + (row % S)] = acc;
+    }
   }
 }
 
@@ -450,10 +467,11 @@ extern "C" int avs_attention_bwd(const void* qkv, long long ld_qkv, const void* 
   a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.S = S; a.S_pad = (S + 63) & ~63; a.H = H; a.D = H * head_dim;
   a.scale = rsqrtf((float)head_dim);
   a.scale_log2 = a.scale * 1.4426950408889634f;
-  const long long total = (long long)n_seq * S * H;
-  const int dblocks = (int)min((long long)avs_num_sms() * 8, ceil_div_ll(total * 32, 256));
-  attn_delta_kernel<<<dblocks, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, ld_o, S, H, head_dim,
-                                                 total);
+  const long long rows = (long long)n_seq * S;
+  const long long chunks = rows * H * (head_dim / 8);
+  const int dblocks = (int)min((long long)avs_num_sms() * 8, ceil_div_ll(chunks, 256));
+  if (head_dim == 64) attn_delta_kernel<64><<<dblocks, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, ld_o, S, H, rows);
+  else attn_delta_kernel<32><<<dblocks, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, ld_o, S, H, rows);
   int rc = avs_check_launch("attn_delta_kernel");
   if (rc) return rc;
   const int smem_dq = 2 * a.S_pad * head_dim * 2;

@@ -48,6 +48,12 @@ struct GemmMaps {
   CUtensorMap a, b, c, in, aux;
 };
 
+int avs_make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_cols,
+                          int box_rows, int swizzle_bytes) {
+  return make_tmap_2d(map, ptr, rows, cols, ld, box_cols, box_rows,
+                      swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 template <int AM, int BM, int BN>
 static int launch_gemm(const GemmMaps& tm, GemmArgs& args, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
