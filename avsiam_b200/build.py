@@ -19,7 +19,7 @@ OBJ_DIR = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v",
-          "--expt-relaxed-constexpr"]
+          "--expt-relaxed-constexpr"] + os.environ.get("AVS_EXTRA_NVCC_FLAGS", "").split()
 
 
 def sources() -> list[str]:

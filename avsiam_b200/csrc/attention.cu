@@ -19,6 +19,7 @@
 // kernel (warp owns 16 queries, K and V resident), each recomputing P from the saved log-sum-exp.
 #include "../../include/avsiam_b200.h"
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -430,6 +431,14 @@ int check_common(const void* qkv, long long ld_qkv, long long ld_o, int n_seq, i
 
 }  // namespace
 
+bool avs_attention_tc_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("AVS_ATTN_TC");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 extern "C" int avs_attention_fwd(const void* qkv, long long ld_qkv, void* out, long long ld_o, float* lse2, int n_seq,
                                  int S, int H, int head_dim, void* stream) {
   if (check_common(qkv, ld_qkv, ld_o, n_seq, S, H, head_dim, "avs_attention_fwd")) return -1;
@@ -474,6 +483,10 @@ extern "C" int avs_attention_bwd(const void* qkv, long long ld_qkv, const void* 
   else attn_delta_kernel<32><<<dblocks, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, ld_o, S, H, rows);
   int rc = avs_check_launch("attn_delta_kernel");
   if (rc) return rc;
+  if (avs_attention_tc_enabled()) {
+    rc = avs_attention_bwd_tc(qkv, ld_qkv, dout, ld_o, lse2, delta, dqkv, n_seq, S, H, head_dim, stream_);
+    if (rc != -2) return rc;
+  }
   const int smem_dq = 2 * a.S_pad * head_dim * 2;
   const int smem_dkv = smem_dq + 2 * a.S_pad * 4;
   dim3 grid(H, n_seq);

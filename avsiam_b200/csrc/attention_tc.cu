@@ -1,0 +1,496 @@
+// tcgen05 / TMEM attention backward for the AVSiam shapes (MAE decoder: S = 708, head_dim 32; encoder / fusion:
+// S <= 256, head_dim 64).  One CTA per (sequence, head) computes dQ, dK and dV in ONE pass (the mma.sync path in
+// attention.cu needs two kernels that each recompute P), with every product on the 5th-generation tensor cores.
+//
+// Replaces the backward of F.scaled_dot_product_attention in Attention.forward (cav_mae_base.py:58-77).
+//
+// Structure (per CTA, 18 warps):
+//   warp 0      loader: streams the 128-key blocks K_j, V_j (double-buffered) into swizzled shared memory
+//   warp 1      one elected thread issues every tcgen05.mma
+//   warps 2-17  "softmax" warps in two ping-pong groups of 8 (one per TMEM buffer): thread = one key row (TMEM
+//               lane), the two warps of a lane quarter split the sub-step's 64 query columns
+// Shared memory: Q and dO of the whole head stay resident (rows of head_dim bf16, SWIZZLE_64B / SWIZZLE_128B so the
+// same bytes serve as K-major operand of S^T = K Q^T and as MN-major operand of dK = dS^T Q), K_j / V_j blocks,
+// the dS^T tile (double-buffered, MN-major A operand of dQ = dS K), log-sum-exp and delta rows.
+// Tensor memory (512 columns, all used):
+//   [0,128)    two 64-column buffers  S^T[kv, q]   (fp32) — overwritten in place by P^T  (bf16 pairs, A operand of dV)
+//   [128,256)  two 64-column buffers  dP^T[kv, q]  (fp32) — overwritten in place by dS^T (bf16 pairs, A operand of dK)
+//   [256, ..)  dK_j, dV_j accumulators (head_dim columns each), then dQ_i for EVERY query block of the head
+// so dQ is accumulated across the key blocks without atomics and without a second pass.
+// Per 64-query sub-step the tensor pipe needs ~320 cycles and the 8192 exponentials 512 MUFU cycles; the MMA warp
+// runs one sub-step ahead (S^T / dP^T of sub-step t+1 are issued before the products that consume P^T / dS^T of
+// sub-step t-1), so the softmax warps — the bound — never wait for the tensor pipe.
+#include "../../include/avsiam_b200.h"
+#include "common.cuh"
+#include <stdlib.h>
+#include <type_traits>
+
+namespace {
+
+constexpr int TCB_GROUP_WARPS = 8;                 // softmax warps per ping-pong group (4 lane quarters x 2 column halves)
+constexpr int TCB_COMPUTE_WARPS = 2 * TCB_GROUP_WARPS;
+constexpr int TCB_THREADS = 64 + 32 * TCB_COMPUTE_WARPS;
+constexpr int DS_TILE_BYTES = 128 * 128 * 2;  // [128 keys][128 queries] bf16 = two SWIZZLE_128B atoms of 64 queries
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// generic shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
+  if constexpr (N == 32) tmem_ld_32x32b_x32(taddr, r);
+  else if constexpr (N == 16) tmem_ld_32x32b_x16(taddr, r);
+  else tmem_ld_32x32b_x8(taddr, r);
+}
+template <int N>
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t (&r)[N]) {
+  if constexpr (N == 16) tmem_st_32x32b_x16(taddr, r);
+  else tmem_st_32x32b_x8(taddr, r);
+}
+
+template <int HD>
+struct TcCfg {
+  static constexpr int ROWB = HD * 2;                    // bytes per row of a Q/K/V/dO tile
+  static constexpr uint32_t LT = (HD == 64) ? 2u : 4u;   // SWIZZLE_128B : SWIZZLE_64B
+  static constexpr int SBO = 8 * ROWB;                   // 8-row group pitch
+  static constexpr int KSTEPS = HD / 16;                 // k-steps of the head_dim contraction
+  static constexpr int BLK_BYTES = 128 * ROWB;           // one 128-row block
+  static constexpr int COL_S = 0, COL_DP = 128, COL_DK = 256, COL_DV = 256 + HD, COL_DQ = 256 + 2 * HD;
+  static constexpr int MAX_NB = (512 - COL_DQ) / HD;     // query blocks whose dQ fits in TMEM: 6 (hd 32) / 2 (hd 64)
+};
+
+// byte offset of 16-byte chunk `chunk` of row `row` in a swizzled [rows][HD] bf16 tile (tile base 1024-aligned)
+template <int HD>
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
+  const int sw = (HD == 64) ? (row & 7) : ((row >> 1) & 3);
+  return (uint32_t)(row * (HD * 2) + ((chunk ^ sw) << 4));
+}
+
+// rows [row0, row0+nrows) of a [*, ld] bf16 matrix (HD columns at src) -> swizzled tile rows [0, nrows);
+// rows at or beyond S are zero-filled.  `tid`/`nthr` = the cooperating threads.
+template <int HD>
+__device__ __forceinline__ void load_rows_async(uint32_t tile, const bf16* __restrict__ src, long long ld, int row0,
+                                                int nrows, int S, int tid, int nthr) {
+  constexpr int CPR = HD / 8;
+  for (int i = tid; i < nrows * CPR; i += nthr) {
+    const int r = i / CPR, c = i % CPR;
+    const uint32_t dst = tile + tile_off<HD>(r, c);
+    if (row0 + r < S) cp_async16(dst, src + (long long)(row0 + r) * ld + c * 8);
+    else st_shared_v4(dst, 0u, 0u, 0u, 0u);
+  }
+}
+
+#ifdef AVS_TC_TRACE
+#define TC_TRACE(slot, idx) do { if (a.trace && blockIdx.x == 0 && blockIdx.y == 0) a.trace[(slot) * 512 + (idx)] = clock64(); } while (0)
+#else
+#define TC_TRACE(slot, idx) do {} while (0)
+#endif
+
+struct TcArgs {
+  long long* trace;   // debug timeline (AVS_TC_TRACE builds only)
+  int exp;            // debug: bitmask of pipeline pieces to skip (timing experiments; results are wrong)
+  const bf16* qkv;
+  const bf16* dout;
+  const float* lse2;
+  const float* delta;
+  bf16* dqkv;
+  long long ld_qkv, ld_o;
+  int S, NB, H, D;
+  float scale, scale_log2;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArgs a) {
+  using C = TcCfg<HD>;
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  const int NB = a.NB, S = a.S;
+  const int S_pad = NB * 128;
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sDO = sQ + NB * C::BLK_BYTES;
+  const uint32_t sK = sDO + NB * C::BLK_BYTES;   // [2]
+  const uint32_t sV = sK + 2 * C::BLK_BYTES;     // [2]
+  const uint32_t sDS = sV + 2 * C::BLK_BYTES;    // [2]
+  uint8_t* tail = smem + 2 * NB * C::BLK_BYTES + 4 * C::BLK_BYTES + 2 * DS_TILE_BYTES;
+  float* s_lse = reinterpret_cast<float*>(tail);
+  float* s_delta = s_lse + S_pad;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + S_pad);
+  uint64_t* kv_full = bars;        // [2] loader -> MMA
+  uint64_t* kv_empty = bars + 2;   // [2] MMA -> loader
+  uint64_t* s_full = bars + 4;     // [2] MMA -> softmax warps: S^T / dP^T of a sub-step are in TMEM
+  uint64_t* p_full = bars + 6;     // [2] softmax warps -> MMA: P^T / dS^T written (TMEM + smem)
+  uint64_t* ds_empty = bars + 8;   // [2] MMA -> softmax warps: dS^T smem tile consumed by the dQ product
+  uint64_t* dkv_full = bars + 10;  // MMA -> softmax warps: dK_j, dV_j complete
+  uint64_t* dkv_empty = bars + 11; // softmax warps -> MMA: dK_j, dV_j read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, seq = blockIdx.y;
+  const long long row_base = (long long)seq * S;
+  const bf16* qb = a.qkv + row_base * a.ld_qkv + h * HD;
+  const bf16* dob = a.dout + row_base * a.ld_o + h * HD;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], TCB_GROUP_WARPS);
+      mbar_init(&ds_empty[i], 1);
+    }
+    mbar_init(dkv_full, 1);
+    mbar_init(dkv_empty, TCB_GROUP_WARPS);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  // whole-head Q, dO, log-sum-exp and delta
+  load_rows_async<HD>(sQ, qb, a.ld_qkv, 0, S_pad, S, threadIdx.x, TCB_THREADS);
+  load_rows_async<HD>(sDO, dob, a.ld_o, 0, S_pad, S, threadIdx.x, TCB_THREADS);
+  {
+    const long long sb = ((long long)seq * a.H + h) * S;
+    for (int i = threadIdx.x; i < S_pad; i += TCB_THREADS) {
+      s_lse[i] = i < S ? a.lse2[sb + i] : INFINITY;  // padded queries: p = exp2(-inf) = 0
+      s_delta[i] = i < S ? a.delta[sb + i] : 0.f;
+    }
+  }
+  cp_async_wait_all();
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int T = NB * NB * 2;  // 64-query sub-steps
+
+  if (warp == 0) {
+    // ============================ loader: K_j, V_j ============================
+    for (int j = 0; j < NB; ++j) {
+      if (j >= 2) mbar_wait(&kv_empty[j & 1], (uint32_t)(((j >> 1) - 1) & 1));
+      load_rows_async<HD>(sK + (j & 1) * C::BLK_BYTES, qb + a.D, a.ld_qkv, j * 128, 128, S, lane, 32);
+      load_rows_async<HD>(sV + (j & 1) * C::BLK_BYTES, qb + 2 * a.D, a.ld_qkv, j * 128, 128, S, lane, 32);
+      cp_async_wait_all();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&kv_full[j & 1]);
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    // One thread issues ~16 MMAs per 64-query sub-step, so its scalar work is kept minimal: every descriptor is a
+    // precomputed 64-bit base plus a 16-byte-unit offset added to the low word, and the (j, i, half) indices are
+    // carried incrementally (no divisions).
+    // The whole warp runs the loop convergently (so descriptors / TMEM addresses live in uniform registers); one
+    // elected lane issues.
+    {
+      constexpr uint32_t ID_S = idesc_bf16(128, 64, 0, 0);    // S^T / dP^T : A, B K-major
+      constexpr uint32_t ID_TS = idesc_bf16(128, HD, 0, 1);   // dV / dK    : A in TMEM, B MN-major
+      constexpr uint32_t ID_DQ = idesc_bf16(128, HD, 1, 1);   // dQ         : A (dS^T tile) and B (K_j) MN-major
+      constexpr uint32_t BLK16 = C::BLK_BYTES >> 4, HALF16 = (64 * C::ROWB) >> 4, K16ROWS = (16 * C::ROWB) >> 4;
+      const uint64_t kK = make_desc(sK, 0, C::SBO, C::LT), kV = make_desc(sV, 0, C::SBO, C::LT);
+      const uint64_t kQ = make_desc(sQ, 0, C::SBO, C::LT), kDO = make_desc(sDO, 0, C::SBO, C::LT);
+      const uint64_t mQ = make_desc(sQ, C::SBO, C::SBO, C::LT), mDO = make_desc(sDO, C::SBO, C::SBO, C::LT);
+      const uint64_t mK = make_desc(sK, C::SBO, C::SBO, C::LT);
+      const uint64_t aDS = make_desc(sDS, 16384, 1024, 2u);
+      // state of the sub-step whose S^T / dP^T are issued now (c*) and of the previous one (p*)
+      int cj = 0, ci = 0, ch = 0;
+      int pj = 0, pi = 0, ph = 0;
+      for (int t = 0; t <= T; ++t) {
+        const uint32_t b = (uint32_t)(t & 1);
+        if (t < T) {
+          if (ci == 0 && ch == 0) {
+            mbar_wait(&kv_full[cj & 1], (uint32_t)((cj >> 1) & 1));
+            tc_fence_after();
+          }
+          const uint32_t kvo = (uint32_t)(cj & 1) * BLK16;
+          const uint32_t qo = (uint32_t)(ci * 2 + ch) * HALF16;
+          if (lane == 0) TC_TRACE(0, t);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k = 0; k < C::KSTEPS; ++k)
+              umma_bf16_ss(tmem + C::COL_S + b * 64, kK + (kvo + 2 * k), kQ + (qo + 2 * k), ID_S, k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < C::KSTEPS; ++k)
+              umma_bf16_ss(tmem + C::COL_DP + b * 64, kV + (kvo + 2 * k), kDO + (qo + 2 * k), ID_S, k > 0 ? 1u : 0u);
+            umma_commit(&s_full[b]);
+          }
+          __syncwarp();
+          if (lane == 0) TC_TRACE(11, t);
+        }
+        if (t >= 1) {
+          const uint32_t pb = b ^ 1u;
+          const int u = t - 1;
+          if (lane == 0) TC_TRACE(1, t);
+          mbar_wait(&p_full[pb], (uint32_t)((u >> 1) & 1));
+          tc_fence_after();
+          if (lane == 0) TC_TRACE(2, t);
+          const bool first = (pi == 0 && ph == 0);
+          if (first && pj > 0) {
+            mbar_wait(dkv_empty, (uint32_t)((pj - 1) & 1));
+            tc_fence_after();
+          }
+          const uint32_t qo = (uint32_t)(pi * 2 + ph) * HALF16;
+          // dV_j += P^T dO_i ,  dK_j += dS^T Q_i   (A: bf16 pairs in TMEM, 8 columns per k-step, written by the
+          // softmax warps over the first 8 of each 16-column chunk of S^T / dP^T)
+          const int n = u >> 1;
+          const uint32_t dso = (uint32_t)(n & 1) * (DS_TILE_BYTES >> 4);
+          const uint32_t kvo = (uint32_t)(pj & 1) * BLK16;
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ts(tmem + C::COL_DV, tmem + C::COL_S + pb * 64 + k * 16,
+                           mDO + (qo + k * K16ROWS), ID_TS, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ts(tmem + C::COL_DK, tmem + C::COL_DP + pb * 64 + k * 16,
+                           mQ + (qo + k * K16ROWS), ID_TS, (first && k == 0) ? 0u : 1u);
+            if (ph == 1) {
+              // dQ_i += dS K_j : A = dS^T tile [128 keys][128 queries] read MN-major (two 64-query atoms 16 KB apart)
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                umma_bf16_ss(tmem + C::COL_DQ + pi * HD, aDS + (dso + k * 128), mK + (kvo + k * K16ROWS), ID_DQ,
+                             (pj > 0 || k > 0) ? 1u : 0u);
+              umma_commit(&ds_empty[n & 1]);
+              if (pi == NB - 1) {
+                umma_commit(dkv_full);
+                umma_commit(&kv_empty[pj & 1]);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) TC_TRACE(12, t);
+        }
+        pj = cj; pi = ci; ph = ch;
+        if (++ch == 2) {
+          ch = 0;
+          if (++ci == NB) {
+            ci = 0;
+            ++cj;
+          }
+        }
+      }
+    }
+  } else {
+    // ============================ softmax warps ============================
+    // Two groups of 8 warps work ping-pong: group g owns TMEM buffer g and therefore every sub-step with
+    // (t & 1) == g, i.e. the query half g of each 128-query block.  While one group waits for its tcgen05.ld /
+    // fence / barrier round trips the other keeps the MUFU pipe busy.
+    const int grp = (warp - 2) >> 3;
+    const int quarter = warp & 3;               // TMEM lane quarter this warp may access
+    const int half = ((warp - 2) & 7) >> 2;     // which 32 of the sub-step's 64 query columns
+    const int row = quarter * 32 + lane;        // key row inside the block == TMEM lane
+    const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
+    bf16* dkb = a.dqkv + row_base * a.ld_qkv + a.D + h * HD;
+    bf16* dvb = a.dqkv + row_base * a.ld_qkv + 2 * a.D + h * HD;
+    bf16* dqb = a.dqkv + row_base * a.ld_qkv + h * HD;
+    constexpr int EC = HD / 2;  // epilogue columns per warp
+
+    auto store_row = [&](bf16* dst, const uint32_t* r, float mul) {
+#pragma unroll
+      for (int c = 0; c < EC; c += 8) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(r[c]) * mul, __uint_as_float(r[c + 1]) * mul);
+        o.y = pack_bf16x2(__uint_as_float(r[c + 2]) * mul, __uint_as_float(r[c + 3]) * mul);
+        o.z = pack_bf16x2(__uint_as_float(r[c + 4]) * mul, __uint_as_float(r[c + 5]) * mul);
+        o.w = pack_bf16x2(__uint_as_float(r[c + 6]) * mul, __uint_as_float(r[c + 7]) * mul);
+        *reinterpret_cast<uint4*>(dst + c) = o;
+      }
+    };
+    // dK_j / dV_j leave through group 0; group 1 only tracks the barrier phase (a waiter may not lag a phase)
+    auto epilogue_dkv = [&](int j) {
+      mbar_wait(dkv_full, (uint32_t)(j & 1));
+      tc_fence_after();
+      if (grp != 0) return;
+      uint32_t rk[EC], rv[EC];
+      tmem_ld_n<EC>(tlane + C::COL_DK + half * EC, rk);
+      tmem_ld_n<EC>(tlane + C::COL_DV + half * EC, rv);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dkv_empty);
+      const int kr = j * 128 + row;
+      if (kr < S) {
+        store_row(dkb + (long long)kr * a.ld_qkv + half * EC, rk, a.scale);
+        store_row(dvb + (long long)kr * a.ld_qkv + half * EC, rv, 1.0f);
+      }
+    };
+
+    const uint32_t s_lse_u = smem_u32(s_lse), s_delta_u = smem_u32(s_delta);
+    const uint32_t tS = tlane + C::COL_S + grp * 64 + half * 32, tDP = tlane + C::COL_DP + grp * 64 + half * 32;
+    auto substep = [&](auto mask_tag, int n, int j, int i) {
+      constexpr bool MASK = decltype(mask_tag)::value;   // last key block: rows at or beyond S contribute nothing
+      const bool tr = (lane == 0 && ((warp - 2) & 7) == 0);
+      if (tr) TC_TRACE(3 + grp * 4, n);
+      if (n >= 2) mbar_wait(&ds_empty[n & 1], (uint32_t)(((n >> 1) - 1) & 1));
+      mbar_wait(&s_full[grp], (uint32_t)(n & 1));
+      tc_fence_after();
+      if (tr) TC_TRACE(4 + grp * 4, n);
+      const bool kv_ok = !MASK || (j * 128 + row) < S;
+      const uint32_t ds = sDS + (n & 1) * DS_TILE_BYTES + grp * 16384 + row * 128;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {      // two chunks of 16 query columns
+        uint32_t sr[16], dr[16];
+        if (!(a.exp & 4)) {
+          tmem_ld_32x32b_x16(tS + cc * 16, sr);
+          tmem_ld_32x32b_x16(tDP + cc * 16, dr);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) sr[c] = dr[c] = 0x3f000000u + lane + c;
+        }
+        const uint32_t qoff = (uint32_t)((i * 128 + grp * 64 + half * 32 + cc * 16) * 4);
+        tmem_ld_wait();
+        if (tr && grp == 0) TC_TRACE(13 + cc * 2, n);
+        uint32_t pw[8], dw[8];
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) {
+          float4 ls = make_float4(1.f, 2.f, 3.f, 4.f), dl = ls;
+          if (!(a.exp & 1)) {
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+                       : "=f"(ls.x), "=f"(ls.y), "=f"(ls.z), "=f"(ls.w) : "r"(s_lse_u + qoff + c * 4));
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+                       : "=f"(dl.x), "=f"(dl.y), "=f"(dl.z), "=f"(dl.w) : "r"(s_delta_u + qoff + c * 4));
+          }
+          float p0 = fmaf(__uint_as_float(sr[c]), a.scale_log2, -ls.x);
+          float p1 = fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -ls.y);
+          float p2 = fmaf(__uint_as_float(sr[c + 2]), a.scale_log2, -ls.z);
+          float p3 = fmaf(__uint_as_float(sr[c + 3]), a.scale_log2, -ls.w);
+          if (!(a.exp & 8)) { p0 = exp2f(p0); p1 = exp2f(p1); p2 = exp2f(p2); p3 = exp2f(p3); }
+          if (MASK && !kv_ok) p0 = p1 = p2 = p3 = 0.f;
+          const float d0 = p0 * (__uint_as_float(dr[c]) - dl.x);
+          const float d1 = p1 * (__uint_as_float(dr[c + 1]) - dl.y);
+          const float d2 = p2 * (__uint_as_float(dr[c + 2]) - dl.z);
+          const float d3 = p3 * (__uint_as_float(dr[c + 3]) - dl.w);
+          pw[c / 2] = pack_bf16x2(p0, p1);
+          pw[c / 2 + 1] = pack_bf16x2(p2, p3);
+          dw[c / 2] = pack_bf16x2(d0, d1);
+          dw[c / 2 + 1] = pack_bf16x2(d2, d3);
+        }
+        if (tr && grp == 0) { asm volatile("" :: "r"(pw[0]), "r"(dw[7]) : "memory"); TC_TRACE(14 + cc * 2, n); }
+        // bf16 pairs overwrite the first 8 columns of this chunk's own 16 fp32 columns: k-step (2*half + cc)
+        if (!(a.exp & 16)) {
+          tmem_st_32x32b_x8(tS + cc * 16, pw);
+          tmem_st_32x32b_x8(tDP + cc * 16, dw);
+        }
+        if (!(a.exp & 2))
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          st_shared_v4(ds + (((half * 4 + cc * 2 + c) ^ (row & 7)) << 4), dw[4 * c], dw[4 * c + 1], dw[4 * c + 2],
+                       dw[4 * c + 3]);
+      }
+      if (tr) TC_TRACE(5 + grp * 4, n);
+      tmem_st_wait();
+      if (!(a.exp & 32)) fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[grp]);
+      if (tr) TC_TRACE(6 + grp * 4, n);
+    };
+    {
+      int n = 0;
+      for (int j = 0; j < NB; ++j) {
+#pragma unroll 1
+        for (int i = 0; i < NB; ++i, ++n) {
+          if (j == NB - 1) substep(std::true_type{}, n, j, i);
+          else substep(std::false_type{}, n, j, i);
+          // dK / dV of the previous key block leave one sub-step late, so the tensor pipe's drain is hidden
+          if (i == 0 && j > 0) epilogue_dkv(j - 1);
+        }
+      }
+    }
+    epilogue_dkv(NB - 1);  // also orders every dQ product before the reads below
+#pragma unroll 1
+    for (int i = grp; i < NB; i += 2) {
+      uint32_t rq[EC];
+      tmem_ld_n<EC>(tlane + C::COL_DQ + i * HD + half * EC, rq);
+      tmem_ld_wait();
+      const int qr = i * 128 + row;
+      if (qr < S) store_row(dqb + (long long)qr * a.ld_qkv + half * EC, rq, a.scale);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int HD>
+int launch_bwd(const TcArgs& a, int n_seq, cudaStream_t stream) {
+  using C = TcCfg<HD>;
+  const int S_pad = a.NB * 128;
+  const int smem = 1024 + 2 * a.NB * C::BLK_BYTES + 4 * C::BLK_BYTES + 2 * DS_TILE_BYTES + 2 * S_pad * 4 + 128;
+  cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) {
+    avs_set_error("avs_attention_bwd(tc): cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+    return (int)e;
+  }
+  dim3 grid(a.H, n_seq);
+  attn_bwd_tc_kernel<HD><<<grid, TCB_THREADS, smem, stream>>>(a);
+  return avs_check_launch("attn_bwd_tc_kernel");
+}
+
+long long* g_tc_trace = nullptr;
+
+}  // namespace
+
+extern "C" void avs_debug_set_tc_trace(long long* p) { g_tc_trace = p; }
+
+// Returns -2 when the shape is outside what the TMEM budget covers (the caller then uses the mma.sync kernels of
+// attention.cu — both are CUDA paths of this library).  `delta` must already hold rowsum(dO * O).
+int avs_attention_bwd_tc(const void* qkv, long long ld_qkv, const void* dout, long long ld_o, const float* lse2,
+                         const float* delta, void* dqkv, int n_seq, int S, int H, int head_dim, void* stream) {
+  if (head_dim != 32 && head_dim != 64) return -2;
+  const int NB = (S + 127) / 128;
+  if (NB > (head_dim == 32 ? TcCfg<32>::MAX_NB : TcCfg<64>::MAX_NB)) return -2;
+  TcArgs a = {};
+  a.trace = g_tc_trace;
+  { const char* e = getenv("AVS_TC_EXP"); a.exp = e ? atoi(e) : 0; }
+  a.qkv = (const bf16*)qkv; a.dout = (const bf16*)dout; a.lse2 = lse2; a.delta = delta; a.dqkv = (bf16*)dqkv;
+  a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.S = S; a.NB = NB; a.H = H; a.D = H * head_dim;
+  a.scale = rsqrtf((float)head_dim);
+  a.scale_log2 = a.scale * 1.4426950408889634f;
+  return head_dim == 64 ? launch_bwd<64>(a, n_seq, (cudaStream_t)stream) : launch_bwd<32>(a, n_seq, (cudaStream_t)stream);
+}

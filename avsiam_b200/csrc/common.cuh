@@ -29,10 +29,11 @@ int avs_num_sms();
 // 2-D bf16 row-major tensor map [rows, cols] (pitch ld elements), box {box_cols, box_rows}; swizzle_bytes in {64,128}
 int avs_make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_cols,
                           int box_rows, int swizzle_bytes);
-// tcgen05 forward attention (attention_tc.cu); returns -2 when the shape is not covered (caller falls back to the
-// mma.sync kernel in attention.cu — both are CUDA paths of this library)
-int avs_attention_fwd_tc(const void* qkv, long long ld_qkv, void* out, long long ld_o, float* lse2, int n_seq, int S,
-                         int H, int head_dim, void* stream);
+// tcgen05 attention (attention_tc.cu); each returns -2 when the shape is not covered (the caller then uses the
+// mma.sync kernels in attention.cu — both are CUDA paths of this library)
+int avs_attention_bwd_tc(const void* qkv, long long ld_qkv, const void* dout, long long ld_o, const float* lse2,
+                         const float* delta, void* dqkv, int n_seq, int S, int H, int head_dim, void* stream);
+bool avs_attention_tc_enabled();  // AVS_ATTN_TC=0 in the environment selects the mma.sync kernels (A/B timing)
 
 // ---------------------------------------------------------------------------------------------
 // Device PTX helpers

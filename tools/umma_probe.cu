@@ -1,0 +1,223 @@
+// Microbenchmark: how long do chains of small tcgen05.mma instructions take?  (design input for attention_tc.cu)
+// One CTA per SM; one thread issues `reps` rounds of a pattern of MMAs (M=128, N, K=16, bf16), either all into the
+// same TMEM accumulator (dependent chain) or round-robin over several accumulators, with A from smem (SS) or TMEM (TS),
+// then commits and waits.  Prints cycles per MMA.   Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o
+// tools/umma_probe tools/umma_probe.cu
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../avsiam_b200/csrc/common.cuh"
+void avs_set_error(const char*, ...) {}
+int avs_check_launch(const char*) { return 0; }
+
+__device__ __forceinline__ uint64_t mk_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t lt) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)lt << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc(int m, int n, int am, int bm) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)am << 15) | ((uint32_t)bm << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// mode: 0 = SS K-major A/B (SW128), 1 = TS (A in TMEM) with MN-major B (SW128), 2 = SS MN-major A and B (SW128)
+//       3 = SS K-major SW64 (64-byte rows, 32 bytes per k-step)   4 = TS, B MN-major SW64 (64-byte rows)
+//       5 = SS K-major SW32 (32-byte rows, one k-step per slab)   6 = TS, B MN-major SW32 (two 16-element atoms)
+//       7 = SS: A = MN-major SW128 (dS tile), B = MN-major SW64   8 = like 7 with B MN-major SW32
+template <int N, int NACC, int MODE>
+__global__ void __launch_bounds__(128, 1) probe(long long* out, int reps) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) ((uint32_t*)smem)[i] = 0x3c003c00u;
+  if (warp == 0) {
+    tmem_alloc(&slot, 512);
+    tmem_relinquish();
+  }
+  if (threadIdx.x == 32) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  if (warp == 1) {
+    const uint32_t sa = smem_u32(smem), sb = sa + 32 * 1024;
+    const uint64_t da = (MODE == 2 || MODE == 7 || MODE == 8) ? mk_desc(sa, 16384, 1024, 2)
+                        : MODE == 3 ? mk_desc(sa, 0, 512, 4) : MODE == 5 ? mk_desc(sa, 0, 256, 6) : mk_desc(sa, 0, 1024, 2);
+    const uint64_t db = MODE == 0 ? mk_desc(sb, 0, 1024, 2) : MODE == 3 ? mk_desc(sb, 0, 512, 4)
+                        : MODE == 5 ? mk_desc(sb, 0, 256, 6) : (MODE == 4 || MODE == 7) ? mk_desc(sb, 512, 512, 4)
+                        : (MODE == 6 || MODE == 8) ? mk_desc(sb, 4096, 256, 6) : mk_desc(sb, 1024, 1024, 2);
+    constexpr bool A_MN = (MODE == 2 || MODE == 7 || MODE == 8);
+    constexpr bool B_MN = !(MODE == 0 || MODE == 3 || MODE == 5);
+    constexpr bool TS = (MODE == 1 || MODE == 4 || MODE == 6);
+    constexpr uint32_t ID = idesc(128, N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    long long t0 = 0, t1 = 0;
+    for (int rep = 0; rep < 2; ++rep) {  // first round warms up
+      t0 = clock64();
+      if (elect_one_sync()) {
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t acc = tmem + 256 + (uint32_t)((k % NACC) * N);
+            // B k-step advance (16-byte units): MN-major SW128 16 rows x 128 B = 128; SW64 16 x 64 B = 64; SW32 32
+            const uint64_t bk = (MODE == 4 || MODE == 7) ? (uint64_t)(k * 64) : (MODE == 6 || MODE == 8) ? (uint64_t)(k * 32)
+                                                                                : (uint64_t)(k * 128);
+            if (TS) umma_bf16_ts(acc, tmem + (uint32_t)(k * 8), db + bk, ID, 1u);
+            else if (A_MN) umma_bf16_ss(acc, da + (uint64_t)(k * 128), db + bk, ID, 1u);
+            else if (MODE == 3) umma_bf16_ss(acc, da + (uint64_t)(2 * (k & 1)), db + (uint64_t)(2 * (k & 1)), ID, 1u);
+            else if (MODE == 5) umma_bf16_ss(acc, da + (uint64_t)(256 * (k & 1)), db + (uint64_t)(256 * (k & 1)), ID, 1u);
+            else umma_bf16_ss(acc, da + (uint64_t)(2 * (k & 3)), db + (uint64_t)(2 * (k & 3)), ID, 1u);
+          }
+        }
+        umma_commit(&bar);
+      }
+      __syncwarp();
+      mbar_wait(&bar, (uint32_t)rep);
+      t1 = clock64();
+    }
+    if (lane == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int N, int NACC, int MODE>
+void run(const char* name, long long* d_out) {
+  const int reps = 64;
+  cudaFuncSetAttribute(probe<N, NACC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  probe<N, NACC, MODE><<<148, 128, 64 * 1024>>>(d_out, reps);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long cyc = 0;
+  cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
+  printf("%-34s N=%3d acc=%d : %7.1f cycles / MMA   (ideal %3d)  %s\n", name, N, NACC, (double)cyc / (reps * 8), N / 2,
+         e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
+// The exact MMA batch of one 128x128 block-step of attn_bwd_tc_kernel<32> (2 sub-steps), issued back to back.
+// spin: number of extra warps polling an mbarrier that never completes until the end (what idle role warps do).
+__global__ void __launch_bounds__(576, 1) probe_batch(long long* out, int reps, int spin, int variant) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar, never;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += 576) ((uint32_t*)smem)[i] = 0x3c003c00u;
+  if (warp == 0) {
+    tmem_alloc(&slot, 512);
+    tmem_relinquish();
+  }
+  if (threadIdx.x == 32) {
+    mbar_init(&bar, 1);
+    mbar_init(&never, 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  if (warp == 1) {
+    const uint32_t sQ = smem_u32(smem), sDO = sQ + 49152, sK = sDO + 49152, sV = sK + 16384, sDS = sV + 16384;
+    const uint64_t kK = mk_desc(sK, 0, 512, 4), kV = mk_desc(sV, 0, 512, 4), kQ = mk_desc(sQ, 0, 512, 4),
+                   kDO = mk_desc(sDO, 0, 512, 4);
+    const uint64_t mQ = mk_desc(sQ, 512, 512, 4), mDO = mk_desc(sDO, 512, 512, 4), mK = mk_desc(sK, 512, 512, 4);
+    const uint64_t aDS = mk_desc(sDS, 16384, 1024, 2);
+    constexpr uint32_t ID_S = idesc(128, 64, 0, 0), ID_TS = idesc(128, 32, 0, 1), ID_DQ = idesc(128, 32, 1, 1);
+    long long t0 = 0, t1 = 0;
+    for (int rep = 0; rep < 2; ++rep) {
+      t0 = clock64();
+      if (elect_one_sync()) {
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const uint32_t b = hh, qo = (uint32_t)hh * 256;
+            if (variant != 2) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) umma_bf16_ss(tmem + b * 64, kK + (uint64_t)(2 * k), kQ + (uint64_t)(qo + 2 * k), ID_S, k);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) umma_bf16_ss(tmem + 128 + b * 64, kV + (uint64_t)(2 * k), kDO + (uint64_t)(qo + 2 * k), ID_S, k);
+            }
+            if (variant != 3) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem + 288, tmem + b * 64 + k * 16, mDO + (uint64_t)(qo + k * 64), ID_TS, 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem + 256, tmem + 128 + b * 64 + k * 16, mQ + (uint64_t)(qo + k * 64), ID_TS, 1u);
+            }
+            if (variant == 1) umma_commit(&never);
+          }
+          if (variant != 2 && variant != 3) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) umma_bf16_ss(tmem + 320, aDS + (uint64_t)(k * 128), mK + (uint64_t)(k * 64), ID_DQ, 1u);
+          }
+        }
+        umma_commit(&bar);
+      }
+      __syncwarp();
+      mbar_wait(&bar, (uint32_t)rep);
+      t1 = clock64();
+    }
+    if (lane == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+    if (lane == 0) mbar_arrive(&never);
+  } else if (warp >= 2 && warp < 2 + spin && variant != 1) {
+    mbar_wait(&never, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+void run_batch(const char* name, long long* d_out, int spin, int variant) {
+  const int reps = 32;
+  cudaFuncSetAttribute(probe_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  probe_batch<<<148, 576, 200 * 1024>>>(d_out, reps, spin, variant);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long cyc = 0;
+  cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
+  printf("%-44s spin warps=%2d : %7.1f cycles / block-step (model 972)  %s\n", name, spin, (double)cyc / reps,
+         e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
+int main() {
+  long long* d_out;
+  cudaMalloc(&d_out, 8);
+  run<32, 1, 0>("SS K-major, one accumulator", d_out);
+  run<32, 2, 0>("SS K-major, 2 accumulators", d_out);
+  run<32, 4, 0>("SS K-major, 4 accumulators", d_out);
+  run<64, 1, 0>("SS K-major, one accumulator", d_out);
+  run<64, 2, 0>("SS K-major, 2 accumulators", d_out);
+  run<128, 1, 0>("SS K-major, one accumulator", d_out);
+  run<32, 1, 1>("TS (A in TMEM), B MN-major", d_out);
+  run<32, 2, 1>("TS (A in TMEM), B MN-major", d_out);
+  run<32, 4, 1>("TS (A in TMEM), B MN-major", d_out);
+  run<64, 1, 1>("TS (A in TMEM), B MN-major", d_out);
+  run<64, 2, 1>("TS (A in TMEM), B MN-major", d_out);
+  run<32, 1, 2>("SS MN-major A and B", d_out);
+  run<32, 2, 2>("SS MN-major A and B", d_out);
+  run<32, 4, 2>("SS MN-major A and B", d_out);
+  run<64, 1, 2>("SS MN-major A and B", d_out);
+  run<64, 2, 2>("SS MN-major A and B", d_out);
+  run<64, 1, 3>("SS K-major SW64 (S^T today)", d_out);
+  run<64, 1, 5>("SS K-major SW32 slabs", d_out);
+  run<32, 1, 4>("TS, B MN-major SW64 (dV today)", d_out);
+  run<32, 1, 6>("TS, B MN-major SW32", d_out);
+  run<32, 1, 7>("SS A=dS SW128 MN, B SW64 MN (dQ)", d_out);
+  run<32, 1, 8>("SS A=dS SW128 MN, B SW32 MN", d_out);
+  run_batch("attention batch", d_out, 0, 0);
+  run_batch("attention batch", d_out, 8, 0);
+  run_batch("attention batch", d_out, 16, 0);
+  run_batch("attention batch + commit per sub-step", d_out, 0, 1);
+  run_batch("only dV/dK (TS) [model 262]", d_out, 0, 2);
+  run_batch("only S^T/dP^T (SS N=64) [model 387]", d_out, 0, 3);
+  return 0;
+}
