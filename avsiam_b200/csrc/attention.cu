@@ -483,7 +483,7 @@ extern "C" int avs_attention_bwd(const void* qkv, long long ld_qkv, const void* 
   else attn_delta_kernel<32><<<dblocks, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, ld_o, S, H, rows);
   int rc = avs_check_launch("attn_delta_kernel");
   if (rc) return rc;
-  if (avs_attention_tc_enabled()) {
+  if (avs_attention_tc_enabled() && S >= 96) {  // short sequences (video, S = 49): the mma.sync kernels win
     rc = avs_attention_bwd_tc(qkv, ld_qkv, dout, ld_o, lse2, delta, dqkv, n_seq, S, H, head_dim, stream_);
     if (rc != -2) return rc;
   }

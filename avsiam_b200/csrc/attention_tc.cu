@@ -4,22 +4,25 @@
 //
 // Replaces the backward of F.scaled_dot_product_attention in Attention.forward (cav_mae_base.py:58-77).
 //
-// Structure (per CTA, 18 warps):
+// Structure (per CTA, 19 warps):
 //   warp 0      loader: streams the 128-key blocks K_j, V_j (double-buffered) into swizzled shared memory
-//   warp 1      one elected thread issues every tcgen05.mma
-//   warps 2-17  "softmax" warps in two ping-pong groups of 8 (one per TMEM buffer): thread = one key row (TMEM
+//   warps 1, 2  MMA issuers (PV stream: dV, dK, dQ / QK stream: S^T, dP^T), one elected thread each
+//   warps 3-18  "softmax" warps in two ping-pong groups of 8 (one per TMEM buffer): thread = one key row (TMEM
 //               lane), the two warps of a lane quarter split the sub-step's 64 query columns
 // Shared memory: Q and dO of the whole head stay resident (rows of head_dim bf16, SWIZZLE_64B / SWIZZLE_128B so the
 // same bytes serve as K-major operand of S^T = K Q^T and as MN-major operand of dK = dS^T Q), K_j / V_j blocks,
 // the dS^T tile (double-buffered, MN-major A operand of dQ = dS K), log-sum-exp and delta rows.
 // Tensor memory (512 columns, all used):
-//   [0,128)    two 64-column buffers  S^T[kv, q]   (fp32) — overwritten in place by P^T  (bf16 pairs, A operand of dV)
-//   [128,256)  two 64-column buffers  dP^T[kv, q]  (fp32) — overwritten in place by dS^T (bf16 pairs, A operand of dK)
+//   [0,128)    two 64-column buffers  S^T[kv, q]   (fp32), one per softmax group
+//   [128,256)  two 64-column buffers  dP^T[kv, q]  (fp32) — once read, overwritten in place by P^T and dS^T (bf16 pairs,
+//              the TMEM A operands of dV and dK)
 //   [256, ..)  dK_j, dV_j accumulators (head_dim columns each), then dQ_i for EVERY query block of the head
 // so dQ is accumulated across the key blocks without atomics and without a second pass.
-// Per 64-query sub-step the tensor pipe needs ~320 cycles and the 8192 exponentials 512 MUFU cycles; the MMA warp
-// runs one sub-step ahead (S^T / dP^T of sub-step t+1 are issued before the products that consume P^T / dS^T of
-// sub-step t-1), so the softmax warps — the bound — never wait for the tensor pipe.
+// Pipeline (measured, tools/umma_probe.cu + the AVS_TC_TRACE timeline): the tensor pipe needs ~1030 cycles per
+// 128x128 block (SS MMAs cost 32 + N/4 cycles of operand reads, TS MMAs N/2), the exponentials 1024 MUFU cycles.
+// What bounds the kernel is the round trip softmax -> MMA -> softmax, so the S^T product of sub-step t+2 is issued
+// as soon as the softmax warps have READ S^T of sub-step t (it does not wait for the dV/dK/dQ products of t), and
+// the exponentials of t+2 overlap the tensor work that consumes t.
 #include "../../include/avsiam_b200.h"
 #include "common.cuh"
 #include <stdlib.h>
@@ -29,7 +32,8 @@ namespace {
 
 constexpr int TCB_GROUP_WARPS = 8;                 // softmax warps per ping-pong group (4 lane quarters x 2 column halves)
 constexpr int TCB_COMPUTE_WARPS = 2 * TCB_GROUP_WARPS;
-constexpr int TCB_THREADS = 64 + 32 * TCB_COMPUTE_WARPS;
+constexpr int TCB_FIRST_SOFTMAX_WARP = 3;           // warp 0 loader, warp 1 PV issuer, warp 2 QK issuer
+constexpr int TCB_THREADS = 32 * (TCB_FIRST_SOFTMAX_WARP + TCB_COMPUTE_WARPS);
 constexpr int DS_TILE_BYTES = 128 * 128 * 2;  // [128 keys][128 queries] bf16 = two SWIZZLE_128B atoms of 64 queries
 
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
@@ -129,7 +133,6 @@ __device__ __forceinline__ void load_rows_async(uint32_t tile, const bf16* __res
 
 struct TcArgs {
   long long* trace;   // debug timeline (AVS_TC_TRACE builds only)
-  int exp;            // debug: bitmask of pipeline pieces to skip (timing experiments; results are wrong)
   const bf16* qkv;
   const bf16* dout;
   const float* lse2;
@@ -163,7 +166,10 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
   uint64_t* ds_empty = bars + 8;   // [2] MMA -> softmax warps: dS^T smem tile consumed by the dQ product
   uint64_t* dkv_full = bars + 10;  // MMA -> softmax warps: dK_j, dV_j complete
   uint64_t* dkv_empty = bars + 11; // softmax warps -> MMA: dK_j, dV_j read out
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* s_read = bars + 12;    // [2] softmax warps -> MMA: S^T of a sub-step is in registers, buffer reusable
+  uint64_t* dp_full = bars + 14;   // [2] MMA -> softmax warps: dP^T of a sub-step is in TMEM
+  uint64_t* pv_done = bars + 16;   // [2] PV issuer -> QK issuer: dV/dK of a sub-step have consumed P^T / dS^T
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, seq = blockIdx.y;
@@ -174,16 +180,19 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], 2);      // both MMA issuers commit
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], TCB_GROUP_WARPS);
       mbar_init(&ds_empty[i], 1);
+      mbar_init(&s_read[i], TCB_GROUP_WARPS);
+      mbar_init(&dp_full[i], 1);
+      mbar_init(&pv_done[i], 1);
     }
     mbar_init(dkv_full, 1);
     mbar_init(dkv_empty, TCB_GROUP_WARPS);
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 0) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -216,99 +225,128 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
       __syncwarp();
       if (lane == 0) mbar_arrive(&kv_full[j & 1]);
     }
-  } else if (warp == 1) {
-    // ============================ MMA issuer ============================
-    // One thread issues ~16 MMAs per 64-query sub-step, so its scalar work is kept minimal: every descriptor is a
-    // precomputed 64-bit base plus a 16-byte-unit offset added to the low word, and the (j, i, half) indices are
-    // carried incrementally (no divisions).
-    // The whole warp runs the loop convergently (so descriptors / TMEM addresses live in uniform registers); one
-    // elected lane issues.
-    {
-      constexpr uint32_t ID_S = idesc_bf16(128, 64, 0, 0);    // S^T / dP^T : A, B K-major
-      constexpr uint32_t ID_TS = idesc_bf16(128, HD, 0, 1);   // dV / dK    : A in TMEM, B MN-major
-      constexpr uint32_t ID_DQ = idesc_bf16(128, HD, 1, 1);   // dQ         : A (dS^T tile) and B (K_j) MN-major
-      constexpr uint32_t BLK16 = C::BLK_BYTES >> 4, HALF16 = (64 * C::ROWB) >> 4, K16ROWS = (16 * C::ROWB) >> 4;
+  } else if (warp == 1 || warp == 2) {
+    // ============================ MMA issuers ============================
+    // The MMAs of this kernel are small (16-48 tensor cycles each), so ONE issuing warp's scalar work (descriptor
+    // adds, barrier waits: ~4 cycles per dependent instruction) would bound the kernel.  Two warps issue
+    // independent streams, each visiting its barriers in the order the events happen:
+    //   warp 2 "QK":  S^T(u)  as soon as S^T(u-2) has been read; dP^T(u-2) as soon as dV/dK(u-4) have consumed the
+    //                 P^T / dS^T that live in that buffer
+    //   warp 1 "PV":  dV(u), dK(u) (A operands in TMEM) and, every second sub-step, dQ
+    // Both run convergently (descriptors and TMEM addresses stay in uniform registers); one elected lane issues.
+    constexpr uint32_t ID_S = idesc_bf16(128, 64, 0, 0);    // S^T / dP^T : A, B K-major
+    constexpr uint32_t ID_TS = idesc_bf16(128, HD, 0, 1);   // dV / dK    : A in TMEM, B MN-major
+    constexpr uint32_t ID_DQ = idesc_bf16(128, HD, 1, 1);   // dQ         : A (dS^T tile) and B (K_j) MN-major
+    constexpr uint32_t BLK16 = C::BLK_BYTES >> 4, HALF16 = (64 * C::ROWB) >> 4, K16ROWS = (16 * C::ROWB) >> 4;
+    auto advance = [&](int& j, int& i, int& hh) {
+      if (++hh == 2) {
+        hh = 0;
+        if (++i == NB) {
+          i = 0;
+          ++j;
+        }
+      }
+    };
+    if (warp == 2) {
       const uint64_t kK = make_desc(sK, 0, C::SBO, C::LT), kV = make_desc(sV, 0, C::SBO, C::LT);
       const uint64_t kQ = make_desc(sQ, 0, C::SBO, C::LT), kDO = make_desc(sDO, 0, C::SBO, C::LT);
+      auto issue_s = [&](uint32_t g, int j, int i, int hh) {    // S^T(u) = K_j Q_half^T  -> buffer g
+        const uint32_t kvo = (uint32_t)(j & 1) * BLK16, qo = (uint32_t)(i * 2 + hh) * HALF16;
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int k = 0; k < C::KSTEPS; ++k)
+            umma_bf16_ss(tmem + C::COL_S + g * 64, kK + (kvo + 2 * k), kQ + (qo + 2 * k), ID_S, k > 0 ? 1u : 0u);
+          umma_commit(&s_full[g]);
+        }
+        __syncwarp();
+      };
+      auto issue_dp = [&](uint32_t g, int j, int i, int hh) {   // dP^T(u) = V_j dO_half^T -> buffer g
+        const uint32_t kvo = (uint32_t)(j & 1) * BLK16, qo = (uint32_t)(i * 2 + hh) * HALF16;
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int k = 0; k < C::KSTEPS; ++k)
+            umma_bf16_ss(tmem + C::COL_DP + g * 64, kV + (kvo + 2 * k), kDO + (qo + 2 * k), ID_S, k > 0 ? 1u : 0u);
+          umma_commit(&dp_full[g]);
+          if (i == NB - 1 && hh == 1) umma_commit(&kv_empty[j & 1]);   // last read of K_j / V_j by this warp
+        }
+        __syncwarp();
+      };
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0, 0, 0);
+      issue_s(1, 0, 0, 1);
+      issue_dp(0, 0, 0, 0);
+      issue_dp(1, 0, 0, 1);
+      int sj = 0, si = 0, sh = 0;   // position of sub-step u     (S^T stream)
+      int dj = 0, di = 0, dh = 0;   // position of sub-step u - 2 (dP^T stream)
+      advance(sj, si, sh); advance(sj, si, sh);
+      for (int u = 2; u < T + 2; ++u) {
+        const uint32_t g = (uint32_t)(u & 1);
+        if (u < T) {
+          if (si == 0 && sh == 0) {
+            mbar_wait(&kv_full[sj & 1], (uint32_t)((sj >> 1) & 1));
+            tc_fence_after();
+          }
+          mbar_wait(&s_read[g], (uint32_t)(((u - 2) >> 1) & 1));
+          tc_fence_after();
+          issue_s(g, sj, si, sh);
+          advance(sj, si, sh);
+        }
+        if (u >= 4) {  // dP^T(u - 2) overwrites the buffer that held P^T / dS^T of sub-step u - 4
+          mbar_wait(&pv_done[g], (uint32_t)(((u - 4) >> 1) & 1));
+          tc_fence_after();
+          issue_dp(g, dj, di, dh);
+        }
+        if (u >= 2) advance(dj, di, dh);
+      }
+    } else {
       const uint64_t mQ = make_desc(sQ, C::SBO, C::SBO, C::LT), mDO = make_desc(sDO, C::SBO, C::SBO, C::LT);
       const uint64_t mK = make_desc(sK, C::SBO, C::SBO, C::LT);
       const uint64_t aDS = make_desc(sDS, 16384, 1024, 2u);
-      // state of the sub-step whose S^T / dP^T are issued now (c*) and of the previous one (p*)
       int cj = 0, ci = 0, ch = 0;
-      int pj = 0, pi = 0, ph = 0;
-      for (int t = 0; t <= T; ++t) {
-        const uint32_t b = (uint32_t)(t & 1);
-        if (t < T) {
-          if (ci == 0 && ch == 0) {
-            mbar_wait(&kv_full[cj & 1], (uint32_t)((cj >> 1) & 1));
-            tc_fence_after();
-          }
-          const uint32_t kvo = (uint32_t)(cj & 1) * BLK16;
-          const uint32_t qo = (uint32_t)(ci * 2 + ch) * HALF16;
-          if (lane == 0) TC_TRACE(0, t);
-          if (elect_one_sync()) {
-#pragma unroll
-            for (int k = 0; k < C::KSTEPS; ++k)
-              umma_bf16_ss(tmem + C::COL_S + b * 64, kK + (kvo + 2 * k), kQ + (qo + 2 * k), ID_S, k > 0 ? 1u : 0u);
-#pragma unroll
-            for (int k = 0; k < C::KSTEPS; ++k)
-              umma_bf16_ss(tmem + C::COL_DP + b * 64, kV + (kvo + 2 * k), kDO + (qo + 2 * k), ID_S, k > 0 ? 1u : 0u);
-            umma_commit(&s_full[b]);
-          }
-          __syncwarp();
-          if (lane == 0) TC_TRACE(11, t);
-        }
-        if (t >= 1) {
-          const uint32_t pb = b ^ 1u;
-          const int u = t - 1;
-          if (lane == 0) TC_TRACE(1, t);
-          mbar_wait(&p_full[pb], (uint32_t)((u >> 1) & 1));
+      for (int u = 0; u < T; ++u) {
+        const uint32_t g = (uint32_t)(u & 1);
+        if (lane == 0) TC_TRACE(1, u);
+        mbar_wait(&p_full[g], (uint32_t)((u >> 1) & 1));
+        tc_fence_after();
+        if (lane == 0) TC_TRACE(2, u);
+        const bool first = (ci == 0 && ch == 0);
+        if (first && cj > 0) {
+          mbar_wait(dkv_empty, (uint32_t)((cj - 1) & 1));
           tc_fence_after();
-          if (lane == 0) TC_TRACE(2, t);
-          const bool first = (pi == 0 && ph == 0);
-          if (first && pj > 0) {
-            mbar_wait(dkv_empty, (uint32_t)((pj - 1) & 1));
-            tc_fence_after();
-          }
-          const uint32_t qo = (uint32_t)(pi * 2 + ph) * HALF16;
-          // dV_j += P^T dO_i ,  dK_j += dS^T Q_i   (A: bf16 pairs in TMEM, 8 columns per k-step, written by the
-          // softmax warps over the first 8 of each 16-column chunk of S^T / dP^T)
-          const int n = u >> 1;
-          const uint32_t dso = (uint32_t)(n & 1) * (DS_TILE_BYTES >> 4);
-          const uint32_t kvo = (uint32_t)(pj & 1) * BLK16;
-          if (elect_one_sync()) {
+        }
+        const uint32_t qo = (uint32_t)(ci * 2 + ch) * HALF16;
+        const int n = u >> 1;
+        const uint32_t dso = (uint32_t)(n & 1) * (DS_TILE_BYTES >> 4);
+        const uint32_t kvo = (uint32_t)(cj & 1) * BLK16;
+        if (elect_one_sync()) {
+          // dV_j += P^T dO_i ,  dK_j += dS^T Q_i : A = bf16 pairs in TMEM (8 columns per 16-query k-step), written by
+          // the softmax warps over the dP^T buffer: per 16-column chunk  [P^T (8) | dS^T (8)]
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ts(tmem + C::COL_DV, tmem + C::COL_S + pb * 64 + k * 16,
-                           mDO + (qo + k * K16ROWS), ID_TS, (first && k == 0) ? 0u : 1u);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ts(tmem + C::COL_DV, tmem + C::COL_DP + g * 64 + k * 16, mDO + (qo + k * K16ROWS), ID_TS,
+                         (first && k == 0) ? 0u : 1u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ts(tmem + C::COL_DK, tmem + C::COL_DP + pb * 64 + k * 16,
-                           mQ + (qo + k * K16ROWS), ID_TS, (first && k == 0) ? 0u : 1u);
-            if (ph == 1) {
-              // dQ_i += dS K_j : A = dS^T tile [128 keys][128 queries] read MN-major (two 64-query atoms 16 KB apart)
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ts(tmem + C::COL_DK, tmem + C::COL_DP + g * 64 + k * 16 + 8, mQ + (qo + k * K16ROWS), ID_TS,
+                         (first && k == 0) ? 0u : 1u);
+          umma_commit(&pv_done[g]);
+          if (ch == 1) {
+            // dQ_i += dS K_j : A = dS^T tile [128 keys][128 queries] read MN-major (two 64-query atoms 16 KB apart)
 #pragma unroll
-              for (int k = 0; k < 8; ++k)
-                umma_bf16_ss(tmem + C::COL_DQ + pi * HD, aDS + (dso + k * 128), mK + (kvo + k * K16ROWS), ID_DQ,
-                             (pj > 0 || k > 0) ? 1u : 0u);
-              umma_commit(&ds_empty[n & 1]);
-              if (pi == NB - 1) {
-                umma_commit(dkv_full);
-                umma_commit(&kv_empty[pj & 1]);
-              }
+            for (int k = 0; k < 8; ++k)
+              umma_bf16_ss(tmem + C::COL_DQ + ci * HD, aDS + (dso + k * 128), mK + (kvo + k * K16ROWS), ID_DQ,
+                           (cj > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&ds_empty[n & 1]);
+            if (ci == NB - 1) {
+              umma_commit(dkv_full);
+              umma_commit(&kv_empty[cj & 1]);
             }
           }
-          __syncwarp();
-          if (lane == 0) TC_TRACE(12, t);
         }
-        pj = cj; pi = ci; ph = ch;
-        if (++ch == 2) {
-          ch = 0;
-          if (++ci == NB) {
-            ci = 0;
-            ++cj;
-          }
-        }
+        __syncwarp();
+        if (lane == 0) TC_TRACE(12, u);
+        advance(cj, ci, ch);
       }
     }
   } else {
@@ -316,9 +354,9 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
     // Two groups of 8 warps work ping-pong: group g owns TMEM buffer g and therefore every sub-step with
     // (t & 1) == g, i.e. the query half g of each 128-query block.  While one group waits for its tcgen05.ld /
     // fence / barrier round trips the other keeps the MUFU pipe busy.
-    const int grp = (warp - 2) >> 3;
+    const int grp = (warp - TCB_FIRST_SOFTMAX_WARP) >> 3;
     const int quarter = warp & 3;               // TMEM lane quarter this warp may access
-    const int half = ((warp - 2) & 7) >> 2;     // which 32 of the sub-step's 64 query columns
+    const int half = ((warp - TCB_FIRST_SOFTMAX_WARP) & 7) >> 2;     // which 32 of the sub-step's 64 query columns
     const int row = quarter * 32 + lane;        // key row inside the block == TMEM lane
     const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
     bf16* dkb = a.dqkv + row_base * a.ld_qkv + a.D + h * HD;
@@ -360,67 +398,74 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
     const uint32_t tS = tlane + C::COL_S + grp * 64 + half * 32, tDP = tlane + C::COL_DP + grp * 64 + half * 32;
     auto substep = [&](auto mask_tag, int n, int j, int i) {
       constexpr bool MASK = decltype(mask_tag)::value;   // last key block: rows at or beyond S contribute nothing
-      const bool tr = (lane == 0 && ((warp - 2) & 7) == 0);
+      const bool tr = (lane == 0 && ((warp - TCB_FIRST_SOFTMAX_WARP) & 7) == 0);
+      const bool kv_ok = !MASK || (j * 128 + row) < S;
+      const uint32_t qoff = (uint32_t)((i * 128 + grp * 64 + half * 32) * 4);
+      // ---- phase 1: P = exp2(S^T * scale - lse)   (needs only S^T; frees the S^T buffer immediately)
       if (tr) TC_TRACE(3 + grp * 4, n);
-      if (n >= 2) mbar_wait(&ds_empty[n & 1], (uint32_t)(((n >> 1) - 1) & 1));
       mbar_wait(&s_full[grp], (uint32_t)(n & 1));
       tc_fence_after();
       if (tr) TC_TRACE(4 + grp * 4, n);
-      const bool kv_ok = !MASK || (j * 128 + row) < S;
+      uint32_t pw[16];
+      {
+        uint32_t sr[32];
+        tmem_ld_32x32b_x32(tS, sr);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_read[grp]);
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          float4 ls;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+                       : "=f"(ls.x), "=f"(ls.y), "=f"(ls.z), "=f"(ls.w) : "r"(s_lse_u + qoff + c * 4));
+          float p0 = exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -ls.x));
+          float p1 = exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -ls.y));
+          float p2 = exp2f(fmaf(__uint_as_float(sr[c + 2]), a.scale_log2, -ls.z));
+          float p3 = exp2f(fmaf(__uint_as_float(sr[c + 3]), a.scale_log2, -ls.w));
+          if (MASK && !kv_ok) p0 = p1 = p2 = p3 = 0.f;
+          pw[c / 2] = pack_bf16x2(p0, p1);
+          pw[c / 2 + 1] = pack_bf16x2(p2, p3);
+        }
+      }
+      // ---- phase 2: dS = P o (dP^T - delta); P^T and dS^T replace dP^T in TMEM, dS^T also goes to shared memory
+      if (n >= 2) mbar_wait(&ds_empty[n & 1], (uint32_t)(((n >> 1) - 1) & 1));
+      mbar_wait(&dp_full[grp], (uint32_t)(n & 1));
+      tc_fence_after();
+      if (tr) TC_TRACE(5 + grp * 4, n);
       const uint32_t ds = sDS + (n & 1) * DS_TILE_BYTES + grp * 16384 + row * 128;
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {      // two chunks of 16 query columns
-        uint32_t sr[16], dr[16];
-        if (!(a.exp & 4)) {
-          tmem_ld_32x32b_x16(tS + cc * 16, sr);
-          tmem_ld_32x32b_x16(tDP + cc * 16, dr);
-        } else {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) sr[c] = dr[c] = 0x3f000000u + lane + c;
-        }
-        const uint32_t qoff = (uint32_t)((i * 128 + grp * 64 + half * 32 + cc * 16) * 4);
+        uint32_t dr[16];
+        tmem_ld_32x32b_x16(tDP + cc * 16, dr);
         tmem_ld_wait();
-        if (tr && grp == 0) TC_TRACE(13 + cc * 2, n);
-        uint32_t pw[8], dw[8];
+        uint32_t st[16];                   // [P^T (8 words) | dS^T (8 words)] of this chunk
 #pragma unroll
         for (int c = 0; c < 16; c += 4) {
-          float4 ls = make_float4(1.f, 2.f, 3.f, 4.f), dl = ls;
-          if (!(a.exp & 1)) {
+          float4 dl;
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
-                       : "=f"(ls.x), "=f"(ls.y), "=f"(ls.z), "=f"(ls.w) : "r"(s_lse_u + qoff + c * 4));
-          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
-                       : "=f"(dl.x), "=f"(dl.y), "=f"(dl.z), "=f"(dl.w) : "r"(s_delta_u + qoff + c * 4));
-          }
-          float p0 = fmaf(__uint_as_float(sr[c]), a.scale_log2, -ls.x);
-          float p1 = fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -ls.y);
-          float p2 = fmaf(__uint_as_float(sr[c + 2]), a.scale_log2, -ls.z);
-          float p3 = fmaf(__uint_as_float(sr[c + 3]), a.scale_log2, -ls.w);
-          if (!(a.exp & 8)) { p0 = exp2f(p0); p1 = exp2f(p1); p2 = exp2f(p2); p3 = exp2f(p3); }
-          if (MASK && !kv_ok) p0 = p1 = p2 = p3 = 0.f;
+                       : "=f"(dl.x), "=f"(dl.y), "=f"(dl.z), "=f"(dl.w) : "r"(s_delta_u + qoff + (cc * 16 + c) * 4));
+          const uint32_t w0 = pw[cc * 8 + c / 2], w1 = pw[cc * 8 + c / 2 + 1];
+          // the bf16-rounded probabilities (exactly what the dV product uses), widened back to fp32
+          const float p0 = __uint_as_float(w0 << 16), p1 = __uint_as_float(w0 & 0xffff0000u);
+          const float p2 = __uint_as_float(w1 << 16), p3 = __uint_as_float(w1 & 0xffff0000u);
           const float d0 = p0 * (__uint_as_float(dr[c]) - dl.x);
           const float d1 = p1 * (__uint_as_float(dr[c + 1]) - dl.y);
           const float d2 = p2 * (__uint_as_float(dr[c + 2]) - dl.z);
           const float d3 = p3 * (__uint_as_float(dr[c + 3]) - dl.w);
-          pw[c / 2] = pack_bf16x2(p0, p1);
-          pw[c / 2 + 1] = pack_bf16x2(p2, p3);
-          dw[c / 2] = pack_bf16x2(d0, d1);
-          dw[c / 2 + 1] = pack_bf16x2(d2, d3);
+          st[c / 2] = w0;
+          st[c / 2 + 1] = w1;
+          st[8 + c / 2] = pack_bf16x2(d0, d1);
+          st[8 + c / 2 + 1] = pack_bf16x2(d2, d3);
         }
-        if (tr && grp == 0) { asm volatile("" :: "r"(pw[0]), "r"(dw[7]) : "memory"); TC_TRACE(14 + cc * 2, n); }
-        // bf16 pairs overwrite the first 8 columns of this chunk's own 16 fp32 columns: k-step (2*half + cc)
-        if (!(a.exp & 16)) {
-          tmem_st_32x32b_x8(tS + cc * 16, pw);
-          tmem_st_32x32b_x8(tDP + cc * 16, dw);
-        }
-        if (!(a.exp & 2))
+        tmem_st_32x32b_x16(tDP + cc * 16, st);
 #pragma unroll
         for (int c = 0; c < 2; ++c)
-          st_shared_v4(ds + (((half * 4 + cc * 2 + c) ^ (row & 7)) << 4), dw[4 * c], dw[4 * c + 1], dw[4 * c + 2],
-                       dw[4 * c + 3]);
+          st_shared_v4(ds + (((half * 4 + cc * 2 + c) ^ (row & 7)) << 4), st[8 + 4 * c], st[8 + 4 * c + 1],
+                       st[8 + 4 * c + 2], st[8 + 4 * c + 3]);
       }
-      if (tr) TC_TRACE(5 + grp * 4, n);
       tmem_st_wait();
-      if (!(a.exp & 32)) fence_proxy_async();
+      fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[grp]);
@@ -451,7 +496,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -487,7 +532,6 @@ int avs_attention_bwd_tc(const void* qkv, long long ld_qkv, const void* dout, lo
   if (NB > (head_dim == 32 ? TcCfg<32>::MAX_NB : TcCfg<64>::MAX_NB)) return -2;
   TcArgs a = {};
   a.trace = g_tc_trace;
-  { const char* e = getenv("AVS_TC_EXP"); a.exp = e ? atoi(e) : 0; }
   a.qkv = (const bf16*)qkv; a.dout = (const bf16*)dout; a.lse2 = lse2; a.delta = delta; a.dqkv = (bf16*)dqkv;
   a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.S = S; a.NB = NB; a.H = H; a.D = H * head_dim;
   a.scale = rsqrtf((float)head_dim);

@@ -218,4 +218,5 @@ def test_state_dict_round_trip_keeps_arena_binding():
         l1 = float(model(audio.to(DEV), imgs.to(DEV), mae_loss_weight=1.0, contrast_loss_weight=0.0)[0])
         model.load_state_dict(saved)
         l2 = float(model(audio.to(DEV), imgs.to(DEV), mae_loss_weight=1.0, contrast_loss_weight=0.0)[0])
-    assert l0 != l1 and l0 == l2
+    # the loss reductions use fp32 atomics (summation order varies run to run): equal up to fp32 rounding
+    assert abs(l0 - l1) > 1e-4 * abs(l0) and l2 == pytest.approx(l0, rel=1e-5)

@@ -18,16 +18,14 @@ lib.avs_debug_set_tc_trace(ctypes.c_void_p(trace.data_ptr()))
 ops.attention_bwd(qkv, out, dout, lse, delta, dqkv, n_seq, S, H, hd)
 torch.cuda.synchronize()
 tr = trace.cpu().reshape(20, 512)
-t0 = int(tr[0, 0])
-names = ["mma:issueS", "mma:wait_p", "mma:got_p", "A:top", "A:got_s", "A:computed", "A:arrived", "B:top", "B:got_s", "B:computed", "B:arrived"]
-print("MMA thread (t: issueS, issuedS, wait_p, got_p, issued dV/dK/dQ) relative cycles")
-for t in range(0, 30):
-    print(t, [int(tr[k, t]) - t0 if int(tr[k, t]) else None for k in (0, 11, 1, 2, 12)])
-print("group A / B per n: top, got_s, computed, arrived")
-for n in range(0, 14):
-    print(n, [int(tr[k, n]) - t0 if int(tr[k, n]) else None for k in range(3, 11)])
-print("group A detail per n: got_s, c0 ldwait, c0 math, c1 ldwait, c1 math, computed(before st wait), arrived")
-for n in range(0, 14):
-    print(n, [int(tr[k, n]) - t0 if int(tr[k, n]) else None for k in (4, 13, 14, 15, 16, 5, 6)])
-last = max(int(tr[k].max()) for k in range(11)) - t0
-print("total cycles", last)
+nz = tr[tr > 0]
+t0 = int(nz.min())
+def rel(k, i):
+    v = int(tr[k, i]); return v - t0 if v else None
+print("MMA thread per sub-step u: [before wait p_full, got p_full, issued dV/dK(/dQ)+dP^T]")
+for u in range(0, 26):
+    print(u, [rel(k, u) for k in (1, 2, 12)])
+print("softmax group A | B per block-step n: [top, got S^T, got dP^T, arrived p_full]")
+for n in range(0, 13):
+    print(n, [rel(k, n) for k in (3, 4, 5, 6)], "|", [rel(k, n) for k in (7, 8, 9, 10)])
+print("total cycles", int(tr.max()) - t0)

@@ -188,6 +188,99 @@ void run_batch(const char* name, long long* d_out, int spin, int variant) {
          e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
 
+// Same batch, but issued the way the kernel does: per sub-step [S^T,dP^T -> commit s_full] ... [wait p_full] [dV,dK(,dQ)].
+// variant 4: only tcgen05.fence::after_thread_sync between the groups; variant 5: real handshake with an instant responder
+__global__ void __launch_bounds__(576, 1) probe_hs(long long* out, int reps, int variant) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar, s_full[2], p_full[2];
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += 576) ((uint32_t*)smem)[i] = 0x3c003c00u;
+  if (warp == 0) {
+    tmem_alloc(&slot, 512);
+    tmem_relinquish();
+  }
+  if (threadIdx.x == 32) {
+    mbar_init(&bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 1); }
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  const int T = reps * 2;
+  if (warp == 1) {
+    const uint32_t sQ = smem_u32(smem), sDO = sQ + 49152, sK = sDO + 49152, sV = sK + 16384, sDS = sV + 16384;
+    const uint64_t kK = mk_desc(sK, 0, 512, 4), kV = mk_desc(sV, 0, 512, 4), kQ = mk_desc(sQ, 0, 512, 4),
+                   kDO = mk_desc(sDO, 0, 512, 4);
+    const uint64_t mQ = mk_desc(sQ, 512, 512, 4), mDO = mk_desc(sDO, 512, 512, 4), mK = mk_desc(sK, 512, 512, 4);
+    const uint64_t aDS = mk_desc(sDS, 16384, 1024, 2);
+    constexpr uint32_t ID_S = idesc(128, 64, 0, 0), ID_TS = idesc(128, 32, 0, 1), ID_DQ = idesc(128, 32, 1, 1);
+    const long long t0 = clock64();
+    for (int t = 0; t <= T; ++t) {
+      const uint32_t b = t & 1;
+      if (t < T) {
+        const uint32_t qo = b * 256;
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) umma_bf16_ss(tmem + b * 64, kK + (uint64_t)(2 * k), kQ + (uint64_t)(qo + 2 * k), ID_S, k);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) umma_bf16_ss(tmem + 128 + b * 64, kV + (uint64_t)(2 * k), kDO + (uint64_t)(qo + 2 * k), ID_S, k);
+          umma_commit(&s_full[b]);
+        }
+        __syncwarp();
+      }
+      if (t >= 1) {
+        const uint32_t pb = b ^ 1, qo = pb * 256;
+        const int u = t - 1;
+        if (variant == 5) mbar_wait(&p_full[pb], (uint32_t)((u >> 1) & 1));
+        tc_fence_after();
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem + 288, tmem + pb * 64 + k * 16, mDO + (uint64_t)(qo + k * 64), ID_TS, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem + 256, tmem + 128 + pb * 64 + k * 16, mQ + (uint64_t)(qo + k * 64), ID_TS, 1u);
+          if (pb == 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) umma_bf16_ss(tmem + 320, aDS + (uint64_t)(k * 128), mK + (uint64_t)(k * 64), ID_DQ, 1u);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one_sync()) umma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (lane == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+  } else if ((warp == 2 || warp == 3) && variant == 5) {
+    const int g = warp - 2;
+    for (int n = 0; n < reps; ++n) {
+      mbar_wait(&s_full[g], (uint32_t)(n & 1));
+      tc_fence_after();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+void run_hs(const char* name, long long* d_out, int variant) {
+  const int reps = 32;
+  cudaFuncSetAttribute(probe_hs, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  probe_hs<<<148, 576, 200 * 1024>>>(d_out, reps, variant);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long cyc = 0;
+  cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
+  printf("%-60s : %7.1f cycles / block-step   %s\n", name, (double)cyc / reps, e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
 int main() {
   long long* d_out;
   cudaMalloc(&d_out, 8);
@@ -219,5 +312,7 @@ int main() {
   run_batch("attention batch + commit per sub-step", d_out, 0, 1);
   run_batch("only dV/dK (TS) [model 262]", d_out, 0, 2);
   run_batch("only S^T/dP^T (SS N=64) [model 387]", d_out, 0, 3);
+  run_hs("kernel-order issue, fences only", d_out, 4);
+  run_hs("kernel-order issue, handshake with instant responder", d_out, 5);
   return 0;
 }
