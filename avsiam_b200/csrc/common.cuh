@@ -207,40 +207,33 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
-// exact-erf GELU (timm Mlp uses nn.GELU default, approximate='none').
-// The GEMM epilogues evaluate it ~10^8 times per step on 8 warps that must keep pace with the tensor pipe, so the
-// normal CDF is a minimax odd polynomial on the FMA pipe (no MUFU, no branches):
-//   Phi(x)   = 0.5 + x*Q(x^2), |x| clamped to 4.0 : |Phi err| <= 2.4e-5, |gelu err| <= 1.9e-4 (bf16 ulp at 1 is 3.9e-3)
-//   gelu'(x) = 0.5 + x*R(x^2), |x| clamped to 4.5 : |err| <= 1.9e-4
-// (fit: Chebyshev least squares against scipy erf; tools/fit_gelu_poly.py reproduces the coefficients.)
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float xc = fminf(fmaxf(x, -4.0f), 4.0f);
-  const float t = xc * xc;
-  float q = 9.566814702e-11f;
-  q = fmaf(q, t, -8.025974552e-09f);
-  q = fmaf(q, t, 3.002519975e-07f);
-  q = fmaf(q, t, -6.720556939e-06f);
-  q = fmaf(q, t, 1.025099482e-04f);
-  q = fmaf(q, t, -1.151216682e-03f);
-  q = fmaf(q, t, 9.921516292e-03f);
-  q = fmaf(q, t, -6.646095216e-02f);
-  q = fmaf(q, t, 3.989394903e-01f);
-  return x * fmaf(xc, q, 0.5f);
+// exact-erf GELU (timm Mlp uses nn.GELU default, approximate='none'):  gelu(x) = x * Phi(x).
+// The GEMM epilogues evaluate it ~10^8 times per step on warps that must keep pace with the tensor pipe.  A pure
+// FMA-pipe polynomial costs ~13 issue slots per element and made the fc1 GEMMs epilogue-bound (ncu: 621
+// instructions per 32-column chunk), so the normal CDF is evaluated as a sigmoid of a fitted odd polynomial,
+//   Phi(x) ~= 1 / (1 + exp2(x * Q(t))),  t = min(x^2, 5.5^2),
+// which moves the transcendental part to the otherwise idle MUFU pipe (ex2 + rcp) and leaves 6 FMA-pipe
+// instructions:  |gelu err| <= 2.6e-5, |gelu' err| <= 1.1e-4  (bf16 ulp at 1 is 3.9e-3; the clamp keeps the fit in
+// range, beyond it the sigmoid is saturated).  gelu' is the exact derivative of the approximation,
+//   gelu'(x) = s + x s (1 - s) R(t),  R = P + 2 t P'.   Coefficients: tools/fit_gelu_poly.py.
+__device__ __forceinline__ float gelu_sigmoid(float x) {   // Phi(x)
+  const float t = fminf(x * x, 30.25f);
+  float q = 1.014263253e-03f;
+  q = fmaf(q, t, -1.067757234e-01f);
+  q = fmaf(q, t, -2.301121235e+00f);
+  return __fdividef(1.0f, 1.0f + exp2f(x * q));
 }
+__device__ __forceinline__ float gelu_erf(float x) { return x * gelu_sigmoid(x); }
 __device__ __forceinline__ float dgelu_erf(float x) {
-  const float xc = fminf(fmaxf(x, -4.5f), 4.5f);
-  const float t = xc * xc;
-  float q = -2.743805010e-11f;
-  q = fmaf(q, t, 3.034134721e-09f);
-  q = fmaf(q, t, -1.475804652e-07f);
-  q = fmaf(q, t, 4.182222256e-06f);
-  q = fmaf(q, t, -7.728275523e-05f);
-  q = fmaf(q, t, 9.887785418e-04f);
-  q = fmaf(q, t, -9.041387588e-03f);
-  q = fmaf(q, t, 5.918052420e-02f);
-  q = fmaf(q, t, -2.655833960e-01f);
-  q = fmaf(q, t, 7.978483438e-01f);
-  return fmaf(xc, q, 0.5f);
+  const float t = fminf(x * x, 30.25f);
+  float q = 1.014263253e-03f;
+  q = fmaf(q, t, -1.067757234e-01f);
+  q = fmaf(q, t, -2.301121235e+00f);
+  const float s = __fdividef(1.0f, 1.0f + exp2f(x * q));
+  float r = -3.515168559e-03f;
+  r = fmaf(r, t, 2.220338732e-01f);
+  r = fmaf(r, t, 1.595015764e+00f);
+  return fmaf(x * (s * (1.0f - s)), r, s);
 }
 
 // ---- TMA store / bulk-group plumbing (epilogues) ----
@@ -252,6 +245,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");

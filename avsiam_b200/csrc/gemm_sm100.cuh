@@ -72,7 +72,8 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int BAR_BYTES = 512;
-  // per epilogue warp: [in x2][out][aux_out] staging tiles (only the ones the launch uses)
+  // per epilogue warp: [in x2][out][aux_out] staging tiles (only the ones the launch uses).  (Double-buffering the
+  // output tiles was measured and bought nothing: the mainloop, not the store latency, bounds these kernels.)
   static __host__ __device__ int epi_bytes_per_warp(int tma_epi, int has_in, int has_aux_out) {
     return tma_epi ? GEMM_EPI_BUF * (1 + (has_in ? 2 : 0) + (has_aux_out ? 1 : 0)) : 0;
   }
@@ -175,18 +176,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   if (warp == 0) {
     // ============================ TMA producer ============================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int ks = t % args.split_k;
-        const int mn = t / args.split_k;
-        const int m0 = (mn / n_tiles) * GEMM_BLOCK_M;
-        const int n0 = (mn % n_tiles) * BLOCK_N;
-        const int kb0 = ks * args.kb_per_split;
-        const int kb1 = min(total_kb, kb0 + args.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // The whole warp runs the loop convergently (loop state stays in uniform registers); one elected lane issues.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int ks = t % args.split_k;
+      const int mn = t / args.split_k;
+      const int m0 = (mn / n_tiles) * GEMM_BLOCK_M;
+      const int n0 = (mn % n_tiles) * BLOCK_N;
+      const int kb0 = ks * args.kb_per_split;
+      const int kb1 = min(total_kb, kb0 + args.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
           uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
@@ -205,56 +207,63 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             for (int j = 0; j < BLOCK_N / 64; ++j)
               tma_load_2d(sb + j * (GEMM_BLOCK_K * 128), &tma_b, &full_bar[stage], n0 + j * 64, k0);
           }
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, BLOCK_N, A_MAJOR, B_MAJOR);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int ks = t % args.split_k;
-        const int kb0 = ks * args.kb_per_split;
-        const int kb1 = min(total_kb, kb0 + args.kb_per_split);
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    // One k-block is only 4 MMAs (~512 tensor cycles at BLOCK_N = 256), so the issuing warp's scalar work must stay
+    // well below that: the warp runs convergently, every descriptor is a precomputed 64-bit base plus a 16-byte-unit
+    // offset (stage and k-step), and one elected lane issues the 4 MMAs and the commit back to back.
+    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, BLOCK_N, A_MAJOR, B_MAJOR);
+    // K-major: step 16 elements (32 B) inside the 128 B swizzle row; 8-row groups 1024 B apart.
+    // MN-major: step 16 reduction rows (2 swizzle atoms = 2048 B); atoms along MN are BLOCK_K*128 B apart (LBO),
+    //           8-row K groups 1024 B apart (SBO).
+    const uint32_t mn_lbo = args.desc_variant ? 1024 : GEMM_BLOCK_K * 128;
+    const uint32_t mn_sbo = args.desc_variant ? GEMM_BLOCK_K * 128 : 1024;
+    const uint64_t da0 = (A_MAJOR == MAJOR_K) ? make_smem_desc(smem_u32(smem_a), 0, 1024)
+                                              : make_smem_desc(smem_u32(smem_a), mn_lbo, mn_sbo);
+    const uint64_t db0 = (B_MAJOR == MAJOR_K) ? make_smem_desc(smem_u32(smem_b), 0, 1024)
+                                              : make_smem_desc(smem_u32(smem_b), mn_lbo, mn_sbo);
+    constexpr uint32_t A_K16 = ((A_MAJOR == MAJOR_K) ? 32 : 2048) >> 4, B_K16 = ((B_MAJOR == MAJOR_K) ? 32 : 2048) >> 4;
+    constexpr uint32_t A_STAGE16 = Cfg::A_BYTES >> 4, B_STAGE16 = Cfg::B_BYTES >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int ks = t % args.split_k;
+      const int kb0 = ks * args.kb_per_split;
+      const int kb1 = min(total_kb, kb0 + args.kb_per_split);
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem_a + stage * Cfg::A_BYTES);
-          const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_BYTES);
+        if (elect_one_sync()) {
+          const uint64_t da = da0 + (uint64_t)((uint32_t)stage * A_STAGE16);
+          const uint64_t db = db0 + (uint64_t)((uint32_t)stage * B_STAGE16);
 #pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
-            // K-major: step 16 elements (32 B) inside the 128 B swizzle row; 8-row groups 1024 B apart.
-            // MN-major: step 16 reduction rows (2 swizzle atoms = 2048 B); atoms along MN are
-            //           BLOCK_K*128 B apart (LBO), 8-row K groups 1024 B apart (SBO).
-            const uint32_t mn_lbo = args.desc_variant ? 1024 : GEMM_BLOCK_K * 128;
-            const uint32_t mn_sbo = args.desc_variant ? GEMM_BLOCK_K * 128 : 1024;
-            const uint64_t da = (A_MAJOR == MAJOR_K) ? make_smem_desc(sa + k * 32, 0, 1024)
-                                                     : make_smem_desc(sa + k * 2048, mn_lbo, mn_sbo);
-            const uint64_t db = (B_MAJOR == MAJOR_K) ? make_smem_desc(sb + k * 32, 0, 1024)
-                                                     : make_smem_desc(sb + k * 2048, mn_lbo, mn_sbo);
-            umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k)
+            umma_bf16_ss(tmem_d, da + (uint64_t)(k * A_K16), db + (uint64_t)(k * B_K16), idesc,
+                         (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ============================ epilogue (8 warps) ============================
@@ -325,11 +334,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (ep.bias != nullptr && lead_split && col_ok) {
+          if (full) {   // interior chunk: no per-group predicates (the epilogue is issue-bound)
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (full || nc + j < args.N) {
-              const float4 b = *reinterpret_cast<const float4*>(ep.bias + nc + j);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + nc + j));
               v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (nc + j < args.N) {
+                const float4 b = *reinterpret_cast<const float4*>(ep.bias + nc + j);
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
             }
           }
         }
@@ -344,16 +361,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
         if (tma_epi) {
           // ---------------- bf16 outputs: staged in smem, moved by TMA ----------------
-          if (lane == 0) bulk_wait_read0();  // the previous chunk's stores have finished reading the staging tiles
-          __syncwarp();
+          // Everything is computed in registers first; the wait for the previous chunk's TMA stores (they read the
+          // staging tiles) comes as late as possible so that it overlaps this chunk's math.
+          uint4 ax[4];
           if (ep.flags & EPI_GELU) {
             if (args.has_aux_out) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                uint4 o;
-                o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                *reinterpret_cast<uint4*>(aux_buf + epi_tile_off(lane, j)) = o;
+                ax[j].x = pack_bf16x2(v[8 * j], v[8 * j + 1]); ax[j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                ax[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); ax[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
               }
             }
 #pragma unroll
@@ -392,18 +408,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               f = unpack_bf16x2(in4[j].w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
             }
           }
+          uint4 o[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-            o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-            *reinterpret_cast<uint4*>(out_buf + epi_tile_off(lane, j)) = o;
+            o[j].x = pack_bf16x2(v[8 * j], v[8 * j + 1]); o[j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            o[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); o[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
           }
+          if (lane == 0) bulk_wait_read0();  // the previous chunk's stores have finished reading the staging tiles
+          __syncwarp();
+          if ((ep.flags & EPI_GELU) && args.has_aux_out) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(aux_buf + epi_tile_off(lane, j)) = ax[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(out_buf + epi_tile_off(lane, j)) = o[j];
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && col_ok && m0 + quarter * 32 < args.M) {  // TMA clips the M / N tails of the box
-            tma_store_2d(&tma_c, out_buf, nc, m0 + quarter * 32);
-            if (args.has_aux_out) tma_store_2d(&tma_aux, aux_buf, nc, m0 + quarter * 32);
+          if (lane == 0) {
+            if (col_ok && m0 + quarter * 32 < args.M) {  // TMA clips the M / N tails of the box
+              tma_store_2d(&tma_c, out_buf, nc, m0 + quarter * 32);
+              if (args.has_aux_out) tma_store_2d(&tma_aux, aux_buf, nc, m0 + quarter * 32);
+            }
             bulk_commit();
           }
         } else if (row_ok && col_ok) {
