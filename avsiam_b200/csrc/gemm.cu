@@ -127,19 +127,20 @@ extern "C" int avs_gemm_bf16(const void* A, long long lda, int a_major, const vo
   if (b_major == 0) rc = make_tmap_2d(&tm.b, B, N, K, ldb, GEMM_BLOCK_K, BN);
   else rc = make_tmap_2d(&tm.b, B, K, N, ldb, 64, GEMM_BLOCK_K);
   if (rc) return rc;
-  // bf16 outputs leave (and the residual / dGELU operand arrives) as [32 x 32] tiles moved by TMA, 64-byte swizzle
+  // bf16 outputs leave as [32 x 64] tiles (128-byte swizzle), the residual / dGELU operand arrives as [32 x 32]
+  // tiles (64-byte swizzle), all moved by TMA
   const bool tma_epi = !out_f32;
   const void* in_ptr = nullptr;
   long long in_ld = 0;
   if (tma_epi) {
     AVS_REQUIRE(!(epi->resid && (epi->flags & AVS_EPI_DGELU)), "avs_gemm_bf16: resid and DGELU cannot be combined");
-    if ((rc = make_tmap_2d(&tm.c, C, M, N, ldc, GEMM_EPI_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_tmap_2d(&tm.c, C, M, N, ldc, 2 * GEMM_EPI_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     if (epi->flags & AVS_EPI_DGELU) { in_ptr = epi->aux_in; in_ld = epi->ld_aux; }
     else if (epi->resid) { in_ptr = epi->resid; in_ld = epi->ld_resid; }
     if (in_ptr && (rc = make_tmap_2d(&tm.in, in_ptr, M, N, in_ld, GEMM_EPI_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B)))
       return rc;
     if ((epi->flags & AVS_EPI_GELU) && epi->aux_out &&
-        (rc = make_tmap_2d(&tm.aux, epi->aux_out, M, N, epi->ld_aux, GEMM_EPI_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B)))
+        (rc = make_tmap_2d(&tm.aux, epi->aux_out, M, N, epi->ld_aux, 2 * GEMM_EPI_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_128B)))
       return rc;
   } else {
     AVS_REQUIRE(!epi->resid && !(epi->flags & (AVS_EPI_GELU | AVS_EPI_DGELU)),

@@ -61,7 +61,11 @@ constexpr int GEMM_EPI_WARPS = 8;  // two warps per TMEM lane quarter, each taki
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp0 TMA, warp1 MMA, warps2-9 epilogue
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_EPI_CHUNK = 32;                 // columns per epilogue chunk (one tcgen05.ld 32x32b.x32)
-constexpr int GEMM_EPI_BUF = 32 * GEMM_EPI_CHUNK * 2;  // one [32 rows x 32 cols] bf16 staging tile = 2 KB
+constexpr int GEMM_EPI_BUF = 32 * GEMM_EPI_CHUNK * 2;  // one [32 rows x 32 cols] bf16 input staging tile = 2 KB
+// Output staging tiles are [32 rows x 64 cols] (128-byte rows, SWIZZLE_128B) and leave every SECOND chunk: the TMA
+// unit turns each box row into one L2 write request, so 64-byte rows (the 32-column tiles of v2) made the stores —
+// 2048 row requests per 128x256 tile — the bound of every bf16-output GEMM (ncu: MMA warp polling tmem_empty).
+constexpr int GEMM_OUT_BUF = 32 * 64 * 2;
 constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 
 template <int BLOCK_N>
@@ -75,7 +79,7 @@ struct GemmCfg {
   // per epilogue warp: [in x2][out][aux_out] staging tiles (only the ones the launch uses).  (Double-buffering the
   // output tiles was measured and bought nothing: the mainloop, not the store latency, bounds these kernels.)
   static __host__ __device__ int epi_bytes_per_warp(int tma_epi, int has_in, int has_aux_out) {
-    return tma_epi ? GEMM_EPI_BUF * (1 + (has_in ? 2 : 0) + (has_aux_out ? 1 : 0)) : 0;
+    return tma_epi ? GEMM_EPI_BUF * (has_in ? 2 : 0) + GEMM_OUT_BUF * (1 + (has_aux_out ? 1 : 0)) : 0;
   }
   static __host__ int pick_stages(int epi_per_warp) {
     int s = (GEMM_SMEM_LIMIT - 1024 - BAR_BYTES - GEMM_EPI_WARPS * epi_per_warp) / STAGE_BYTES;
@@ -114,6 +118,9 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float 
 // byte offset of 16-byte chunk `j` (0..3) of row `r` inside a [32 x 32] bf16 staging tile laid out the way TMA's
 // SWIZZLE_64B expects it (chunk index XOR address bits 7..8) — also conflict-free for one-row-per-lane accesses.
 __device__ __forceinline__ uint32_t epi_tile_off(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
+
+// byte offset of 16-byte chunk `j` (0..7) of row `r` inside a [32 x 64] bf16 output staging tile, SWIZZLE_128B
+__device__ __forceinline__ uint32_t out_tile_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
 template <int A_MAJOR, int B_MAJOR, int BLOCK_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -275,8 +282,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const GemmEpilogue& ep = args.epi;
     uint8_t* my_epi = smem_epi + ew * epi_per_warp;
     uint8_t* in_buf = my_epi;                                        // [2][2 KB] when has_in
-    uint8_t* out_buf = my_epi + (args.has_in ? 2 * GEMM_EPI_BUF : 0);
-    uint8_t* aux_buf = out_buf + GEMM_EPI_BUF;
+    uint8_t* out_buf = my_epi + (args.has_in ? 2 * GEMM_EPI_BUF : 0);   // 1024-byte aligned (128 B swizzle pattern)
+    uint8_t* aux_buf = out_buf + GEMM_OUT_BUF;
     uint64_t* my_in_bar = in_bar + 2 * ew;
     const bool tma_epi = args.tma_epi != 0;
     const bool has_in = tma_epi && args.has_in;
@@ -414,22 +421,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             o[j].x = pack_bf16x2(v[8 * j], v[8 * j + 1]); o[j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
             o[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); o[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
           }
-          if (lane == 0) bulk_wait_read0();  // the previous chunk's stores have finished reading the staging tiles
-          __syncwarp();
+          const int hsel = c & 1;   // which 64-byte half of the 128-byte staging rows this chunk fills
+          if (hsel == 0) {
+            if (lane == 0) bulk_wait_read0();  // the previous pair's stores have finished reading the staging tiles
+            __syncwarp();
+          }
           if ((ep.flags & EPI_GELU) && args.has_aux_out) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(aux_buf + epi_tile_off(lane, j)) = ax[j];
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(aux_buf + out_tile_off(lane, hsel * 4 + j)) = ax[j];
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(out_buf + epi_tile_off(lane, j)) = o[j];
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (col_ok && m0 + quarter * 32 < args.M) {  // TMA clips the M / N tails of the box
-              tma_store_2d(&tma_c, out_buf, nc, m0 + quarter * 32);
-              if (args.has_aux_out) tma_store_2d(&tma_aux, aux_buf, nc, m0 + quarter * 32);
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(out_buf + out_tile_off(lane, hsel * 4 + j)) = o[j];
+          if (hsel == 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int nc0 = nc - GEMM_EPI_CHUNK;   // first column of the pair
+              if (nc0 < args.N && m0 + quarter * 32 < args.M) {  // TMA clips the M / N tails of the box
+                tma_store_2d(&tma_c, out_buf, nc0, m0 + quarter * 32);
+                if (args.has_aux_out) tma_store_2d(&tma_aux, aux_buf, nc0, m0 + quarter * 32);
+              }
+              bulk_commit();
             }
-            bulk_commit();
           }
         } else if (row_ok && col_ok) {
           // ---------------- fp32 outputs (wgrad / split-K accumulation): direct stores ----------------

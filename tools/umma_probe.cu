@@ -281,9 +281,156 @@ void run_hs(const char* name, long long* d_out, int variant) {
   printf("%-60s : %7.1f cycles / block-step   %s\n", name, (double)cyc / reps, e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
 
+// N = 256 SS MMAs (the GEMM mainloop) with and without concurrent shared-memory fill traffic from other warps
+// (stands in for the TMA writes of the next stages: 12 KB per MMA in the real kernel).
+__global__ void __launch_bounds__(320, 1) probe_n256(long long* out, int reps, int writers, const void* gsrc) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  __shared__ volatile int stop;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 192 * 1024 / 4; i += 320) ((uint32_t*)smem)[i] = 0x3c003c00u;
+  if (warp == 0) {
+    tmem_alloc(&slot, 512);
+    tmem_relinquish();
+  }
+  if (threadIdx.x == 32) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+    stop = 0;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  if (warp == 1) {
+    const uint32_t sa = smem_u32(smem), sb = sa + 16 * 1024;
+    const uint64_t da = mk_desc(sa, 0, 1024, 2), db = mk_desc(sb, 0, 1024, 2);
+    constexpr uint32_t ID = idesc(128, 256, 0, 0);
+    const long long t0 = clock64();
+    if (elect_one_sync()) {
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem + (r & 1) * 256, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), ID, 1u);
+      }
+      umma_commit(&bar);
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (lane == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+    stop = 1;
+  } else if (warp == 2 && writers < 0) {
+    // TMA-engine writes: 1-D bulk copies global -> shared (16 KB each, 4 in flight), like the producer's stage fills
+    __shared__ uint64_t wbar[4];
+    if (lane == 0) {
+      for (int i = 0; i < 4; ++i) mbar_init(&wbar[i], 1);
+      fence_mbar_init();
+      long long n = 0;
+      uint32_t ph[4] = {0, 0, 0, 0};
+      const uint8_t* g = reinterpret_cast<const uint8_t*>(gsrc) + (size_t)blockIdx.x * 65536;
+      for (int i = 0; i < 4; ++i) {
+        mbar_arrive_expect_tx(&wbar[i], 16384);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                         smem_u32(smem) + 64 * 1024 + i * 16384), "l"(g + i * 16384), "r"(16384), "r"(smem_u32(&wbar[i])) : "memory");
+      }
+      while (!stop) {
+        for (int i = 0; i < 4; ++i) {
+          mbar_wait(&wbar[i], ph[i]);
+          ph[i] ^= 1;
+          mbar_arrive_expect_tx(&wbar[i], 16384);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                           smem_u32(smem) + 64 * 1024 + i * 16384), "l"(g + i * 16384), "r"(16384), "r"(smem_u32(&wbar[i])) : "memory");
+          ++n;
+        }
+      }
+      for (int i = 0; i < 4; ++i) mbar_wait(&wbar[i], ph[i]);
+      if (blockIdx.x == 0) out[1] = n * 32;   // in units of 512 B like the st.shared writers
+    }
+  } else if (warp >= 2 && warp < 2 + writers) {
+    // each warp streams 512 B per instruction into a private 16 KB region (different from the operand tiles)
+    const uint32_t base = smem_u32(smem) + 64 * 1024 + (warp - 2) * 16 * 1024 + lane * 16;
+    long long n = 0;
+    while (!stop) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};\n" ::"r"(base + i * 512), "r"(i) : "memory");
+      n += 32;
+    }
+    if (lane == 0 && blockIdx.x == 0) out[1 + (warp - 2)] = n;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+void run_n256(long long* d_out, int writers) {
+  const int reps = 2048;
+  cudaMemset(d_out, 0, 128);
+  cudaFuncSetAttribute(probe_n256, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  static void* gsrc = nullptr;
+  if (!gsrc) { cudaMalloc(&gsrc, 148 * 65536); cudaMemset(gsrc, 0, 148 * 65536); }
+  probe_n256<<<148, 320, 200 * 1024>>>(d_out, reps, writers, gsrc);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h[16];
+  cudaMemcpy(h, d_out, 128, cudaMemcpyDeviceToHost);
+  long long stores = 0;
+  for (int i = 0; i < (writers < 0 ? 1 : writers); ++i) stores += h[1 + i];
+  printf("SS N=256 K-major, %d writer warps: %6.1f cycles / MMA (math 128); concurrent st.shared traffic %5.1f B/cycle  %s\n",
+         writers, (double)h[0] / (reps * 4), (double)stores * 512 / (double)h[0], e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
+// tcgen05.ld throughput: `nw` warps each read their lane quarter, 32 fp32 columns per instruction, `reps` times.
+__global__ void __launch_bounds__(512, 1) probe_ldtm(long long* out, int reps, int nw, int batch) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    tmem_alloc(&slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  uint32_t acc = 0;
+  const long long t0 = clock64();
+  if (warp < nw) {
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int r = 0; r < reps; ++r) {
+      uint32_t v[32], w[32];
+      tmem_ld_32x32b_x32(tl + ((r * 64) & 255), v);
+      if (batch > 1) tmem_ld_32x32b_x32(tl + ((r * 64 + 32) & 255), w);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc ^= v[i];
+      if (batch > 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc ^= w[i];
+      }
+    }
+  }
+  const long long t1 = clock64();
+  if (acc == 0x12345678u) out[3] = acc;
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+void run_ldtm(long long* d_out, int nw, int batch) {
+  const int reps = 1024;
+  probe_ldtm<<<148, 512, 0>>>(d_out, reps, nw, batch);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long cyc = 0;
+  cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
+  const double bytes = (double)nw * reps * batch * 32 * 32 * 4;
+  printf("tcgen05.ld 32x32b.x32: %2d warps, %d loads per wait: %6.1f B/cycle/SM, %6.1f cycles per load  %s\n", nw, batch,
+         bytes / cyc, (double)cyc / (reps * batch), e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
 int main() {
   long long* d_out;
-  cudaMalloc(&d_out, 8);
+  cudaMalloc(&d_out, 256);
   run<32, 1, 0>("SS K-major, one accumulator", d_out);
   run<32, 2, 0>("SS K-major, 2 accumulators", d_out);
   run<32, 4, 0>("SS K-major, 4 accumulators", d_out);
@@ -314,5 +461,7 @@ int main() {
   run_batch("only S^T/dP^T (SS N=64) [model 387]", d_out, 0, 3);
   run_hs("kernel-order issue, fences only", d_out, 4);
   run_hs("kernel-order issue, handshake with instant responder", d_out, 5);
+  for (int w : {0, 4, -1}) run_n256(d_out, w);
+  for (int nw : {1, 4, 8, 16}) for (int b : {1, 2}) run_ldtm(d_out, nw, b);
   return 0;
 }
