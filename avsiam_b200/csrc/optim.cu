@@ -91,40 +91,61 @@ extern "C" int avs_cast_f32_to_bf16(const float* src, void* dst, long long n, vo
   return avs_check_launch("cast_f32_bf16_kernel");
 }
 
-// out[n] += alpha * sum_m dy[m, n]  (bias gradients).  Each CTA owns 64 columns x a strip of rows; 8 warps stride the rows,
-// lanes read 2 adjacent bf16 (coalesced 128 B per warp-row); smem reduce; one fp32 atomic per column per CTA.
+// out[n] += alpha * sum_m dy[m, n]  (bias gradients of fc1 / qkv).  HBM-bound: each CTA owns 256 columns x a strip of
+// rows; 8 warps stride the rows, every lane reads 16 bytes (8 bf16) per row, so a warp moves 512 contiguous bytes per
+// load instruction and keeps 4 rows in flight; smem reduce; one fp32 atomic per column per CTA.
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ out, int M,
                                                      int N, long long ld, int rows_per_cta, float alpha) {
-  const int c0 = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
-  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
   const int r0 = blockIdx.y * rows_per_cta;
   const int r1 = min(M, r0 + rows_per_cta);
-  float a0 = 0.f, a1 = 0.f;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (c0 < N) {
-    for (int r = r0 + warp; r < r1; r += 8) {
-      const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dy + (size_t)r * ld + c0));
-      a0 += f.x; a1 += f.y;
+    const bf16* p = dy + c0;
+    int r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {   // 4 independent 16-byte loads in flight per lane
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(p + (size_t)(r + 8 * k) * ld));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float2 f;
+        f = unpack_bf16x2(u[k].x); a[0] += f.x; a[1] += f.y;
+        f = unpack_bf16x2(u[k].y); a[2] += f.x; a[3] += f.y;
+        f = unpack_bf16x2(u[k].z); a[4] += f.x; a[5] += f.y;
+        f = unpack_bf16x2(u[k].w); a[6] += f.x; a[7] += f.y;
+      }
+    }
+    for (; r < r1; r += 8) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p + (size_t)r * ld));
+      float2 f;
+      f = unpack_bf16x2(u.x); a[0] += f.x; a[1] += f.y;
+      f = unpack_bf16x2(u.y); a[2] += f.x; a[3] += f.y;
+      f = unpack_bf16x2(u.z); a[4] += f.x; a[5] += f.y;
+      f = unpack_bf16x2(u.w); a[6] += f.x; a[7] += f.y;
     }
   }
-  __shared__ float s[8][64];
-  s[warp][(threadIdx.x & 31) * 2] = a0;
-  s[warp][(threadIdx.x & 31) * 2 + 1] = a1;
+  __shared__ float s[8][256];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[warp][lane * 8 + j] = a[j];
   __syncthreads();
-  if (threadIdx.x < 64) {
+  {
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += s[w][threadIdx.x];
-    const int c = blockIdx.x * 64 + threadIdx.x;
+    const int c = blockIdx.x * 256 + threadIdx.x;
     if (c < N) atomicAdd(out + c, t * alpha);
   }
 }
 
 extern "C" int avs_colsum_bf16(const void* dy, long long ld, float* out, int M, int N, float alpha, void* stream) {
   AVS_REQUIRE(dy && out, "avs_colsum_bf16: null pointer");
-  AVS_REQUIRE(N % 2 == 0 && ld % 2 == 0, "avs_colsum_bf16: N and ld must be even");
+  AVS_REQUIRE(N % 8 == 0 && ld % 8 == 0 && ((uintptr_t)dy & 15) == 0,
+              "avs_colsum_bf16: N and ld must be multiples of 8 and dy 16-byte aligned");
   if (M == 0 || N == 0) return 0;
-  const int col_blocks = ceil_div(N, 64);
-  int row_blocks = max(1, (avs_num_sms() * 4) / col_blocks);
+  const int col_blocks = ceil_div(N, 256);
+  int row_blocks = max(1, (avs_num_sms() * 6) / col_blocks);
   int rows_per_cta = max(64, ceil_div(M, row_blocks));
   row_blocks = ceil_div(M, rows_per_cta);
   dim3 grid(col_blocks, row_blocks);
