@@ -220,6 +220,41 @@ def seq_mean_fwd(y, out, n_seq, seq_len, D, y_seq_stride=None, y_off=0):
                "avs_seq_mean_fwd")
 
 
+def seq_mean_bwd(dpool, dx, n_seq, seg_len, D, seq_stride, off):
+    _chk(dpool, F32, "seq_mean_bwd.dpool"); _chk(dx, BF16, "seq_mean_bwd.dx")
+    _lib.check(_lib.lib().avs_seq_mean_bwd(dpool.data_ptr(), dx.data_ptr(), n_seq, seg_len, D, seq_stride, off,
+                                           _stream()), "avs_seq_mean_bwd")
+
+
+# --------------------------------------------------------------------------------------------- finetune heads
+def head_fwd(x, gamma, beta, eps, W, bias):
+    """logits = Linear(LayerNorm(x)); x fp32 [B, D]. Returns (logits fp32 [B, C], saved) for head_bwd."""
+    _chk(x, F32, "head.x"); _chk(W, F32, "head.W")
+    B, D = x.shape
+    C = W.shape[0]
+    xhat, y = torch.empty_like(x), torch.empty_like(x)
+    rstd = torch.empty(B, dtype=F32, device=x.device)
+    logits = torch.empty(B, C, dtype=F32, device=x.device)
+    _lib.check(_lib.lib().avs_head_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, W.data_ptr(),
+                                       bias.data_ptr(), xhat.data_ptr(), rstd.data_ptr(), y.data_ptr(),
+                                       logits.data_ptr(), B, C, D, _stream()), "avs_head_fwd")
+    return logits, (xhat, rstd, y)
+
+
+def head_bwd(dlogits, saved, gamma, W, dW, dbias, dgamma, dbeta):
+    """Accumulates dW / dbias / dgamma / dbeta; returns dx fp32 [B, D]."""
+    xhat, rstd, y = saved
+    _chk(dlogits, F32, "head.dlogits")
+    B, D = xhat.shape
+    C = W.shape[0]
+    scratch, dx = torch.empty_like(xhat), torch.empty_like(xhat)
+    _lib.check(_lib.lib().avs_head_bwd(dlogits.data_ptr(), xhat.data_ptr(), rstd.data_ptr(), y.data_ptr(),
+                                       gamma.data_ptr(), W.data_ptr(), dW.data_ptr(), dbias.data_ptr(),
+                                       dgamma.data_ptr(), dbeta.data_ptr(), scratch.data_ptr(), dx.data_ptr(), B, C, D,
+                                       _stream()), "avs_head_bwd")
+    return dx
+
+
 # --------------------------------------------------------------------------------------------- attention
 def attention_fwd(qkv, out, lse2, n_seq, S, H, head_dim):
     _chk(qkv, BF16, "attn.qkv", contiguous=False); _chk(out, BF16, "attn.out", contiguous=False)

@@ -122,6 +122,22 @@ int avs_layernorm_bwd(const void* dy, const float* dpool, float pool_scale, cons
 /* out fp32 [n_seq, D] = mean over the seq_len tokens of each sequence (.mean(dim=1), cav_mae_base.py:563-566,729) */
 int avs_seq_mean_fwd(const void* y, float* out, int n_seq, int seq_len, int D, int y_seq_stride, int y_off,
                      void* stream);
+/* backward of a token mean over the segment [off, off+seg_len) of every sequence (rows s*seq_stride + off + t):
+ * dx bf16 (overwrite) = dpool[s, :] / seg_len.   av[:, :512].mean(1) | av[:, 512:].mean(1), cav_mae_base.py:1025-1028 */
+int avs_seq_mean_bwd(const float* dpool, void* dx, int n_seq, int seg_len, int D, int seq_stride, int off,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Finetune classification heads: logits = Linear(LayerNorm(x)), x fp32 [B, D] pooled features
+ * (nn.Sequential(nn.LayerNorm(D), nn.Linear(D, C)): mlp_head / mlp_head_a / mlp_head_mm, cav_mae_base.py:813-815).
+ * All fp32, parameters read from the fp32 master copy.  fwd saves xhat [B,D], rstd [B], y [B,D] for bwd.
+ * bwd ACCUMULATES dW [C,D], dbias [C], dgamma [D], dbeta [D] and overwrites dx [B,D]; dy_scratch fp32 [B,D].
+ * ------------------------------------------------------------------------------------------------ */
+int avs_head_fwd(const float* x, const float* gamma, const float* beta, float eps, const float* W, const float* bias,
+                 float* xhat, float* rstd, float* y, float* logits, int B, int C, int D, void* stream);
+int avs_head_bwd(const float* dlogits, const float* xhat, const float* rstd, const float* y, const float* gamma,
+                 const float* W, float* dW, float* dbias, float* dgamma, float* dbeta, float* dy_scratch, float* dx,
+                 int B, int C, int D, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused attention (flash-style), packed QKV in / O out.  Attention.forward, cav_mae_base.py:58-77.

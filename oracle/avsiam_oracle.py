@@ -504,3 +504,103 @@ def adam_step(p, g, m, v, step: int, lr=2e-4, beta1=0.95, beta2=0.999, eps=1e-8,
     bc2 = 1 - beta2 ** step
     denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
     p.addcdiv_(m, denom, value=-lr / bc1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Finetune model CAVMAEFT_BASE (cav_mae_base.py:745-1036) — SURVEY.md §8(f) rank 1
+# ---------------------------------------------------------------------------------------------------------
+def ft_param_shapes(d: Dims = VIT_B, label_dim: int = 527) -> "OrderedDict[str, tuple]":
+    """Unique parameters of CAVMAEFT_BASE keyed as in its state_dict (:750-820): the shared ViT with the per-modality
+    LayerNorm copies, the unused my_patch_embed* copies, four LayerNorm+Linear heads and the two fusion blocks."""
+    D, p = d.embed_dim, d.patch
+    sh = OrderedDict()
+    for k, s in _vit_shapes(d).items():
+        sh[f"vit_base.{k}"] = s
+    sh["my_patch_embed.proj.weight"] = (D, d.in_chans, p, p); sh["my_patch_embed.proj.bias"] = (D,)
+    sh["my_patch_embed_a.proj.weight"] = (D, 1, p, p); sh["my_patch_embed_a.proj.bias"] = (D,)
+    for name, din in (("mlp_head", D), ("mlp_head_a", D), ("mlp_head_mm", 2 * D), ("mlp_head_mm_v2", D)):
+        sh[f"{name}.0.weight"] = (din,); sh[f"{name}.0.bias"] = (din,)
+        sh[f"{name}.1.weight"] = (label_dim, din); sh[f"{name}.1.bias"] = (label_dim,)
+    for name in ("mm_layer_1", "mm_layer_2"):
+        for k, s in _block_shapes(D, 4 * D).items():
+            sh[f"{name}.{k}"] = s
+    return sh
+
+
+def init_ft_state(d: Dims = VIT_B, label_dim: int = 527, seed: int = 0, skip_heads: bool = False) -> State:
+    """Seeded weights for the finetune model, same scheme as init_state (every tensor from its own generator)."""
+    import zlib
+
+    sd: State = OrderedDict()
+    for k, shape in ft_param_shapes(d, label_dim).items():
+        if skip_heads and ".head." in k:
+            continue
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(("ft:" + k).encode())) % (2**31))
+        t = torch.randn(shape, generator=g, dtype=torch.float32)
+        is_ln = ("norm" in k) or (k.startswith("mlp_head") and ".0." in k)
+        if is_ln and k.endswith(".weight"):
+            t = 1.0 + 0.1 * t
+        elif is_ln and k.endswith(".bias"):
+            t = 0.05 * t
+        elif k.endswith(".bias"):
+            t = 0.02 * t
+        elif "pos_embed" in k or "token" in k:
+            t = 0.02 * t
+        elif "patch_embed" in k:
+            t = t * (1.0 / math.sqrt(shape[1] * shape[2] * shape[3]))
+        else:
+            t = t * (0.7 / math.sqrt(shape[-1]))
+        sd[k] = t
+    return sd
+
+
+def ft_head(x, sd: State, name: str):
+    """nn.Sequential(nn.LayerNorm(D), nn.Linear(D, label_dim)) — cav_mae_base.py:813-816 (LayerNorm eps 1e-5)."""
+    h = layer_norm(x, sd[name + ".0.weight"], sd[name + ".0.bias"], LN_EPS_BLOCK)
+    return F.linear(h, sd[name + ".1.weight"], sd[name + ".1.bias"])
+
+
+def ft_encode_audio(audio, sd: State, d: Dims):
+    """:830-840 — patch embed, + pos, + norm_pre_a (Identity) doubling, 12 shared blocks with the 'a' norms, norm_a."""
+    a = patch_embed_audio(audio, sd["vit_base.patch_embed_a.proj.weight"], sd["vit_base.patch_embed_a.proj.bias"], d)
+    a = a + sd["vit_base.pos_embed_a"]
+    a = a + a
+    for i in range(d.depth):
+        a = block(a, sd, f"vit_base.blocks.{i}.", d.heads, "a")
+    return layer_norm(a, sd["vit_base.norm_a.weight"], sd["vit_base.norm_a.bias"], LN_EPS_FINAL)
+
+
+def ft_encode_video(video, sd: State, d: Dims):
+    """:855-871 — video [B, T, C, H, W] -> (B T) frames, shared blocks with the 'v' norms, vit_base.norm."""
+    v = video.reshape(-1, *video.shape[2:])
+    v = patch_embed_video(v, sd["vit_base.patch_embed.proj.weight"], sd["vit_base.patch_embed.proj.bias"], d)
+    v = v + sd["vit_base.pos_embed"][:, 1:]
+    v = v + v
+    for i in range(d.depth):
+        v = block(v, sd, f"vit_base.blocks.{i}.", d.heads, "v")
+    return layer_norm(v, sd["vit_base.norm.weight"], sd["vit_base.norm.bias"], LN_EPS_FINAL)
+
+
+def forward_ft(audio, video, sd: State, d: Dims, mode: str):
+    """CAVMAEFT_BASE.forward training paths (is_eval=False), cav_mae_base.py:827-1036.
+       'audioonly' -> out_a [B, C];  'videoonly' -> [B, T, C] squeezed at T == 1;  'mm_grad' -> (out, out_a, out_v)
+       (the reference's torch.cat((a, v), dim=1) at :1019 requires one frame per sample)."""
+    if mode == "audioonly":
+        a = ft_encode_audio(audio, sd, d)
+        return ft_head(a.mean(dim=1), sd, "mlp_head_a")
+    if mode == "videoonly":
+        bs, t = video.shape[0], video.shape[1]
+        v = ft_encode_video(video, sd, d)
+        x = ft_head(v.mean(dim=1), sd, "mlp_head")
+        return x.reshape(bs, t, -1).squeeze(1)
+    if mode == "mm_grad":
+        a = ft_encode_audio(audio, sd, d)
+        v = ft_encode_video(video, sd, d)
+        out_a = ft_head(a.mean(dim=1), sd, "mlp_head_a")
+        out_v = ft_head(v.mean(dim=1), sd, "mlp_head")
+        av = torch.cat((a, v), dim=1)
+        av = block(av, sd, "mm_layer_1.", d.heads, "a")
+        av = block(av, sd, "mm_layer_2.", d.heads, "a")
+        av = torch.cat((av[:, :d.Ta].mean(dim=1), av[:, d.Ta:].mean(dim=1)), dim=-1)
+        return ft_head(av, sd, "mlp_head_mm"), out_a, out_v
+    raise ValueError(f"unsupported mode {mode!r}")

@@ -75,3 +75,47 @@ def test_forward_backward_matches_reference(cases, state, idx):
     for k, gref in c["grad_full"].items():
         cos = torch.nn.functional.cosine_similarity(state[k].grad.flatten().double(), gref.flatten().double(), dim=0)
         assert float(cos) > 0.99999, (k, float(cos))
+
+
+# ------------------------------------------------------------------------------------------------ finetune model
+@pytest.fixture(scope="module")
+def ft_cases(golden_dir):
+    return torch.load(os.path.join(golden_dir, "cavmaeft_base_forward.pt"), weights_only=False)
+
+
+def test_ft_layout_matches_reference(golden_dir):
+    layout = json.load(open(os.path.join(golden_dir, "ft_state_dict_layout.json")))
+    shapes = O.ft_param_shapes(O.VIT_B, 527)
+    want = set(shapes) | {k.replace("vit_base.blocks.", "my_blocks.") for k in shapes if k.startswith("vit_base.blocks.")}
+    assert set(layout) == want
+    for k, s in shapes.items():
+        assert tuple(layout[k]) == tuple(s)
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_ft_forward_backward_matches_reference(ft_cases, idx):
+    """CAVMAEFT_BASE.forward (cav_mae_base.py:827-1036) executed by the reference itself vs the oracle restatement."""
+    from oracle.make_golden_ft import ft_loss, synth_ft_inputs
+    c = ft_cases[idx]
+    d = O.VIT_B
+    sd = O.init_ft_state(d, c["label_dim"], seed=0, skip_heads=True)
+    for v in sd.values():
+        v.requires_grad_(True)
+    audio, video, labels = synth_ft_inputs(c["B"], c["T"], d, c["seed"])
+    outs = O.forward_ft(audio, video, sd, d, c["mode"])
+    outs_t = outs if isinstance(outs, tuple) else (outs,)
+    for o, ref in zip(outs_t, c["logits"]):
+        assert torch.allclose(o, ref, rtol=1e-4, atol=2e-5)
+    lab = labels if c["mode"] != "videoonly" or c["T"] == 1 else labels.unsqueeze(1).expand(-1, c["T"], -1)
+    loss = ft_loss(outs, lab)
+    assert float(loss) == pytest.approx(c["loss"], rel=2e-5)
+    loss.backward()
+    got = {k for k, v in sd.items() if v.grad is not None}
+    want = {k for k in c["grad_norm"] if ".head." not in k}
+    assert got == want, (sorted(got - want)[:5], sorted(want - got)[:5])
+    for k in want:
+        g = sd[k].grad.double().flatten()
+        assert float(g.norm()) == pytest.approx(c["grad_norm"][k], rel=2e-3, abs=1e-8), k
+    for k, gref in c["grad_full"].items():
+        cos = torch.nn.functional.cosine_similarity(sd[k].grad.flatten().double(), gref.flatten().double(), dim=0)
+        assert float(cos) > 0.99999, (k, float(cos))
