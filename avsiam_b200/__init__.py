@@ -5,11 +5,12 @@ path `FusedAdam`, `B200DDP`, `patch()`.  Importing the package never touches the
 libavsiam_b200.so and raises if it is missing (there is no CPU / PyTorch fallback).
 """
 from .cav_mae_base import CAVMAE_BASE, _Dims as Dims  # noqa: F401
+from .cav_mae_ft import CAVMAEFT_BASE  # noqa: F401
 from .ddp import B200DDP, GradSync  # noqa: F401
 from .gather_layer import GatherLayer  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 
-__all__ = ["CAVMAE_BASE", "Dims", "GatherLayer", "FusedAdam", "B200DDP", "GradSync", "patch"]
+__all__ = ["CAVMAE_BASE", "CAVMAEFT_BASE", "Dims", "GatherLayer", "FusedAdam", "B200DDP", "GradSync", "patch"]
 __version__ = "0.1.0"
 
 
@@ -28,6 +29,9 @@ def patch(traintest_module=None, models_module=None):
         old = getattr(models_module, "CAVMAE_BASE", None)
         models_module.CAVMAE_BASE = CAVMAE_BASE
         undo.append(lambda: setattr(models_module, "CAVMAE_BASE", old))
+        old_ft = getattr(models_module, "CAVMAEFT_BASE", None)
+        models_module.CAVMAEFT_BASE = CAVMAEFT_BASE                       # run_cavmae_ft_base.py
+        undo.append(lambda: setattr(models_module, "CAVMAEFT_BASE", old_ft))
     if traintest_module is not None:
         old_ddp = getattr(traintest_module, "DDP", None)
         traintest_module.DDP = B200DDP

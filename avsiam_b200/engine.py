@@ -362,6 +362,49 @@ class Engine:
             tape.append(bwd)
         return y, pooled
 
+    # -------------------------------------------------------------------------------------------- finetune heads
+    def head(self, tape: Optional[list], x: Act, name: str) -> Act:
+        """nn.Sequential(nn.LayerNorm(D), nn.Linear(D, label_dim)) on pooled fp32 features [B, D]
+        (CAVMAEFT_BASE.mlp_head / mlp_head_a / mlp_head_mm, cav_mae_base.py:813-815)."""
+        P = self.P
+        logits, saved = ops.head_fwd(x.t, P.f32(name + ".0.weight"), P.f32(name + ".0.bias"), LN_EPS_BLOCK,
+                                     P.f32(name + ".1.weight"), P.f32(name + ".1.bias"))
+        out = Act(logits)
+        if tape is not None:
+            def bwd():
+                if out.g is None:
+                    return
+                x.g = ops.head_bwd(out.g.contiguous().float(), saved, P.f32(name + ".0.weight"),
+                                   P.f32(name + ".1.weight"), P.grad(name + ".1.weight"), P.grad(name + ".1.bias"),
+                                   P.grad(name + ".0.weight"), P.grad(name + ".0.bias"))
+            bwd.touch = (name + ".",)
+            tape.append(bwd)
+        return out
+
+    def segment_means(self, tape: Optional[list], x: Act, n_seq: int, seg_lens: Sequence[int]) -> Act:
+        """torch.cat((av[:, :Ta].mean(1), av[:, Ta:].mean(1)), dim=-1)  (cav_mae_base.py:1025-1028): fp32 [n_seq, k*D]
+        from bf16 tokens [n_seq * sum(seg_lens), D]."""
+        D = x.t.shape[1]
+        stride = sum(seg_lens)
+        parts, off = [], 0
+        for L in seg_lens:
+            m = self._empty(n_seq, D, dtype=F32)
+            ops.seq_mean_fwd(x.t, m, n_seq, L, D, y_seq_stride=stride, y_off=off)
+            parts.append(m)
+            off += L
+        out = Act(torch.cat(parts, dim=1))
+        if tape is not None:
+            def bwd():
+                dx = self._empty(n_seq * stride, D)
+                off = 0
+                for j, L in enumerate(seg_lens):
+                    ops.seq_mean_bwd(out.g[:, j * D:(j + 1) * D].contiguous(), dx, n_seq, L, D, stride, off)
+                    off += L
+                x.g = dx
+            bwd.touch = ()
+            tape.append(bwd)
+        return out
+
     # -------------------------------------------------------------------------------------------- MAE branch
     def mae_branch(self, tape: Optional[list], xcat: Act, audio, imgs, B: int, keep_a: int, keep_v: int,
                    ids_restore_a, ids_restore_v, mask_a, mask_v, up_a: Optional[torch.Tensor],
