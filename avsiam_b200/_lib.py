@@ -53,7 +53,7 @@ SIGNATURES = {
     "avs_head_fwd": [_P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "avs_head_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "avs_attention_fwd": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _P],
-    "avs_attention_bwd": [_P, _L, _P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _P],
+    "avs_attention_bwd": [_P, _L, _P, _P, _L, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "avs_mae_loss_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P],
     "avs_mae_loss_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P],
     "avs_infonce_workspace_bytes": [_I, _I],

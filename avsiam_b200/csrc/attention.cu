@@ -464,8 +464,8 @@ extern "C" int avs_attention_fwd(const void* qkv, long long ld_qkv, void* out, l
 
 // delta: scratch [n_seq, H, S] fp32
 extern "C" int avs_attention_bwd(const void* qkv, long long ld_qkv, const void* out, const void* dout, long long ld_o,
-                                 const float* lse2, float* delta, void* dqkv, int n_seq, int S, int H, int head_dim,
-                                 void* stream_) {
+                                 const float* lse2, float* delta, void* dqkv, float* dbias, int n_seq, int S, int H,
+                                 int head_dim, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (check_common(qkv, ld_qkv, ld_o, n_seq, S, H, head_dim, "avs_attention_bwd")) return -1;
   AVS_REQUIRE(out && dout && lse2 && delta && dqkv, "avs_attention_bwd: null pointer");
@@ -484,7 +484,7 @@ extern "C" int avs_attention_bwd(const void* qkv, long long ld_qkv, const void* 
   int rc = avs_check_launch("attn_delta_kernel");
   if (rc) return rc;
   if (avs_attention_tc_enabled() && S >= 96) {  // short sequences (video, S = 49): the mma.sync kernels win
-    rc = avs_attention_bwd_tc(qkv, ld_qkv, dout, ld_o, lse2, delta, dqkv, n_seq, S, H, head_dim, stream_);
+    rc = avs_attention_bwd_tc(qkv, ld_qkv, dout, ld_o, lse2, delta, dqkv, dbias, n_seq, S, H, head_dim, stream_);
     if (rc != -2) return rc;
   }
   const int smem_dq = 2 * a.S_pad * head_dim * 2;
@@ -503,5 +503,8 @@ extern "C" int avs_attention_bwd(const void* qkv, long long ld_qkv, const void* 
     if ((rc = avs_check_launch("attn_bwd_dkv_kernel"))) return rc;
     attn_bwd_dq_kernel<32><<<grid, ATT_THREADS, smem_dq, stream>>>(a);
   }
-  return avs_check_launch("attn_bwd_dq_kernel");
+  if ((rc = avs_check_launch("attn_bwd_dq_kernel"))) return rc;
+  // qkv-bias gradient: the tcgen05 kernel accumulates it in its epilogues; this path takes one more pass over dQKV
+  if (dbias != nullptr) return avs_colsum_bf16(dqkv, ld_qkv, dbias, n_seq * S, 3 * a.D, 1.0f, stream_);
+  return 0;
 }

@@ -93,6 +93,23 @@ __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t (&r)[N]
   else tmem_st_32x32b_x8(taddr, r);
 }
 
+// Column sums over the 32 rows a warp holds (one row per lane, N columns per lane): recursive halving, so N = 16
+// costs 16 shuffles instead of 80.  On return lane L holds the sum of column  (N == 32 ? L : (L >> 1) & 15)  in v[0].
+template <int N>
+__device__ __forceinline__ void warp_colsum(float (&v)[N], int lane) {
+#pragma unroll
+  for (int n = N / 2, o = 16; n >= 1; n >>= 1, o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = up ? v[i] : v[i + n];
+      const float keep = up ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  if (N == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 template <int HD>
 struct TcCfg {
   static constexpr int ROWB = HD * 2;                    // bytes per row of a Q/K/V/dO tile
@@ -138,6 +155,7 @@ struct TcArgs {
   const float* lse2;
   const float* delta;
   bf16* dqkv;
+  float* dbias;       // optional fp32 [3*D]: += column sums of dQ | dK | dV (gradient of the qkv bias)
   long long ld_qkv, ld_o;
   int S, NB, H, D;
   float scale, scale_log2;
@@ -170,6 +188,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
   uint64_t* dp_full = bars + 14;   // [2] MMA -> softmax warps: dP^T of a sub-step is in TMEM
   uint64_t* pv_done = bars + 16;   // [2] PV issuer -> QK issuer: dV/dK of a sub-step have consumed P^T / dS^T
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  float* s_db = reinterpret_cast<float*>(bars + 20);   // [3 * HD] column sums of dQ | dK | dV of this head
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, seq = blockIdx.y;
@@ -196,6 +215,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  if (threadIdx.x < 3 * HD) s_db[threadIdx.x] = 0.f;
   // whole-head Q, dO, log-sum-exp and delta
   load_rows_async<HD>(sQ, qb, a.ld_qkv, 0, S_pad, S, threadIdx.x, TCB_THREADS);
   load_rows_async<HD>(sDO, dob, a.ld_o, 0, S_pad, S, threadIdx.x, TCB_THREADS);
@@ -375,6 +395,14 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
         *reinterpret_cast<uint4*>(dst + c) = o;
       }
     };
+    auto add_colsum = [&](const uint32_t (&r)[EC], float mul, int col0) {
+      float v[EC];
+#pragma unroll
+      for (int c = 0; c < EC; ++c) v[c] = __uint_as_float(r[c]);
+      warp_colsum<EC>(v, lane);
+      if (EC == 32) atomicAdd(&s_db[col0 + lane], v[0] * mul);
+      else if ((lane & 1) == 0) atomicAdd(&s_db[col0 + ((lane >> 1) & 15)], v[0] * mul);
+    };
     // dK_j / dV_j leave through group 0; group 1 only tracks the barrier phase (a waiter may not lag a phase)
     auto epilogue_dkv = [&](int j) {
       mbar_wait(dkv_full, (uint32_t)(j & 1));
@@ -391,6 +419,10 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
       if (kr < S) {
         store_row(dkb + (long long)kr * a.ld_qkv + half * EC, rk, a.scale);
         store_row(dvb + (long long)kr * a.ld_qkv + half * EC, rv, 1.0f);
+      }
+      if (a.dbias != nullptr) {   // rows at or beyond S hold exact zeros (P^T / dS^T are masked there)
+        add_colsum(rk, a.scale, HD + half * EC);
+        add_colsum(rv, 1.0f, 2 * HD + half * EC);
       }
     };
 
@@ -491,11 +523,14 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
       tmem_ld_wait();
       const int qr = i * 128 + row;
       if (qr < S) store_row(dqb + (long long)qr * a.ld_qkv + half * EC, rq, a.scale);
+      if (a.dbias != nullptr) add_colsum(rq, a.scale, half * EC);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (a.dbias != nullptr && threadIdx.x < 3 * HD)   // one atomic per column per CTA
+    atomicAdd(a.dbias + (threadIdx.x / HD) * a.D + h * HD + (threadIdx.x % HD), s_db[threadIdx.x]);
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
@@ -506,7 +541,7 @@ template <int HD>
 int launch_bwd(const TcArgs& a, int n_seq, cudaStream_t stream) {
   using C = TcCfg<HD>;
   const int S_pad = a.NB * 128;
-  const int smem = 1024 + 2 * a.NB * C::BLK_BYTES + 4 * C::BLK_BYTES + 2 * DS_TILE_BYTES + 2 * S_pad * 4 + 128;
+  const int smem = 1024 + 2 * a.NB * C::BLK_BYTES + 4 * C::BLK_BYTES + 2 * DS_TILE_BYTES + 2 * S_pad * 4 + 1024;
   cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
     avs_set_error("avs_attention_bwd(tc): cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
@@ -526,13 +561,14 @@ extern "C" void avs_debug_set_tc_trace(long long* p) { g_tc_trace = p; }
 // Returns -2 when the shape is outside what the TMEM budget covers (the caller then uses the mma.sync kernels of
 // attention.cu — both are CUDA paths of this library).  `delta` must already hold rowsum(dO * O).
 int avs_attention_bwd_tc(const void* qkv, long long ld_qkv, const void* dout, long long ld_o, const float* lse2,
-                         const float* delta, void* dqkv, int n_seq, int S, int H, int head_dim, void* stream) {
+                         const float* delta, void* dqkv, float* dbias, int n_seq, int S, int H, int head_dim,
+                         void* stream) {
   if (head_dim != 32 && head_dim != 64) return -2;
   const int NB = (S + 127) / 128;
   if (NB > (head_dim == 32 ? TcCfg<32>::MAX_NB : TcCfg<64>::MAX_NB)) return -2;
   TcArgs a = {};
   a.trace = g_tc_trace;
-  a.qkv = (const bf16*)qkv; a.dout = (const bf16*)dout; a.lse2 = lse2; a.delta = delta; a.dqkv = (bf16*)dqkv;
+  a.qkv = (const bf16*)qkv; a.dout = (const bf16*)dout; a.lse2 = lse2; a.delta = delta; a.dqkv = (bf16*)dqkv; a.dbias = dbias;
   a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.S = S; a.NB = NB; a.H = H; a.D = H * head_dim;
   a.scale = rsqrtf((float)head_dim);
   a.scale_log2 = a.scale * 1.4426950408889634f;

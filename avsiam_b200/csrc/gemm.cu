@@ -1,5 +1,6 @@
 // Host side of the tcgen05 GEMM: TMA descriptor encoding, tile/split-K selection, C-ABI entry.
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -9,7 +10,7 @@
 
 using namespace avs;
 
-static int g_desc_variant = 0;
+static int g_desc_variant = getenv("AVS_GEMM_DEBUG") ? atoi(getenv("AVS_GEMM_DEBUG")) : 0;
 extern "C" void avs_debug_set_desc_variant(int v) { g_desc_variant = v; }
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {

@@ -46,7 +46,7 @@ struct GemmArgs {
   long long ldc;
   int split_k;          // >=1; >1 requires EPI_OUT_ATOMIC
   int kb_per_split;     // k-blocks (of 64) per split
-  int desc_variant;     // debug: 1 swaps LBO/SBO of MN-major descriptors (probe only)
+  int desc_variant;     // debug bits: 1 swaps LBO/SBO of MN-major descriptors (probe only), 2 skips the TMA stores (timing)
   int stages;           // smem ring depth (runtime: whatever fits beside the epilogue staging buffers)
   int tma_epi;          // 1: bf16 C (and aux_out) leave through TMA stores, resid/aux_in arrive through TMA loads
   int has_in;           // tma_epi: a [M,N] bf16 input tile stream exists (resid or aux_in — never both)
@@ -231,8 +231,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // K-major: step 16 elements (32 B) inside the 128 B swizzle row; 8-row groups 1024 B apart.
     // MN-major: step 16 reduction rows (2 swizzle atoms = 2048 B); atoms along MN are BLOCK_K*128 B apart (LBO),
     //           8-row K groups 1024 B apart (SBO).
-    const uint32_t mn_lbo = args.desc_variant ? 1024 : GEMM_BLOCK_K * 128;
-    const uint32_t mn_sbo = args.desc_variant ? GEMM_BLOCK_K * 128 : 1024;
+    const uint32_t mn_lbo = (args.desc_variant & 1) ? 1024 : GEMM_BLOCK_K * 128;
+    const uint32_t mn_sbo = (args.desc_variant & 1) ? GEMM_BLOCK_K * 128 : 1024;
     const uint64_t da0 = (A_MAJOR == MAJOR_K) ? make_smem_desc(smem_u32(smem_a), 0, 1024)
                                               : make_smem_desc(smem_u32(smem_a), mn_lbo, mn_sbo);
     const uint64_t db0 = (B_MAJOR == MAJOR_K) ? make_smem_desc(smem_u32(smem_b), 0, 1024)
@@ -289,7 +289,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const bool has_in = tma_epi && args.has_in;
 
     // flat per-warp chunk sequence q = tile_iteration * CH + chunk; `in` tiles are prefetched two chunks ahead
+    const bool dbg_no_in = (args.desc_variant & 4) != 0;   // timing experiment: no in-stream TMA loads (wrong results)
     auto issue_in = [&](int q) {
+      if (dbg_no_in) return;
       const int t = blockIdx.x + (q / CH) * (int)gridDim.x;
       if (t >= num_tiles) return;
       const int mn = t / args.split_k;
@@ -384,7 +386,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
           uint4 in4[4];
           if (has_in) {
-            mbar_wait(&my_in_bar[q & 1], (uint32_t)((q >> 1) & 1));
+            if (!dbg_no_in) mbar_wait(&my_in_bar[q & 1], (uint32_t)((q >> 1) & 1));
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               in4[j] = *reinterpret_cast<const uint4*>(in_buf + (q & 1) * GEMM_EPI_BUF + epi_tile_off(lane, j));
@@ -437,7 +439,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             __syncwarp();
             if (lane == 0) {
               const int nc0 = nc - GEMM_EPI_CHUNK;   // first column of the pair
-              if (nc0 < args.N && m0 + quarter * 32 < args.M) {  // TMA clips the M / N tails of the box
+              if (nc0 < args.N && m0 + quarter * 32 < args.M && !(args.desc_variant & 2)) {  // TMA clips the M / N tails (bit 1: timing experiment, no stores)
                 tma_store_2d(&tma_c, out_buf, nc0, m0 + quarter * 32);
                 if (args.has_aux_out) tma_store_2d(&tma_aux, aux_buf, nc0, m0 + quarter * 32);
               }

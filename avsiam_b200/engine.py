@@ -292,9 +292,11 @@ class Engine:
                 for g, lse in zip(groups, lses):
                     delta = self._empty(g.n_seq, heads, g.S, dtype=F32)
                     r0, r1 = g.row0, g.row0 + g.rows
-                    ops.attention_bwd(qkv[r0:r1], o[r0:r1], do[r0:r1], lse, delta, dqkv[r0:r1], g.n_seq, g.S, heads, hd)
+                    ops.attention_bwd(qkv[r0:r1], o[r0:r1], do[r0:r1], lse, delta, dqkv[r0:r1], g.n_seq, g.S, heads, hd,
+                                      dbias=self.P.grad(pfx + "attn.qkv.bias"))   # qkv-bias gradient fused in
                 dln1 = do
-                self._linear_bwd(dqkv, ln1, pfx + "attn.qkv.weight", pfx + "attn.qkv.bias", M, 3 * D, D, dln1)
+                self._linear_bwd(dqkv, ln1, pfx + "attn.qkv.weight", pfx + "attn.qkv.bias", M, 3 * D, D, dln1,
+                                 skip_bias=True)
                 dx = self._empty(M, D)
                 self._ln_bwd_groups(dln1, x, mean1, rstd1, dx, dx1, groups, pfx, "norm1", D, dbias=xin.take_sink())
                 xin.g = dx

@@ -263,14 +263,17 @@ def attention_fwd(qkv, out, lse2, n_seq, S, H, head_dim):
                                             lse2.data_ptr(), n_seq, S, H, head_dim, _stream()), "avs_attention_fwd")
 
 
-def attention_bwd(qkv, out, dout, lse2, delta, dqkv, n_seq, S, H, head_dim):
+def attention_bwd(qkv, out, dout, lse2, delta, dqkv, n_seq, S, H, head_dim, dbias=None):
+    """dbias: optional fp32 [3*H*head_dim], += column sums of dQKV (the qkv-bias gradient)."""
     for t, n in ((qkv, "qkv"), (out, "out"), (dout, "dout"), (dqkv, "dqkv")):
         _chk(t, BF16, "attn_bwd." + n, contiguous=False)
     if dout.stride(0) != out.stride(0) or dqkv.stride(0) != qkv.stride(0):
         raise RuntimeError("attention_bwd: dout/out and dqkv/qkv must share row pitches")
+    if dbias is not None:
+        _chk(dbias, F32, "attn_bwd.dbias")
     _lib.check(_lib.lib().avs_attention_bwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), dout.data_ptr(),
-                                            out.stride(0), lse2.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), n_seq,
-                                            S, H, head_dim, _stream()), "avs_attention_bwd")
+                                            out.stride(0), lse2.data_ptr(), delta.data_ptr(), dqkv.data_ptr(),
+                                            _p(dbias), n_seq, S, H, head_dim, _stream()), "avs_attention_bwd")
 
 
 # --------------------------------------------------------------------------------------------- losses
@@ -399,7 +402,7 @@ def _work_attn_fwd(qkv, out, lse2, n_seq, S, H, hd):
     return 4.0 * n_seq * H * S * S * hd
 
 
-def _work_attn_bwd(qkv, out, dout, lse2, delta, dqkv, n_seq, S, H, hd):
+def _work_attn_bwd(qkv, out, dout, lse2, delta, dqkv, n_seq, S, H, hd, dbias=None):
     return 10.0 * n_seq * H * S * S * hd       # 5 S x S x hd products (QK^T, dO V^T, P^T dO, dS^T Q, dS K)
 
 
@@ -411,8 +414,8 @@ def _detail_gemm(a, b, out, M, N, K, **kw):
 
 
 def _detail_attn(name):
-    def f(*a):
-        n_seq, S, H, hd = a[-4:]
+    def f(*a, **k):
+        n_seq, S, H, hd = a[6:10] if name == "attention_bwd" else a[-4:]
         return f"{name} n_seq={n_seq} S={S} H={H} hd={hd}"
     return f
 

@@ -146,8 +146,11 @@ int avs_head_bwd(const float* dlogits, const float* xhat, const float* rstd, con
  * ---------------------------------------------------------------------------------------------- */
 int avs_attention_fwd(const void* qkv, long long ld_qkv, void* out, long long ld_o, float* lse2, int n_seq, int S,
                       int H, int head_dim, void* stream);
+/* dbias: optional fp32 [3*H*head_dim], += column sums of dQKV (gradient of attn.qkv.bias, cav_mae_base.py:51) —
+ * accumulated in the tcgen05 kernel's epilogues, otherwise one extra pass over dQKV */
 int avs_attention_bwd(const void* qkv, long long ld_qkv, const void* out, const void* dout, long long ld_o,
-                      const float* lse2, float* delta, void* dqkv, int n_seq, int S, int H, int head_dim, void* stream);
+                      const float* lse2, float* delta, void* dqkv, float* dbias, int n_seq, int S, int H, int head_dim,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Masked-MSE reconstruction loss, target read from the raw input (patchify + forward_mae_loss,

@@ -234,7 +234,11 @@ def test_attention_fwd_bwd(n_seq, S, H, hd):
     ref_dqkv = q5.grad.permute(1, 3, 0, 2, 4).reshape(n_seq * S, 3 * D)
     dqkv = torch.full_like(qkv, float("nan"))
     delta = torch.empty(n_seq, H, S, device=DEV)
-    ops.attention_bwd(qkv, out, dout, lse2, delta, dqkv, n_seq, S, H, hd)
+    dbias = torch.ones(3 * D, device=DEV)
+    ops.attention_bwd(qkv, out, dout, lse2, delta, dqkv, n_seq, S, H, hd, dbias=dbias)
+    # fused qkv-bias gradient: 1 + column sums of dQKV (accumulated; fp32 sums of the pre-rounding values)
+    ref_db = 1 + ref_dqkv.sum(0)
+    assert float((dbias - ref_db).abs().max()) <= 2e-2 * float(ref_dqkv.abs().sum(0).max()) + 1e-3
     for i, name in enumerate("qkv"):
         got, want = dqkv[:, i * D:(i + 1) * D].float(), ref_dqkv[:, i * D:(i + 1) * D]
         if S == 1 and name in "qk":   # softmax over one key is constant: dQ = dK = 0 exactly in the reference

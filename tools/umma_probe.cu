@@ -349,6 +349,23 @@ __global__ void __launch_bounds__(320, 1) probe_n256(long long* out, int reps, i
       for (int i = 0; i < 4; ++i) mbar_wait(&wbar[i], ph[i]);
       if (blockIdx.x == 0) out[1] = n * 32;   // in units of 512 B like the st.shared writers
     }
+  } else if (warp >= 2 && writers >= 100 && warp < 2 + (writers - 100)) {
+    // epilogue-like readers: tcgen05.ld 32x32b.x32 + wait in a loop while the MMA stream runs (writers = 100 + #warps)
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    long long n = 0, t_ld = 0;
+    uint32_t acc = 0;
+    while (!stop) {
+      uint32_t v[32];
+      const long long a0 = clock64();
+      tmem_ld_32x32b_x32(tl + (uint32_t)((n * 32) & 255), v);
+      tmem_ld_wait();
+      t_ld += clock64() - a0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc ^= v[i];
+      ++n;
+    }
+    if (acc == 0x12345u) out[15] = acc;
+    if (lane == 0 && blockIdx.x == 0 && warp == 2) { out[1] = n; out[2] = t_ld; }
   } else if (warp >= 2 && warp < 2 + writers) {
     // each warp streams 512 B per instruction into a private 16 KB region (different from the operand tiles)
     const uint32_t base = smem_u32(smem) + 64 * 1024 + (warp - 2) * 16 * 1024 + lane * 16;
@@ -375,6 +392,11 @@ void run_n256(long long* d_out, int writers) {
   cudaError_t e = cudaDeviceSynchronize();
   long long h[16];
   cudaMemcpy(h, d_out, 128, cudaMemcpyDeviceToHost);
+  if (writers >= 100) {
+    printf("SS N=256 K-major with %d warps looping tcgen05.ld.x32: %6.1f cycles / MMA (math 128); tcgen05.ld+wait = %6.1f cycles each  %s\n",
+           writers - 100, (double)h[0] / (reps * 4), h[1] ? (double)h[2] / (double)h[1] : 0.0, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    return;
+  }
   long long stores = 0;
   for (int i = 0; i < (writers < 0 ? 1 : writers); ++i) stores += h[1 + i];
   printf("SS N=256 K-major, %d writer warps: %6.1f cycles / MMA (math 128); concurrent st.shared traffic %5.1f B/cycle  %s\n",
@@ -461,7 +483,7 @@ int main() {
   run_batch("only S^T/dP^T (SS N=64) [model 387]", d_out, 0, 3);
   run_hs("kernel-order issue, fences only", d_out, 4);
   run_hs("kernel-order issue, handshake with instant responder", d_out, 5);
-  for (int w : {0, 4, -1}) run_n256(d_out, w);
+  for (int w : {0, 4, -1, 104, 108}) run_n256(d_out, w);
   for (int nw : {1, 4, 8, 16}) for (int b : {1, 2}) run_ldtm(d_out, nw, b);
   return 0;
 }
