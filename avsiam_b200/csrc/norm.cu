@@ -28,6 +28,16 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = o;
 }
 
+__device__ __forceinline__ void unpack8u(const uint4& u, float (&v)[8]) {
+  float2 f;
+  f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+}
+
+// One warp per row, software-pipelined: the 16-byte loads of the warp's NEXT row are in flight while the current
+// row is reduced and written (one row per warp in flight left the kernel latency-bound at ~3.5 TB/s).
 template <int NCH>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restrict__ x,
                                                             const float* __restrict__ gamma,
@@ -37,18 +47,28 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
                                                             int x_stride, int x_off, int y_stride, int y_off) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = D / 8;
-  for (long long r = (long long)blockIdx.x * 8 + warp; r < M; r += (long long)gridDim.x * 8) {
-    float v[NCH][8];
-    float sum = 0.f;
-    const long long xr = map_row(r, S, x_stride, x_off);
+  const long long stride = (long long)gridDim.x * 8;
+  long long r = (long long)blockIdx.x * 8 + warp;
+  uint4 cur[NCH], nxt[NCH];
+  auto issue = [&](long long row, uint4 (&dst)[NCH]) {
+    const long long xr = map_row(row, S, x_stride, x_off);
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       const int ci = lane + 32 * k;
-      if (ci < nchunks) {
-        load8(x + xr * D + ci * 8, v[k]);
+      dst[k] = (ci < nchunks) ? __ldg(reinterpret_cast<const uint4*>(x + xr * D + ci * 8)) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  if (r < M) issue(r, cur);
+  for (; r < M; r += stride) {
+    const bool more = (r + stride) < M;
+    if (more) issue(r + stride, nxt);
+    float v[NCH][8];
+    float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sum += v[k][j];
-      }
+    for (int k = 0; k < NCH; ++k) {
+      unpack8u(cur[k], v[k]);   // chunks beyond D were loaded as zeros
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[k][j];
     }
     const float mean = warp_sum(sum) / D;
     float sq = 0.f;
@@ -74,16 +94,20 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
       const int ci = lane + 32 * k;
       if (ci < nchunks) {
         float o[8];
-        const float4 g0 = *reinterpret_cast<const float4*>(gamma + ci * 8);
-        const float4 g1 = *reinterpret_cast<const float4*>(gamma + ci * 8 + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(beta + ci * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(beta + ci * 8 + 4);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ci * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + ci * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + ci * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + ci * 8 + 4));
         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
         const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = (v[k][j] - mean) * rstd * g[j] + b[j];
         store8(y + yr * D + ci * 8, o);
       }
+    }
+    if (more) {
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) cur[k] = nxt[k];
     }
   }
 }

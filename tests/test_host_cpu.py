@@ -208,3 +208,36 @@ def test_gather_layer_global_infonce_matches_single_process():
         # (DDP's 1/W average restores the global-loss gradient) — gather_layer.py:34-37
         assert torch.allclose(out[r][2], 2 * ea.grad[3 * r:3 * r + 3], rtol=1e-5, atol=1e-7)
         assert torch.allclose(out[r][3], 2 * ev.grad[3 * r:3 * r + 3], rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ checkpoints
+def test_checkpoint_roundtrip_pt_to_ft_and_weight_average(tmp_path):
+    """`module.`-prefixed save/load, strict=False PT -> FT transfer (run_cavmae_ft_base.py:245-258) and
+    wa_model (run_cavmae_ft_base.py:169-180) on the parameter containers (no GPU needed)."""
+    import dataclasses
+    from avsiam_b200 import CAVMAE_BASE, CAVMAEFT_BASE, Dims
+    from avsiam_b200 import checkpoint as ck
+    from oracle import avsiam_oracle as O
+    d = Dims(**dataclasses.asdict(O.TINY))
+    pt = CAVMAE_BASE(dims=d)
+    pt.load_state_dict(O.with_aliases(O.init_state(O.TINY, seed=3)))
+    path = str(tmp_path / "models" / "audio_model.1.pth")
+    ck.save_model(pt, path)
+    saved = torch.load(path)
+    assert all(k.startswith("module.") for k in saved) and len(saved) == len(pt.state_dict())
+    ft = CAVMAEFT_BASE(label_dim=7, dims=d)
+    missing, unexpected = ck.load_pretrained(ft, path, create_fusion=True)
+    assert all(k.startswith("module.mlp_head") for k in missing)            # only the new heads are missing
+    assert any(k.startswith("module.decoder_") for k in unexpected) and any(k.startswith("module.ast_base.") for k in unexpected)
+    assert torch.equal(ft.vit_base.blocks[1].attn.qkv.weight, pt.vit_base.blocks[1].attn.qkv.weight)
+    assert torch.equal(ft.mm_layer_2.mlp.fc1.weight, ft.vit_base.blocks[O.TINY.depth - 1].mlp.fc1.weight)  # __create_fusion__
+    # weight averaging over two epochs
+    pt2 = CAVMAE_BASE(dims=d)
+    pt2.load_state_dict(O.with_aliases(O.init_state(O.TINY, seed=4)))
+    ck.save_model(pt2, str(tmp_path / "models" / "audio_model.2.pth"))
+    avg = ck.wa_model(str(tmp_path), 1, 2)
+    k = "module.vit_base.blocks.0.mlp.fc2.weight"
+    want = (pt.state_dict()[k[7:]] + pt2.state_dict()[k[7:]]) / 2
+    assert torch.allclose(avg[k], want, atol=1e-7)
+    m3 = CAVMAE_BASE(dims=d)
+    assert ck.load_model(m3, avg) == ([], [])
