@@ -7,11 +7,12 @@ libavsiam_b200.so and raises if it is missing (there is no CPU / PyTorch fallbac
 from .cav_mae_base import CAVMAE_BASE, _Dims as Dims  # noqa: F401
 from .cav_mae_ft import CAVMAEFT_BASE  # noqa: F401
 from . import checkpoint  # noqa: F401
+from .fbank import wav2fbank  # noqa: F401
 from .ddp import B200DDP, GradSync  # noqa: F401
 from .gather_layer import GatherLayer  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 
-__all__ = ["CAVMAE_BASE", "CAVMAEFT_BASE", "Dims", "GatherLayer", "FusedAdam", "B200DDP", "GradSync", "patch"]
+__all__ = ["CAVMAE_BASE", "CAVMAEFT_BASE", "Dims", "GatherLayer", "wav2fbank", "FusedAdam", "B200DDP", "GradSync", "patch"]
 __version__ = "0.1.0"
 
 

@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, seq = blockIdx.y;
+  if (threadIdx.x == 0) TC_TRACE(17, 0);
   const long long row_base = (long long)seq * S;
   const bf16* qb = a.qkv + row_base * a.ld_qkv + h * HD;
   const bf16* dob = a.dout + row_base * a.ld_o + h * HD;
@@ -219,6 +220,9 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
   // whole-head Q, dO, log-sum-exp and delta
   load_rows_async<HD>(sQ, qb, a.ld_qkv, 0, S_pad, S, threadIdx.x, TCB_THREADS);
   load_rows_async<HD>(sDO, dob, a.ld_o, 0, S_pad, S, threadIdx.x, TCB_THREADS);
+  // the first key block comes in with the same cooperative load (one exposed HBM round trip per CTA, not two)
+  load_rows_async<HD>(sK, qb + a.D, a.ld_qkv, 0, 128, S, threadIdx.x, TCB_THREADS);
+  load_rows_async<HD>(sV, qb + 2 * a.D, a.ld_qkv, 0, 128, S, threadIdx.x, TCB_THREADS);
   {
     const long long sb = ((long long)seq * a.H + h) * S;
     for (int i = threadIdx.x; i < S_pad; i += TCB_THREADS) {
@@ -232,11 +236,13 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (threadIdx.x == 0) TC_TRACE(17, 1);
   const int T = NB * NB * 2;  // 64-query sub-steps
 
   if (warp == 0) {
     // ============================ loader: K_j, V_j ============================
-    for (int j = 0; j < NB; ++j) {
+    if (lane == 0) mbar_arrive(&kv_full[0]);   // block 0 was loaded (and fenced) by the whole CTA above
+    for (int j = 1; j < NB; ++j) {
       if (j >= 2) mbar_wait(&kv_empty[j & 1], (uint32_t)(((j >> 1) - 1) & 1));
       load_rows_async<HD>(sK + (j & 1) * C::BLK_BYTES, qb + a.D, a.ld_qkv, j * 128, 128, S, lane, 32);
       load_rows_async<HD>(sV + (j & 1) * C::BLK_BYTES, qb + 2 * a.D, a.ld_qkv, j * 128, 128, S, lane, 32);
@@ -527,8 +533,10 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
     }
   }
 
+  if (threadIdx.x == 96) TC_TRACE(17, 2);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TC_TRACE(17, 3);
   if (a.dbias != nullptr && threadIdx.x < 3 * HD)   // one atomic per column per CTA
     atomicAdd(a.dbias + (threadIdx.x / HD) * a.D + h * HD + (threadIdx.x % HD), s_db[threadIdx.x]);
   if (warp == 0) {

@@ -128,6 +128,17 @@ int avs_seq_mean_bwd(const float* dpool, void* dx, int n_seq, int seg_len, int D
                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Audio front end: batch kaldi log-mel filterbank + loader post-processing (src/dataloader.py:287,323-339,506:
+ * waveform - mean, torchaudio.compliance.kaldi.fbank(htk_compat, hanning, 128 bins, 25 ms / 10 ms, dither 0),
+ * zero-pad / crop to target_len, (x - norm_mean) / norm_std).  16 kHz mono.
+ *   wav fp32 [B, L] (row pitch ld);  melw fp32 [128, 257] triangular weights and mel_range int16 [128, 2] (first /
+ *   last non-zero FFT bin of each filter), both prepared by the host wrapper as kaldi's get_mel_banks defines them;
+ *   mean_scratch fp32 [B] (only when remove_mean);  out fp32 [B, target_len, 128].
+ * ------------------------------------------------------------------------------------------------ */
+int avs_fbank(const float* wav, long long ld, int B, int L, int remove_mean, const float* melw, const short* mel_range,
+              float* mean_scratch, float* out, int target_len, float norm_mean, float norm_std, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Finetune classification heads: logits = Linear(LayerNorm(x)), x fp32 [B, D] pooled features
  * (nn.Sequential(nn.LayerNorm(D), nn.Linear(D, C)): mlp_head / mlp_head_a / mlp_head_mm, cav_mae_base.py:813-815).
  * All fp32, parameters read from the fp32 master copy.  fwd saves xhat [B,D], rstd [B], y [B,D] for bwd.

@@ -119,3 +119,24 @@ def test_ft_forward_backward_matches_reference(ft_cases, idx):
     for k, gref in c["grad_full"].items():
         cos = torch.nn.functional.cosine_similarity(sd[k].grad.flatten().double(), gref.flatten().double(), dim=0)
         assert float(cos) > 0.99999, (k, float(cos))
+
+
+# ------------------------------------------------------------------------------------------------ audio front end
+def test_fbank_oracle_matches_torchaudio_golden(golden_dir):
+    """oracle/fbank_oracle.py (numpy restatement of kaldi fbank) vs torchaudio.compliance.kaldi.fbank called with the
+    reference's arguments (src/dataloader.py:323). torchaudio works in fp32, the oracle in fp64: agreement to 2e-2 in the
+    log domain (the difference sits in near-silent bins), and to 1e-3 on bins above the noise floor."""
+    import numpy as np
+    from oracle import fbank_oracle as FB
+    from oracle.make_golden_fbank import synth_wave
+    for c in torch.load(os.path.join(golden_dir, "fbank_kaldi.pt"), weights_only=False):
+        w = synth_wave(c["seed"], c["n"])
+        fb = FB.kaldi_fbank((w - w.mean()).numpy())
+        ref = c["fbank"].numpy()
+        assert fb.shape == ref.shape == (FB.num_frames(c["n"]), 128)
+        assert float(np.abs(fb - ref).max()) < 2e-2
+        loud = ref > -6.0
+        assert float(np.abs(fb - ref)[loud].max()) < 1e-3
+    # pad / crop / normalise (dataloader.py:331-339,506)
+    out = FB.wav2fbank(synth_wave(2, 48017).numpy(), target_length=1024)
+    assert out.shape == (1024, 128) and abs(float(out[500, 3]) - (0.0 + 5.081) / 4.4849) < 1e-6

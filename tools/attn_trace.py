@@ -4,7 +4,8 @@ import sys, os, ctypes, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from avsiam_b200 import ops, _lib
 lib = ctypes.CDLL(os.path.join(os.path.dirname(_lib.__file__), "libavsiam_b200.so"))
-n_seq, S, H, hd = 64, 708, 16, 32
+import sys as _s
+n_seq, S, H, hd = (64, 708, 16, 32) if len(_s.argv) < 2 else (256, int(_s.argv[1]), 12, 64)
 D = H * hd
 qkv = torch.randn(n_seq * S, 3 * D, device="cuda").bfloat16()
 out = torch.empty(n_seq * S, D, device="cuda", dtype=torch.bfloat16)
@@ -28,4 +29,5 @@ for u in range(0, 26):
 print("softmax group A | B per block-step n: [top, got S^T, got dP^T, arrived p_full]")
 for n in range(0, 13):
     print(n, [rel(k, n) for k in (3, 4, 5, 6)], "|", [rel(k, n) for k in (7, 8, 9, 10)])
+print("CTA lifetime stamps [entry, after prologue sync, a softmax warp done, after final sync]:", [rel(17, i) for i in range(4)])
 print("total cycles", int(tr.max()) - t0)
