@@ -5,7 +5,8 @@ Kept from the reference: constructor signature (:746-747), parameter names / che
 my_blocks.* aliases, my_patch_embed*, mlp_head{,_a,_mm,_mm_v2}, mm_layer_{1,2}; `strict=False` loading of a
 pretraining checkpoint works because the shared names coincide), `__create_fusion__` (:823-825) and
 `forward(a, v, mode, is_eval=False)` for the modes the training / evaluation loops use:
-  'audioonly' (:828-849), 'videoonly' (:852-880), 'mm_grad' training (:983-1036) and evaluation (:936-980).
+  'audioonly' (:828-849), 'videoonly' (:852-880), 'retrieval' (:883-917), 'mm_grad' training (:983-1036) and
+  evaluation (:936-980).
 No masking, no decoder: full sequences (512 audio tokens, 196 tokens per frame) through the 12 shared blocks with
 the per-modality LayerNorms, final norms, token means, LayerNorm+Linear heads; 'mm_grad' adds the two fusion
 blocks over the concatenated 708-token sequence and the [mean_a | mean_v] head.  The returned logits are fp32 and
@@ -192,8 +193,8 @@ class CAVMAEFT_BASE(nn.Module):
         ref = a if a is not None else v
         if not ref.is_cuda:
             raise RuntimeError("avsiam_b200.CAVMAEFT_BASE runs on CUDA (sm_100a) only — there is no CPU path")
-        if mode not in ("audioonly", "videoonly", "mm_grad"):
-            raise ValueError(f"CAVMAEFT_BASE.forward: mode {mode!r} is not implemented (audioonly | videoonly | mm_grad)")
+        if mode not in ("audioonly", "videoonly", "mm_grad", "retrieval"):
+            raise ValueError(f"CAVMAEFT_BASE.forward: unknown mode {mode!r} (audioonly | videoonly | mm_grad | retrieval)")
         dev = ref.device
         eng = self._ensure_engine(dev)
         arena = self._arena
@@ -201,8 +202,10 @@ class CAVMAEFT_BASE(nn.Module):
         want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         tape: Optional[list] = [] if want_grad else None
         arena.refresh_shadow()
-        use_a = mode in ("audioonly", "mm_grad")
-        use_v = mode in ("videoonly", "mm_grad")
+        if mode == "retrieval":
+            tape = None                      # feature extraction (retrieval.py runs it under no_grad)
+        use_a = mode in ("audioonly", "mm_grad", "retrieval")
+        use_v = mode in ("videoonly", "mm_grad", "retrieval")
         B = ref.shape[0]
         audio = a.contiguous().float() if use_a else None
         frames = None
@@ -229,6 +232,14 @@ class CAVMAEFT_BASE(nn.Module):
         elif mode == "videoonly":
             _, pooled = eng.final_norm(tape, x, groups, norm_of, cat=False, pool=True)
             outs.append(eng.head(tape, pooled[0], "mlp_head"))
+        elif mode == "retrieval":
+            # :883-917 — normalised token features of the audio clip and of frame 5 (`return a, v[:, 5]`)
+            y, _ = eng.final_norm(None, x, groups, norm_of, cat=False, pool=False)
+            if T <= 5:
+                raise ValueError("mode 'retrieval' returns v[:, 5]: it needs at least 6 frames per sample")
+            ya = y.t[:B * d.Ta].view(B, d.Ta, -1).float()
+            yv = y.t[B * d.Ta:].view(B, T, d.Tv, -1)[:, 5].float()
+            return ya, yv
         elif not is_eval:
             y, pooled = eng.final_norm(tape, x, groups, norm_of, cat=True, pool=True)
             out_a = eng.head(tape, pooled[0], "mlp_head_a")

@@ -142,6 +142,13 @@ def test_ft_eval_paths_and_fused_adam():
             ref = O.ft_head(torch.cat((av[:, :d.Ta].mean(1), av[:, d.Ta:].mean(1)), -1), sd, "mlp_head_mm")
             assert float((out[:, t].cpu() - ref).abs().max()) <= 2e-2 * float(ref.abs().max()) + 2e-3
         assert model(audio.to(DEV), None, "audioonly", is_eval=True).shape == (2, 1, 11)
+        # retrieval features (:883-917): normalised audio tokens and the tokens of frame 5
+        audio6, video6, _ = synth_ft_inputs(2, 6, d, 78, 11)
+        fa, fv = model(audio6.to(DEV), video6.to(DEV), "retrieval")
+        ra = O.ft_encode_audio(audio6, sd, d)
+        rv = O.ft_encode_video(video6, sd, d).reshape(2, 6, d.Tv, -1)[:, 5]
+        assert fa.shape == ra.shape and fv.shape == rv.shape
+        assert float((fa.cpu() - ra).norm() / ra.norm()) < 1e-2 and float((fv.cpu() - rv).norm() / rv.norm()) < 1e-2
     # a few optimisation steps through the fused arena optimizer reduce the loss
     model.direct_grads = True
     opt = FusedAdam(model.parameters(), lr=1e-3, weight_decay=5e-7, betas=(0.95, 0.999), model=model)

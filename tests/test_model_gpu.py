@@ -220,3 +220,24 @@ def test_state_dict_round_trip_keeps_arena_binding():
         l2 = float(model(audio.to(DEV), imgs.to(DEV), mae_loss_weight=1.0, contrast_loss_weight=0.0)[0])
     # the loss reductions use fp32 atomics (summation order varies run to run): equal up to fp32 rounding
     assert abs(l0 - l1) > 1e-4 * abs(l0) and l2 == pytest.approx(l0, rel=1e-5)
+
+
+def test_wide_geometry_against_oracle():
+    """A two-block model with ViT-L's widths (embed 1024, 16 heads of 64, decoder 512 / 16 heads — BASELINE config 5
+    geometry) exercises the D = 1024 LayerNorm / GEMM / attention instantiations end to end."""
+    d = dataclasses.replace(O.TINY, embed_dim=1024, heads=16, dec_dim=512, dec_heads=16)
+    model, sd = make_model(d, "single_pass")
+    B = 2
+    audio, imgs = synth_inputs(B, d, 55)
+    plan = O.make_mask_plan(B, d, 56, two_pass=False)
+    ref, state = run_oracle(O.forward_single_pass, audio, imgs, sd, d, plan, mae_loss_weight=1.0,
+                            contrast_loss_weight=0.01)
+    model.mask_plan = plan
+    out = model(audio.to(DEV), imgs.to(DEV), 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+    check_losses(out, ref)
+    out[0].backward()
+    named = dict(model.named_parameters())
+    want = {k for k, v in state.items() if v.grad is not None}
+    low = [(k, cos(named[k].grad, state[k].grad)) for k in want if float(state[k].grad.norm()) > 1e-9]
+    low = [(k, c) for k, c in low if c < GRAD_COS_MIN]
+    assert not low, low[:8]
