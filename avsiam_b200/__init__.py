@@ -8,11 +8,12 @@ from .cav_mae_base import CAVMAE_BASE, _Dims as Dims  # noqa: F401
 from .cav_mae_ft import CAVMAEFT_BASE  # noqa: F401
 from . import checkpoint  # noqa: F401
 from .fbank import wav2fbank  # noqa: F401
+from .stats import calculate_stats, d_prime  # noqa: F401
 from .ddp import B200DDP, GradSync  # noqa: F401
 from .gather_layer import GatherLayer  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 
-__all__ = ["CAVMAE_BASE", "CAVMAEFT_BASE", "Dims", "GatherLayer", "wav2fbank", "FusedAdam", "B200DDP", "GradSync", "patch"]
+__all__ = ["CAVMAE_BASE", "CAVMAEFT_BASE", "Dims", "GatherLayer", "wav2fbank", "calculate_stats", "d_prime", "FusedAdam", "B200DDP", "GradSync", "patch"]
 __version__ = "0.1.0"
 
 

@@ -139,6 +139,15 @@ int avs_fbank(const float* wav, long long ld, int B, int L, int remove_mean, con
               float* mean_scratch, float* out, int target_len, float norm_mean, float norm_std, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Evaluation statistics (src/utilities/stats.py:11-68): per-class average precision and ROC-AUC with scikit-learn's
+ * tie-grouped definitions, and top-1 accuracy.  output / target fp32 [N, C] row-major (target > 0 = positive);
+ * pos_scratch fp32 [C, N]; ap / auc fp32 [C] (classes without a positive or without a negative: auc = -1, ap = 0 / 1);
+ * hits int32 [1], += number of samples whose argmax(output) == argmax(target) (caller zeroes it).
+ * ------------------------------------------------------------------------------------------------ */
+int avs_eval_stats(const float* output, const float* target, int N, int C, float* pos_scratch, float* ap, float* auc,
+                   int* hits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Finetune classification heads: logits = Linear(LayerNorm(x)), x fp32 [B, D] pooled features
  * (nn.Sequential(nn.LayerNorm(D), nn.Linear(D, C)): mlp_head / mlp_head_a / mlp_head_mm, cav_mae_base.py:813-815).
  * All fp32, parameters read from the fp32 master copy.  fwd saves xhat [B,D], rstd [B], y [B,D] for bwd.

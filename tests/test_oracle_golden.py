@@ -140,3 +140,17 @@ def test_fbank_oracle_matches_torchaudio_golden(golden_dir):
     # pad / crop / normalise (dataloader.py:331-339,506)
     out = FB.wav2fbank(synth_wave(2, 48017).numpy(), target_length=1024)
     assert out.shape == (1024, 128) and abs(float(out[500, 3]) - (0.0 + 5.081) / 4.4849) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ evaluation statistics
+def test_stats_oracle_matches_sklearn_golden(golden_dir):
+    """oracle/stats_oracle.py vs the scikit-learn calls of src/utilities/stats.py:11-68 (including heavy score ties)."""
+    import numpy as np
+    from oracle import stats_oracle as S
+    from oracle.make_golden_stats import synth_eval
+    for c in torch.load(os.path.join(golden_dir, "eval_stats.pt"), weights_only=False):
+        o, t = synth_eval(c["seed"], c["n"], c["c"], c["ties"])
+        ap, auc, acc = S.calculate_stats(o, t)
+        assert np.abs(ap - c["AP"].numpy()).max() < 1e-12 and np.abs(auc - c["auc"].numpy()).max() < 1e-12
+        assert acc == c["acc"]
+    assert abs(S.d_prime(0.9) - 1.8123876) < 1e-6          # scipy.stats.norm.ppf(0.9) * sqrt(2)
