@@ -110,6 +110,12 @@ __device__ __forceinline__ void warp_colsum(float (&v)[N], int lane) {
   if (N == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+__device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;\n" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+
 template <int HD>
 struct TcCfg {
   static constexpr int ROWB = HD * 2;                    // bytes per row of a Q/K/V/dO tile
@@ -484,17 +490,15 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
                        : "=f"(dl.x), "=f"(dl.y), "=f"(dl.z), "=f"(dl.w) : "r"(s_delta_u + qoff + (cc * 16 + c) * 4));
           const uint32_t w0 = pw[cc * 8 + c / 2], w1 = pw[cc * 8 + c / 2 + 1];
-          // the bf16-rounded probabilities (exactly what the dV product uses), widened back to fp32
-          const float p0 = __uint_as_float(w0 << 16), p1 = __uint_as_float(w0 & 0xffff0000u);
-          const float p2 = __uint_as_float(w1 << 16), p3 = __uint_as_float(w1 & 0xffff0000u);
-          const float d0 = p0 * (__uint_as_float(dr[c]) - dl.x);
-          const float d1 = p1 * (__uint_as_float(dr[c + 1]) - dl.y);
-          const float d2 = p2 * (__uint_as_float(dr[c + 2]) - dl.z);
-          const float d3 = p3 * (__uint_as_float(dr[c + 3]) - dl.w);
+          // dS = P o (dP - delta) in packed bf16 (HMUL2.BF16): P is already the bf16-rounded probability the dV product
+          // uses; the difference is rounded to bf16 once more, the product once — the softmax warps are issue-bound and
+          // this is 8 instead of 14 instructions per 4 elements
+          const uint32_t e0 = pack_bf16x2(__uint_as_float(dr[c]) - dl.x, __uint_as_float(dr[c + 1]) - dl.y);
+          const uint32_t e1 = pack_bf16x2(__uint_as_float(dr[c + 2]) - dl.z, __uint_as_float(dr[c + 3]) - dl.w);
           st[c / 2] = w0;
           st[c / 2 + 1] = w1;
-          st[8 + c / 2] = pack_bf16x2(d0, d1);
-          st[8 + c / 2 + 1] = pack_bf16x2(d2, d3);
+          st[8 + c / 2] = hmul2_bf16(w0, e0);
+          st[8 + c / 2 + 1] = hmul2_bf16(w1, e1);
         }
         tmem_st_32x32b_x16(tDP + cc * 16, st);
 #pragma unroll
