@@ -181,26 +181,28 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const AttnArgs
       gemm_a_tT<HD, NT>(s, qf, sK, kv0, lane);
       const bool tail = kv0 + 8 * NT > S;
       float mx0 = -INFINITY, mx1 = -INFINITY;
+      // the row max is taken on the raw scores (scale > 0 commutes with max), so that scaling and max subtraction
+      // are ONE FFMA per element in the exponent below
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
+        if (tail) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          s[nt][j] *= a.scale_log2;
-          if (tail && (kv0 + nt * 8 + (lane & 3) * 2 + (j & 1)) >= S) s[nt][j] = -INFINITY;
+          for (int j = 0; j < 4; ++j)
+            if ((kv0 + nt * 8 + (lane & 3) * 2 + (j & 1)) >= S) s[nt][j] = -INFINITY;
         }
         mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
         mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
       }
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float nm0 = fmaxf(m0, mx0), nm1 = fmaxf(m1, mx1);
+      const float nm0 = fmaxf(m0, mx0 * a.scale_log2), nm1 = fmaxf(m1, mx1 * a.scale_log2);
       const float corr0 = exp2f(m0 - nm0), corr1 = exp2f(m1 - nm1);
       m0 = nm0; m1 = nm1;
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        s[nt][0] = exp2f(s[nt][0] - m0); s[nt][1] = exp2f(s[nt][1] - m0);
-        s[nt][2] = exp2f(s[nt][2] - m1); s[nt][3] = exp2f(s[nt][3] - m1);
+        s[nt][0] = exp2f(fmaf(s[nt][0], a.scale_log2, -m0)); s[nt][1] = exp2f(fmaf(s[nt][1], a.scale_log2, -m0));
+        s[nt][2] = exp2f(fmaf(s[nt][2], a.scale_log2, -m1)); s[nt][3] = exp2f(fmaf(s[nt][3], a.scale_log2, -m1));
         rs0 += s[nt][0] + s[nt][1];
         rs1 += s[nt][2] + s[nt][3];
       }
