@@ -51,6 +51,10 @@ SIGNATURES = {
     "avs_seq_mean_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
     "avs_seq_mean_bwd": [_P, _P, _I, _I, _I, _I, _I, _P],
     "avs_eval_stats": [_P, _P, _I, _I, _P, _P, _P, _P, _P],
+    "avs_bce_with_logits": [_P, _P, _P, _P, _L, _P],
+    "avs_cross_entropy_prob": [_P, _P, _P, _P, _I, _I, _P],
+    "avs_cosine_sim": [_P, _P, _I, _I, _I, _P, _P, _P],
+    "avs_retrieval_ranks": [_P, _I, _P, _P, _P],
     "avs_fbank": [_P, _L, _I, _I, _I, _P, _P, _P, _P, _I, _F, _F, _P],
     "avs_head_fwd": [_P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "avs_head_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],

@@ -148,6 +148,28 @@ int avs_eval_stats(const float* output, const float* target, int N, int C, float
                    int* hits, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Classification losses of the finetune loop (traintest_ft_base.py:106-109,148-158), mean reduction, fp32:
+ *   avs_bce_with_logits    nn.BCEWithLogitsLoss()(logits, target), n = B*C elements
+ *   avs_cross_entropy_prob nn.CrossEntropyLoss()(logits [B,C], target [B,C]) with probability targets (the loader's
+ *                          label vectors, dataloader.py:497-503; they need not sum to 1)
+ * *loss += the loss (caller zeroes it); dlogits (optional) = d loss / d logits.
+ * ------------------------------------------------------------------------------------------------ */
+int avs_bce_with_logits(const float* logits, const float* target, float* loss, float* dlogits, long long n,
+                        void* stream);
+int avs_cross_entropy_prob(const float* logits, const float* target, float* loss, float* dlogits, int B, int C,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Retrieval (retrieval.py:27-52).  avs_cosine_sim replaces get_sim_mat's Python double loop:
+ *   sim[i, j] = (a_i . b_j) / (|a_i| |b_j|), a fp32 [n, d], b fp32 [m, d], sim fp32 [n, m]; norm_scratch fp32 [n + m].
+ * avs_retrieval_ranks gives what compute_metrics reads off its row sort of a square sim [n, n]:
+ *   greater[i] = #{j : sim[i,j] > sim[i,i]},  equal[i] = #{j : sim[i,j] == sim[i,i]} (>= 1, the diagonal itself);
+ *   the sorted positions holding the diagonal's value are greater[i] .. greater[i] + equal[i] - 1.
+ * ------------------------------------------------------------------------------------------------ */
+int avs_cosine_sim(const float* a, const float* b, int n, int m, int d, float* norm_scratch, float* sim, void* stream);
+int avs_retrieval_ranks(const float* sim, int n, int* greater, int* equal, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Finetune classification heads: logits = Linear(LayerNorm(x)), x fp32 [B, D] pooled features
  * (nn.Sequential(nn.LayerNorm(D), nn.Linear(D, C)): mlp_head / mlp_head_a / mlp_head_mm, cav_mae_base.py:813-815).
  * All fp32, parameters read from the fp32 master copy.  fwd saves xhat [B,D], rstd [B], y [B,D] for bwd.

@@ -211,6 +211,21 @@ def test_gather_layer_global_infonce_matches_single_process():
 
 
 # ------------------------------------------------------------------------------------------------ checkpoints
+def _concat_case(rank, world):
+    from avsiam_b200.evaluate import distributed_concat
+    t = torch.arange(rank * 6, rank * 6 + 6, dtype=torch.float32).reshape(3, 2)
+    return (distributed_concat(t, 5),)
+
+
+def test_distributed_concat_gathers_in_rank_order_and_truncates():
+    """traintest_cavmae_base.py:21-26: all ranks' rows, rank order, cut to the dataset size."""
+    out = _run2("_concat_case")
+    want = torch.arange(10, dtype=torch.float32).reshape(5, 2)
+    assert torch.equal(out[0][0], want) and torch.equal(out[1][0], want)
+    from avsiam_b200.evaluate import distributed_concat
+    assert torch.equal(distributed_concat(want, 3), want[:3])          # no process group: single-rank identity
+
+
 def test_checkpoint_roundtrip_pt_to_ft_and_weight_average(tmp_path):
     """`module.`-prefixed save/load, strict=False PT -> FT transfer (run_cavmae_ft_base.py:245-258) and
     wa_model (run_cavmae_ft_base.py:169-180) on the parameter containers (no GPU needed)."""

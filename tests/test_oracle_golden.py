@@ -154,3 +154,26 @@ def test_stats_oracle_matches_sklearn_golden(golden_dir):
         assert np.abs(ap - c["AP"].numpy()).max() < 1e-12 and np.abs(auc - c["auc"].numpy()).max() < 1e-12
         assert acc == c["acc"]
     assert abs(S.d_prime(0.9) - 1.8123876) < 1e-6          # scipy.stats.norm.ppf(0.9) * sqrt(2)
+
+
+# ------------------------------------------------------------------------------------------------ evaluation path
+def test_eval_oracle_matches_reference_retrieval_and_torch_losses(golden_dir):
+    """oracle/eval_oracle.py vs the reference's own get_sim_mat / compute_metrics (src/retrieval.py:27-52, run at
+    fixture-generation time) and torch's BCEWithLogitsLoss / CrossEntropyLoss (traintest_ft_base.py:106-109)."""
+    import numpy as np
+    from oracle import eval_oracle as E
+    from oracle.make_golden_eval import synth_features, synth_logits
+    g = torch.load(os.path.join(golden_dir, "eval_path.pt"), weights_only=False)
+    for c in g["retrieval"]:
+        a, v = synth_features(c["seed"], c["n"], c["d"], c["dup"], c["noise"])
+        assert np.abs(E.sim_mat(a, v) - c["sim"].double().numpy()).max() < 1e-6
+        assert E.compute_metrics(c["sim"].numpy()) == c["metrics"]            # ties listed like np.where does
+    assert any(c["metrics"]["MR"] > 1 for c in g["retrieval"])
+    for c in g["loss"]:
+        x, y = synth_logits(c["seed"], c["B"], c["C"], c["smooth"])
+        for name, fn in (("bce", E.bce_with_logits), ("ce", E.cross_entropy_prob)):
+            loss, grad = fn(x, y)
+            assert abs(loss - c[name]) < 1e-9 * max(1.0, abs(c[name]))
+            assert np.abs(grad - c[name + "_grad"].double().numpy()).max() < 1e-8
+    parts = [np.arange(6).reshape(3, 2), np.arange(6, 12).reshape(3, 2)]
+    assert E.distributed_concat(parts, 5).tolist() == np.arange(10).reshape(5, 2).tolist()
