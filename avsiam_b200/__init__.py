@@ -6,7 +6,7 @@ libavsiam_b200.so and raises if it is missing (there is no CPU / PyTorch fallbac
 """
 from .cav_mae_base import CAVMAE_BASE, _Dims as Dims  # noqa: F401
 from .cav_mae_ft import CAVMAEFT_BASE  # noqa: F401
-from . import checkpoint, evaluate, losses  # noqa: F401
+from . import augment, checkpoint, evaluate, losses  # noqa: F401
 from .fbank import wav2fbank  # noqa: F401
 from .stats import calculate_stats, d_prime  # noqa: F401
 from .ddp import B200DDP, GradSync  # noqa: F401

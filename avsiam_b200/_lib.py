@@ -55,6 +55,9 @@ SIGNATURES = {
     "avs_cross_entropy_prob": [_P, _P, _P, _P, _I, _I, _P],
     "avs_cosine_sim": [_P, _P, _I, _I, _I, _P, _P, _P],
     "avs_retrieval_ranks": [_P, _I, _P, _P, _P],
+    "avs_fbank_augment": [_P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P],
+    "avs_frames_preprocess": [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "avs_mix_frames": [_P, _P, _P, _I, _L, _P],
     "avs_fbank": [_P, _L, _I, _I, _I, _P, _P, _P, _P, _I, _F, _F, _P],
     "avs_head_fwd": [_P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "avs_head_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],

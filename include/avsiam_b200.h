@@ -139,6 +139,27 @@ int avs_fbank(const float* wav, long long ld, int B, int L, int remove_mean, con
               float* mean_scratch, float* out, int target_len, float norm_mean, float norm_std, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Input pipeline, per-sample transforms of AudiosetDataset.__getitem__ batched on the device.
+ * avs_fbank_augment (src/dataloader.py:491-516): SpecAugment bands filled with 0.0, (x - mean) / std (unless
+ *   skip_norm), + (noise * noise_scale[b]) / 10 (noise NULL = off; noise_scale = the loader's np.random.rand()), torch.roll along time.  fbank / noise / out fp32 [B, T, F]
+ *   (F % 4 == 0, out != fbank); params int32 [B, 6] = f0, f1, t0, t1 (bands [start, end)), shift, unused.
+ * avs_frames_preprocess (:152-155,455-456): frames uint8 [N, C, H, W] -> / 255 -> antialiased bicubic resize to
+ *   [out_h, out_w] -> (x - mean[c]) / std[c]; fp32 out [N, C, out_h, out_w]; N * C <= 65535 per call.
+ *   wx fp32 [out_w, taps_x], xmin / xsize int32 [out_w]: tap window and normalised weights per output column as
+ *   ATen's _upsample_bicubic2d_aa computes them (prepared by the host wrapper); wy / ymin / ysize likewise for rows.
+ *   tile_rows = output rows per CTA; span_rows >= max over tiles of the input rows a tile's vertical windows cover
+ *   (ymin[last] + ysize[last] - ymin[first]); 4 * (256 + taps_x*out_w + span_rows*out_w + 4*W) bytes of shared memory.
+ * avs_mix_frames (:419-420): image[n] = weight[n] * image[n] + (1 - weight[n]) * image2[n], in place.
+ * ------------------------------------------------------------------------------------------------ */
+int avs_fbank_augment(const float* fbank, const int* params, const float* noise_scale, const float* noise, float* out,
+                      int B, int T, int F, float norm_mean, float norm_std, int skip_norm, void* stream);
+int avs_frames_preprocess(const unsigned char* frames, int N, int C, int H, int W, const float* wx, const int* xmin,
+                          const int* xsize, int taps_x, const float* wy, const int* ymin, const int* ysize, int taps_y,
+                          int out_h, int out_w, int tile_rows, int span_rows, const float* mean, const float* stdv,
+                          float* out, void* stream);
+int avs_mix_frames(float* image, const float* image2, const float* weight, int N, long long per_sample, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Evaluation statistics (src/utilities/stats.py:11-68): per-class average precision and ROC-AUC with scikit-learn's
  * tie-grouped definitions, and top-1 accuracy.  output / target fp32 [N, C] row-major (target > 0 = positive);
  * pos_scratch fp32 [C, N]; ap / auc fp32 [C] (classes without a positive or without a negative: auc = -1, ap = 0 / 1);

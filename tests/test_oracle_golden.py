@@ -177,3 +177,37 @@ def test_eval_oracle_matches_reference_retrieval_and_torch_losses(golden_dir):
             assert np.abs(grad - c[name + "_grad"].double().numpy()).max() < 1e-8
     parts = [np.arange(6).reshape(3, 2), np.arange(6, 12).reshape(3, 2)]
     assert E.distributed_concat(parts, 5).tolist() == np.arange(10).reshape(5, 2).tolist()
+
+
+# ------------------------------------------------------------------------------------------------ loader transforms
+def test_augment_oracle_matches_torchvision_and_torchaudio_golden(golden_dir):
+    """oracle/augment_oracle.py vs torchvision Resize(BICUBIC, antialias)+Normalize and torchaudio Frequency/TimeMasking
+    + noise + roll as src/dataloader.py:152-155,491-516 call them; also the host-side draw replay and tap tables of
+    avsiam_b200.augment (no kernel involved)."""
+    import numpy as np
+    from avsiam_b200 import augment as A
+    from oracle import augment_oracle as AO
+    from oracle.make_golden_augment import MEAN, STD, SUB, synth_fbank, synth_frames
+    g = torch.load(os.path.join(golden_dir, "augment.pt"), weights_only=False)
+    for c in g["frames"]:
+        y = AO.resize_normalize(synth_frames(c["seed"], c["n"], c["h"], c["w"]), 224, MEAN, STD)
+        assert np.abs(y[SUB] - c["sub"].double().numpy()).max() < 2e-5
+        assert abs(y.sum() - c["sum"]) < 1e-6 * c["abs_sum"]
+        for size_in in (c["h"], c["w"]):                                   # product tap tables == oracle matrix
+            xmin, xsize, w = A.aa_resize_weights(size_in, 224)
+            M = AO.aa_matrix(size_in, 224)
+            dense = np.zeros_like(M)
+            for i in range(224):
+                dense[i, xmin[i]:xmin[i] + xsize[i]] = w[i, :xsize[i]]
+            assert np.abs(dense - M).max() < 1e-6
+    for c in g["audio"]:
+        T, F = c["T"], c["F"]
+        gen = torch.Generator().manual_seed(c["seed"])
+        d = A.draw_augment_params(1, T, F, c["freqm"], c["timem"], c["noise"], generator=gen,
+                                  np_rng=np.random.RandomState(c["seed"]), device="cpu", host_noise=True)
+        f0, f1, t0, t1, shift, _ = d.params[0].tolist()
+        y = AO.augment_fbank(synth_fbank(c["seed"], T, F), (f0, f1), (t0, t1), -5.081, 4.4849,
+                             noise=d.noise[0].numpy() if c["noise"] else None,
+                             r=float(d.scale[0]) if c["noise"] else 0.0, shift=shift)
+        assert np.array_equal(y, c["out"].numpy())                         # bit-exact, bands and roll included
+    assert AO.band(0.5, 0.5, 0, 128) == (0, 0)
