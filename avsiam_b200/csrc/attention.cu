@@ -19,6 +19,7 @@
 // kernel (warp owns 16 queries, K and V resident), each recomputing P from the saved log-sum-exp.
 #include "../../include/avsiam_b200.h"
 #include "common.cuh"
+#include <type_traits>
 #include <stdlib.h>
 
 namespace {
@@ -176,15 +177,19 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const AttnArgs
       for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-    for (int kv0 = 0; kv0 < S_pad; kv0 += 8 * NT) {
-      float s[NT][4];
-      gemm_a_tT<HD, NT>(s, qf, sK, kv0, lane);
-      const bool tail = kv0 + 8 * NT > S;
+    // one block of 8 * NTB keys: scores, online softmax, P V.  Full blocks take 64 keys; the last block of the
+    // sequence only as many 16-key steps as it has valid keys (S = 708: 4 valid keys in the 12th block -> NTB = 2,
+    // a quarter of the work instead of a full block of mostly masked columns).
+    auto block = [&](auto ntb_tag, int kv0) {
+      constexpr int NTB = decltype(ntb_tag)::value;
+      float s[NTB][4];
+      gemm_a_tT<HD, NTB>(s, qf, sK, kv0, lane);
+      const bool tail = kv0 + 8 * NTB > S;
       float mx0 = -INFINITY, mx1 = -INFINITY;
       // the row max is taken on the raw scores (scale > 0 commutes with max), so that scaling and max subtraction
       // are ONE FFMA per element in the exponent below
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
+      for (int nt = 0; nt < NTB; ++nt) {
         if (tail) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const AttnArgs
       m0 = nm0; m1 = nm1;
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
+      for (int nt = 0; nt < NTB; ++nt) {
         s[nt][0] = exp2f(fmaf(s[nt][0], a.scale_log2, -m0)); s[nt][1] = exp2f(fmaf(s[nt][1], a.scale_log2, -m0));
         s[nt][2] = exp2f(fmaf(s[nt][2], a.scale_log2, -m1)); s[nt][3] = exp2f(fmaf(s[nt][3], a.scale_log2, -m1));
         rs0 += s[nt][0] + s[nt][1];
@@ -213,9 +218,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const AttnArgs
         o[dn][0] *= corr0; o[dn][1] *= corr0;
         o[dn][2] *= corr1; o[dn][3] *= corr1;
       }
-      uint32_t p[NT / 2][4];
-      pack_c_to_a<NT>(p, s);
-      gemm_p_t<HD, NT / 2>(o, p, sV, kv0, lane);
+      uint32_t p[NTB / 2][4];
+      pack_c_to_a<NTB>(p, s);
+      gemm_p_t<HD, NTB / 2>(o, p, sV, kv0, lane);
+    };
+    int kv0 = 0;
+    for (; kv0 + 8 * NT <= S; kv0 += 8 * NT) block(std::integral_constant<int, NT>{}, kv0);
+    if (kv0 < S) {
+      const int rem = S - kv0;                       // 1 .. 63 valid keys left (tile rows up to S_pad are zero-filled)
+      if constexpr (HD == 32) {                      // (head_dim 64 has no registers to spare for more block shapes)
+        if (rem <= 16) block(std::integral_constant<int, 2>{}, kv0);
+        else if (rem <= 32) block(std::integral_constant<int, 4>{}, kv0);
+        else block(std::integral_constant<int, NT>{}, kv0);
+      } else {
+        block(std::integral_constant<int, NT>{}, kv0);
+      }
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);

@@ -1,0 +1,51 @@
+// MUFU.EX2 issue rate per SM (decides the exponential floor of the attention kernels).
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mufu_probe mufu_probe.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+template <int MODE>
+__global__ void probe(float* out, int iters, float seed, long long* cycles) {
+  float r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = seed + threadIdx.x * 1e-3f + i;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (MODE == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(r[i]));
+      if (MODE == 1) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(r[i]));
+      if (MODE == 2) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(r[i])); asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(r[i])); }
+      if (MODE == 3) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(r[i]));
+    }
+  }
+  const long long t1 = clock64();
+  float acc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc += r[i];
+  if (acc == 0.12345f) out[threadIdx.x] = acc;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+
+template <int MODE>
+void run(const char* name, float* d, long long* dc, int warps_per_sm) {
+  const int iters = 2048, blocks = 148, threads = 32 * warps_per_sm;
+  probe<MODE><<<blocks, threads>>>(d, 16, 1.f, dc);
+  probe<MODE><<<blocks, threads>>>(d, iters, 1.f, dc);
+  cudaDeviceSynchronize();
+  long long c; cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
+  const double per_sm_per_clk = (double)threads * iters * 8 / (double)c;
+  printf("%-22s warps/SM=%2d: %lld cycles, %.1f lane-ops per clk per SM  (%s)\n", name, warps_per_sm, c, per_sm_per_clk,
+         cudaGetErrorString(cudaGetLastError()));
+}
+
+int main() {
+  float* d; long long* dc; cudaMalloc(&d, 4096); cudaMalloc(&dc, 8);
+  for (int w : {4, 8, 16, 32}) {
+    run<0>("ex2.approx", d, dc, w);
+    run<1>("fma", d, dc, w);
+    run<2>("ex2 + fma", d, dc, w);
+    run<3>("rcp.approx", d, dc, w);
+  }
+  return 0;
+}
