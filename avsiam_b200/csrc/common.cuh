@@ -213,28 +213,43 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 // FMA-pipe polynomial costs ~13 issue slots per element and made the fc1 GEMMs epilogue-bound (ncu: 621
 // instructions per 32-column chunk), so the normal CDF is evaluated as a sigmoid of a fitted odd polynomial,
 //   Phi(x) ~= 1 / (1 + exp2(x * Q(t))),  t = min(x^2, 5.5^2),
-// which moves the transcendental part to the otherwise idle MUFU pipe (ex2 + rcp) and leaves 6 FMA-pipe
-// instructions:  |gelu err| <= 2.6e-5, |gelu' err| <= 1.1e-4  (bf16 ulp at 1 is 3.9e-3; the clamp keeps the fit in
-// range, beyond it the sigmoid is saturated).  gelu' is the exact derivative of the approximation,
+// which moves the transcendental part to the MUFU pipe and leaves 6 FMA-pipe instructions; the fit itself has
+// |gelu err| <= 2.6e-5, |gelu' err| <= 1.1e-4  (bf16 ulp at 1 is 3.9e-3; the clamp keeps the fit in range, beyond it
+// the sigmoid is saturated).  gelu' is the exact derivative of the approximation,
 //   gelu'(x) = s + x s (1 - s) R(t),  R = P + 2 t P'.   Coefficients: tools/fit_gelu_poly.py.
+// The sigmoid is evaluated with the hardware tanh (sigmoid(2y) = (1 + tanh y) / 2, y = x (c0 + c1 t + c2 t^2),
+// c0 = 0.79751 ~ sqrt(2/pi)): ONE MUFU per element instead of ex2 + rcp.  That matters because the GELU / dGELU
+// epilogues of the K = 512 / 768 GEMMs are MUFU-bound, not FMA-bound: MUFU issues 16 lanes per clock per SM
+// (tools/mufu_probe.cu), so 2 MUFU x 128 x 256 elements = 4096 cycles per tile against a 3072-cycle mainloop.
+// tanh.approx.f32 has a relative error of 2^-11 (absolute 4.9e-4 near saturation), i.e. |gelu err| <= 2.5e-4 |x| —
+// below the bf16 rounding of the stored activation for x > 0, above it (but < 1.3e-3 absolute) in the negative tail.
+__device__ __forceinline__ float tanh_approx(float y) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;\n" : "=f"(r) : "f"(y));
+  return r;
+}
+__device__ __forceinline__ float gelu_tanh_arg(float x, float t) {
+  float q = -3.515168559e-04f;
+  q = fmaf(q, t, 3.700564594e-02f);
+  q = fmaf(q, t, 7.975078770e-01f);
+  return x * q;
+}
 __device__ __forceinline__ float gelu_sigmoid(float x) {   // Phi(x)
   const float t = fminf(x * x, 30.25f);
-  float q = 1.014263253e-03f;
-  q = fmaf(q, t, -1.067757234e-01f);
-  q = fmaf(q, t, -2.301121235e+00f);
-  return __fdividef(1.0f, 1.0f + exp2f(x * q));
+  return fmaf(0.5f, tanh_approx(gelu_tanh_arg(x, t)), 0.5f);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return x * gelu_sigmoid(x); }
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float t = fminf(x * x, 30.25f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx(gelu_tanh_arg(x, t)), hx);
+}
 __device__ __forceinline__ float dgelu_erf(float x) {
   const float t = fminf(x * x, 30.25f);
-  float q = 1.014263253e-03f;
-  q = fmaf(q, t, -1.067757234e-01f);
-  q = fmaf(q, t, -2.301121235e+00f);
-  const float s = __fdividef(1.0f, 1.0f + exp2f(x * q));
+  const float s = fmaf(0.5f, tanh_approx(gelu_tanh_arg(x, t)), 0.5f);
   float r = -3.515168559e-03f;
   r = fmaf(r, t, 2.220338732e-01f);
   r = fmaf(r, t, 1.595015764e+00f);
-  return fmaf(x * (s * (1.0f - s)), r, s);
+  return fmaf(x * fmaf(-s, s, s), r, s);
 }
 
 // ---- TMA store / bulk-group plumbing (epilogues) ----
