@@ -463,6 +463,11 @@ extern "C" int avs_attention_fwd(const void* qkv, long long ld_qkv, void* out, l
   if (check_common(qkv, ld_qkv, ld_o, n_seq, S, H, head_dim, "avs_attention_fwd")) return -1;
   AVS_REQUIRE(out && lse2, "avs_attention_fwd: null pointer");
   if (n_seq == 0) return 0;
+  static const bool fwd_tc = avs_attention_tc_enabled() && !(getenv("AVS_ATTN_FWD_TC") && atoi(getenv("AVS_ATTN_FWD_TC")) == 0);
+  if (fwd_tc) {   // long head_dim-32 sequences (MAE decoder): tcgen05 kernel, exponential-bound instead of issue-bound
+    const int rc = avs_attention_fwd_tc(qkv, ld_qkv, out, ld_o, lse2, n_seq, S, H, head_dim, stream);
+    if (rc != -2) return rc;
+  }
   AttnArgs a = {};
   a.qkv = (const bf16*)qkv; a.out = (bf16*)out; a.lse2 = lse2;
   a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.S = S; a.S_pad = (S + 63) & ~63; a.H = H; a.D = H * head_dim;

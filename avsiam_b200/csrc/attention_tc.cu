@@ -25,6 +25,7 @@
 // the exponentials of t+2 overlap the tensor work that consumes t.
 #include "../../include/avsiam_b200.h"
 #include "common.cuh"
+#include <stdio.h>
 #include <stdlib.h>
 #include <type_traits>
 
@@ -564,6 +565,346 @@ int launch_bwd(const TcArgs& a, int n_seq, cudaStream_t stream) {
   return avs_check_launch("attn_bwd_tc_kernel");
 }
 
+// =====================================================================================================
+// tcgen05 / TMEM attention FORWARD (MAE decoder shape: head_dim 32, 256 <= S <= 768).
+//
+// The forward of F.scaled_dot_product_attention (cav_mae_base.py:58-77) at head_dim 32 is bound by the exponentials
+// (MUFU.EX2 issues 16 lanes per clock per SM — tools/mufu_probe.cu — against S^2 exponentials per head), not by the
+// tensor pipe.  Everything else is kept off the softmax warps:
+//   * thread = query row (TMEM lane): row max and row sum are per-thread serial reductions — no shuffles.
+//   * online softmax with a LAZY running maximum: the maximum a row exponentiates against is only raised when the
+//     new block exceeds it by more than 2^8 (probabilities then stay below 256, exact in the final O / l); raising it
+//     rescales O in tensor memory (tcgen05.ld / st by the owning thread).  That happens in the first one or two units
+//     of a query block and almost never afterwards, so there is no correction warp and no second pass.
+//   * P goes back to TENSOR MEMORY as packed bf16 and is the A operand of the P V product (tcgen05.mma with A in TMEM),
+//     so the probabilities never touch shared memory.
+//   * one CTA = one (sequence, head), 6 warps (loader, MMA issuer, 4 softmax warps = the 4 TMEM lane quarters),
+//     K and V of the whole head resident in swizzled shared memory (2 x 45 KB), Q blocks streamed (2 x 8 KB),
+//     256 TMEM columns: TWO CTAs PER SM (the occupancy API reports 1 for any kernel with tcgen05.alloc; the hardware
+//     co-schedules two 256-column CTAs — tools/tmem_occ_probe.cu), so one CTA's prologue / epilogue runs under the
+//     other's MUFU work.
+// Work unit = 64 keys: S[b] (64 fp32 columns, double-buffered) -> P[b] (32 packed columns, double-buffered) -> O.
+// The last unit of a sequence only takes as many 16-key steps as it has valid keys (S = 708: N = 16).
+// =====================================================================================================
+constexpr int TCF_SOFTMAX_WARPS = 4;
+constexpr int TCF_FIRST_SOFTMAX_WARP = 2;
+constexpr int TCF_THREADS = 32 * (TCF_FIRST_SOFTMAX_WARP + TCF_SOFTMAX_WARPS);
+constexpr int TCF_COL_S = 0, TCF_COL_P = 128, TCF_COL_O = 192, TCF_TMEM_COLS = 256;
+constexpr float TCF_LAZY = 8.0f;   // log2 of the largest probability tolerated before the running maximum is raised
+
+struct TcFwdArgs {
+  const bf16* qkv;
+  bf16* out;
+  float* lse2;
+  long long ld_qkv, ld_o;
+  int S, NB, NU, H, D;   // NB = 128-query blocks, NU = 64-key units
+  float scale_log2;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwdArgs a) {
+  using C = TcCfg<HD>;
+  static_assert(TCF_COL_O + HD <= TCF_TMEM_COLS, "O does not fit the TMEM allocation");
+  // two CTAs per SM leave no room for alignment slack: the dynamic window itself must be 1024-byte aligned (it is the
+  // only shared memory of the kernel, so it starts at the CTA's base); checked, not assumed
+  extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
+  uint8_t* smem = tc_smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int S = a.S, NB = a.NB, NU = a.NU;
+  const int n_last = (((S - (NU - 1) * 64) + 15) >> 4) << 4;   // MMA N of the last unit (16 .. 64)
+  const int kv_rows = (NU - 1) * 64 + n_last;                   // rows the MMAs touch (multiple of 16: tiles stay 1 KB aligned)
+  const uint32_t sK = smem_u32(smem);
+  const uint32_t sV = sK + kv_rows * C::ROWB;
+  const uint32_t sQ = sV + kv_rows * C::ROWB;          // [2] 128-row blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kv_rows * C::ROWB + 2 * C::BLK_BYTES);
+  uint64_t* q_full = bars;          // [2] loader -> issuer
+  uint64_t* q_empty = bars + 2;     // [2] issuer (commit) -> loader
+  uint64_t* s_full = bars + 4;      // [2] issuer (commit) -> softmax: S unit in TMEM
+  uint64_t* s_read = bars + 6;      // [2] softmax -> issuer: S unit is in registers
+  uint64_t* p_full = bars + 8;      // [2] softmax -> issuer: P unit written to TMEM
+  uint64_t* p_empty = bars + 10;    // [2] issuer (commit) -> softmax: P V of that unit has retired
+  uint64_t* o_full = bars + 12;     // issuer (commit) -> softmax: O of a query block complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, seq = blockIdx.y;
+  const long long row_base = (long long)seq * S;
+  const bf16* qb = a.qkv + row_base * a.ld_qkv + h * HD;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_read[i], TCF_SOFTMAX_WARPS);
+      mbar_init(&p_full[i], TCF_SOFTMAX_WARPS);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, TCF_TMEM_COLS);
+    tmem_relinquish();
+  }
+  // K, V of the whole head and the first Q block: one cooperative load, one exposed HBM round trip
+  load_rows_async<HD>(sK, qb + a.D, a.ld_qkv, 0, kv_rows, S, threadIdx.x, TCF_THREADS);
+  load_rows_async<HD>(sV, qb + 2 * a.D, a.ld_qkv, 0, kv_rows, S, threadIdx.x, TCF_THREADS);
+  load_rows_async<HD>(sQ, qb, a.ld_qkv, 0, 128, S, threadIdx.x, TCF_THREADS);
+  cp_async_wait_all();
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int U = NB * NU;
+
+  if (warp == 0) {
+    // ============================ loader: Q blocks 1 .. NB-1 ============================
+    if (lane == 0) mbar_arrive(&q_full[0]);
+    for (int i = 1; i < NB; ++i) {
+      if (i >= 2) mbar_wait(&q_empty[i & 1], (uint32_t)(((i >> 1) - 1) & 1));
+      load_rows_async<HD>(sQ + (i & 1) * C::BLK_BYTES, qb, a.ld_qkv, i * 128, 128, S, lane, 32);
+      cp_async_wait_all();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_full[i & 1]);
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    // iteration u: S(u) as soon as the softmax warps hold S(u-2) in registers, then O += P(u-1) V.
+    constexpr uint32_t ID_PV = idesc_bf16(128, HD, 0, 1);     // A = P in TMEM, B = V rows MN-major
+    constexpr uint32_t K16ROWS = (16 * C::ROWB) >> 4, UNIT16 = (64 * C::ROWB) >> 4, BLK16 = C::BLK_BYTES >> 4;
+    const uint64_t kQ = make_desc(sQ, 0, C::SBO, C::LT), kK = make_desc(sK, 0, C::SBO, C::LT);
+    const uint64_t mV = make_desc(sV, C::SBO, C::SBO, C::LT);
+    const uint32_t id_s_full = idesc_bf16(128, 64, 0, 0), id_s_last = idesc_bf16(128, n_last, 0, 0);
+    int si = 0, sj = 0;          // S stream position: query block, key unit
+    int pj = -1;                 // key unit of u-1
+    for (int u = 0; u <= U; ++u) {
+      if (u < U) {
+        const uint32_t b = (uint32_t)(u & 1);
+        if (sj == 0) {
+          mbar_wait(&q_full[si & 1], (uint32_t)((si >> 1) & 1));
+          tc_fence_after();
+        }
+        if (u >= 2) {
+          mbar_wait(&s_read[b], (uint32_t)(((u - 2) >> 1) & 1));
+          tc_fence_after();
+        }
+        const uint32_t qo = (uint32_t)(si & 1) * BLK16, ko = (uint32_t)sj * UNIT16;
+        if (elect_one_sync()) {
+          const uint32_t id = (sj == NU - 1) ? id_s_last : id_s_full;
+#pragma unroll
+          for (int k = 0; k < C::KSTEPS; ++k)
+            umma_bf16_ss(tmem + TCF_COL_S + b * 64, kQ + (qo + 2 * k), kK + (ko + 2 * k), id, k > 0 ? 1u : 0u);
+          umma_commit(&s_full[b]);
+          if (sj == NU - 1) umma_commit(&q_empty[si & 1]);    // last read of this Q block
+        }
+        __syncwarp();
+      }
+      if (u >= 1) {   // O += P(u-1) V
+        const int w = u - 1;
+        const uint32_t pb = (uint32_t)(w & 1);
+        mbar_wait(&p_full[pb], (uint32_t)((w >> 1) & 1));
+        tc_fence_after();
+        const int ksteps = (pj == NU - 1) ? (n_last >> 4) : 4;
+        const uint32_t vo = (uint32_t)pj * UNIT16;
+        if (elect_one_sync()) {
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16_ts(tmem + TCF_COL_O, tmem + TCF_COL_P + pb * 32 + k * 8, mV + (vo + k * K16ROWS), ID_PV,
+                         (pj > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&p_empty[pb]);
+          if (pj == NU - 1) umma_commit(o_full);
+        }
+        __syncwarp();
+      }
+      pj = sj;
+      if (++sj == NU) { sj = 0; ++si; }
+    }
+  } else {
+    // ============================ softmax warps ============================
+    const int quarter = warp & 3;                   // the TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;            // query row inside the block == TMEM lane
+    const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
+    bf16* ob = a.out + row_base * a.ld_o + h * HD;
+    float* lp = a.lse2 + ((long long)seq * a.H + h) * S;
+    const int valid_last = S - (NU - 1) * 64;       // valid keys of the last unit (1 .. 64)
+    float m_run = -INFINITY, l0 = 0.f, l1 = 0.f;
+    uint32_t s0[32], s1[32];                        // scores of the current unit, keys 0-31 / 32-63
+    mbar_wait(&s_full[0], 0);
+    tc_fence_after();
+    tmem_ld_32x32b_x32(tlane + TCF_COL_S, s0);
+    tmem_ld_32x32b_x32(tlane + TCF_COL_S + 32, s1);
+
+    // one 32-key half: exponentials, row sum, bf16 pairs.  MASKED only in the last unit of the sequence (keys at or
+    // beyond S): the interior units carry no per-element predicates
+    auto half_unit = [&](auto mask_tag, const uint32_t (&sr)[32], uint32_t (&pw)[16], int key0) {
+      constexpr bool MASKED = decltype(mask_tag)::value;
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        float p0 = exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run));
+        float p1 = exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -m_run));
+        if (MASKED) {
+          if (key0 + c >= valid_last) p0 = 0.f;
+          if (key0 + c + 1 >= valid_last) p1 = 0.f;
+        }
+        l0 += p0;
+        l1 += p1;
+        pw[c >> 1] = pack_bf16x2(p0, p1);
+      }
+    };
+    int jj = 0, i = 0;
+    for (int u = 0; u < U; ++u) {
+      const uint32_t b = (uint32_t)(u & 1), pb = b, bn = b ^ 1u;
+      tmem_ld_wait();                                  // S(u) is in registers
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_read[b]);
+      const bool last = (jj == NU - 1);
+      // ---- running maximum (lazy): raw-score max of the unit's valid keys
+      float mx;
+      if (!last) {
+        float a0 = -INFINITY, a1 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          a0 = fmaxf(a0, fmaxf(__uint_as_float(s0[c]), __uint_as_float(s0[c + 1])));
+          a1 = fmaxf(a1, fmaxf(__uint_as_float(s1[c]), __uint_as_float(s1[c + 1])));
+        }
+        mx = fmaxf(a0, a1);
+      } else {
+        mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (c < valid_last) mx = fmaxf(mx, __uint_as_float(s0[c]));
+          if (c + 32 < valid_last) mx = fmaxf(mx, __uint_as_float(s1[c]));
+        }
+      }
+      const float m_new = mx * a.scale_log2;            // scale > 0 commutes with max
+      const bool raise = m_new > m_run + TCF_LAZY;      // always true in the first unit of a query block (m_run = -inf)
+      if (__any_sync(0xffffffffu, raise)) {
+        const float m_upd = raise ? m_new : m_run;
+        if (jj > 0) {
+          // O and l were accumulated against the old maximum: rescale (factor 1 for the rows that keep theirs).
+          // Every P V product issued so far must have retired before O is read: the latest one signals p_empty.
+          const float f = exp2f(m_run - m_upd);
+          mbar_wait(&p_empty[bn], (uint32_t)(((u - 1) >> 1) & 1));
+          tc_fence_after();
+          uint32_t ro[HD];
+          tmem_ld_n<HD>(tlane + TCF_COL_O, ro);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < HD; ++c) ro[c] = __float_as_uint(__uint_as_float(ro[c]) * f);
+          tmem_st_32x32b_x32(tlane + TCF_COL_O, ro);
+          l0 *= f;
+          l1 *= f;
+        }
+        m_run = m_upd;
+      }
+      uint32_t pw[16];
+      // ---- half 0: keys 0 .. 31 of the unit
+      if (last) half_unit(std::true_type{}, s0, pw, 0);
+      else half_unit(std::false_type{}, s0, pw, 0);
+      if (u >= 2) {
+        mbar_wait(&p_empty[pb], (uint32_t)(((u >> 1) - 1) & 1));
+        tc_fence_after();
+      }
+      tmem_st_32x32b_x16(tlane + TCF_COL_P + pb * 32, pw);
+      if (u + 1 < U) {      // the registers of this half take the same half of S(u+1) while half 1 is computed
+        mbar_wait(&s_full[bn], (uint32_t)(((u + 1) >> 1) & 1));
+        tc_fence_after();
+        tmem_ld_32x32b_x32(tlane + TCF_COL_S + bn * 64, s0);
+      }
+      // ---- half 1: keys 32 .. 63
+      if (last) half_unit(std::true_type{}, s1, pw, 32);
+      else half_unit(std::false_type{}, s1, pw, 32);
+      tmem_st_32x32b_x16(tlane + TCF_COL_P + pb * 32 + 16, pw);
+      if (u + 1 < U) tmem_ld_32x32b_x32(tlane + TCF_COL_S + bn * 64 + 32, s1);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[pb]);
+      if (last) {
+        // ---- epilogue of query block i: O / l, log-sum-exp
+        mbar_wait(o_full, (uint32_t)(i & 1));
+        tc_fence_after();
+        uint32_t ro[HD];
+        tmem_ld_n<HD>(tlane + TCF_COL_O, ro);
+        tmem_ld_wait();   // (also completes the prefetch of the next unit's scores)
+        const float l = l0 + l1;
+        const float inv = 1.f / l;
+        const int qr = i * 128 + row;
+        if (qr < S) {
+          bf16* dst = ob + (long long)qr * a.ld_o;
+#pragma unroll
+          for (int c = 0; c < HD; c += 8) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(ro[c]) * inv, __uint_as_float(ro[c + 1]) * inv);
+            o.y = pack_bf16x2(__uint_as_float(ro[c + 2]) * inv, __uint_as_float(ro[c + 3]) * inv);
+            o.z = pack_bf16x2(__uint_as_float(ro[c + 4]) * inv, __uint_as_float(ro[c + 5]) * inv);
+            o.w = pack_bf16x2(__uint_as_float(ro[c + 6]) * inv, __uint_as_float(ro[c + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c) = o;
+          }
+          lp[qr] = m_run + log2f(l);
+        }
+        // the first P V of the next query block (accumulate = 0 into O) is issued only after these warps have produced
+        // its P, i.e. after the tcgen05.ld above has completed: no extra barrier needed
+        m_run = -INFINITY; l0 = 0.f; l1 = 0.f;
+        jj = 0; ++i;
+      } else {
+        ++jj;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TCF_TMEM_COLS);
+  }
+}
+
+template <int HD>
+int launch_fwd(const TcFwdArgs& a, int n_seq, cudaStream_t stream) {
+  using C = TcCfg<HD>;
+  const int n_last = (((a.S - (a.NU - 1) * 64) + 15) >> 4) << 4;
+  const int smem = 2 * ((a.NU - 1) * 64 + n_last) * C::ROWB + 2 * C::BLK_BYTES + 256;
+  static int smem_set = 0;
+  if (smem > smem_set || getenv("AVS_TC_DEBUG")) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      avs_set_error("avs_attention_fwd(tc): cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+      return (int)e;
+    }
+    // two CTAs per SM need the full shared-memory carve-out
+    cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    if (getenv("AVS_TC_DEBUG")) {
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_fwd_tc_kernel<HD>, TCF_THREADS, smem);
+      fprintf(stderr, "[avs] attn_fwd_tc: smem %d B, %d CTAs per SM\n", smem, nb);
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, attn_fwd_tc_kernel<HD>);
+      int dev = 0, smem_sm = 0, smem_res = 0, regs_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+      cudaDeviceGetAttribute(&smem_res, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+      cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+      fprintf(stderr, "[avs]   static smem %zu, regs %d, maxThreads %d, maxDyn %d | SM: smem %d, reserved/block %d, regs %d\n",
+              fa.sharedSizeBytes, fa.numRegs, fa.maxThreadsPerBlock, fa.maxDynamicSharedSizeBytes, smem_sm, smem_res,
+              regs_sm);
+      for (int sz : {32768, 65536, 98304, 106496, 110592}) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_fwd_tc_kernel<HD>, TCF_THREADS, sz);
+        fprintf(stderr, "[avs]   dyn smem %d -> %d CTAs per SM\n", sz, nb);
+      }
+    }
+    smem_set = smem;
+  }
+  dim3 grid(a.H, n_seq);
+  attn_fwd_tc_kernel<HD><<<grid, TCF_THREADS, smem, stream>>>(a);
+  return avs_check_launch("attn_fwd_tc_kernel");
+}
+
 long long* g_tc_trace = nullptr;
 
 }  // namespace
@@ -585,4 +926,16 @@ int avs_attention_bwd_tc(const void* qkv, long long ld_qkv, const void* dout, lo
   a.scale = rsqrtf((float)head_dim);
   a.scale_log2 = a.scale * 1.4426950408889634f;
   return head_dim == 64 ? launch_bwd<64>(a, n_seq, (cudaStream_t)stream) : launch_bwd<32>(a, n_seq, (cudaStream_t)stream);
+}
+
+// Forward on the tcgen05 path: head_dim 32, 256 <= S <= 768 (K and V of a head resident in shared memory, two CTAs
+// per SM).  Returns -2 for other shapes (the caller then uses the mma.sync kernel of attention.cu).
+int avs_attention_fwd_tc(const void* qkv, long long ld_qkv, void* out, long long ld_o, float* lse2, int n_seq, int S,
+                         int H, int head_dim, void* stream) {
+  if (head_dim != 32 || S < 256 || S > 768) return -2;
+  TcFwdArgs a = {};
+  a.qkv = (const bf16*)qkv; a.out = (bf16*)out; a.lse2 = lse2;
+  a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.S = S; a.NB = (S + 127) / 128; a.NU = (S + 63) / 64; a.H = H; a.D = H * head_dim;
+  a.scale_log2 = rsqrtf((float)head_dim) * 1.4426950408889634f;
+  return launch_fwd<32>(a, n_seq, (cudaStream_t)stream);
 }

@@ -34,6 +34,8 @@ int avs_make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, long long rows, lon
 int avs_attention_bwd_tc(const void* qkv, long long ld_qkv, const void* dout, long long ld_o, const float* lse2,
                          const float* delta, void* dqkv, float* dbias, int n_seq, int S, int H, int head_dim,
                          void* stream);
+int avs_attention_fwd_tc(const void* qkv, long long ld_qkv, void* out, long long ld_o, float* lse2, int n_seq, int S,
+                         int H, int head_dim, void* stream);
 bool avs_attention_tc_enabled();  // AVS_ATTN_TC=0 in the environment selects the mma.sync kernels (A/B timing)
 
 // ---------------------------------------------------------------------------------------------
