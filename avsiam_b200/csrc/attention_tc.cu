@@ -82,6 +82,12 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
                "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x1(uint32_t taddr, uint32_t (&r)[1]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(r[0]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x1(uint32_t taddr, const uint32_t (&r)[1]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};\n" ::"r"(taddr), "r"(r[0]) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
   if constexpr (N == 32) tmem_ld_32x32b_x32(taddr, r);
@@ -589,7 +595,7 @@ int launch_bwd(const TcArgs& a, int n_seq, cudaStream_t stream) {
 constexpr int TCF_SOFTMAX_WARPS = 4;
 constexpr int TCF_FIRST_SOFTMAX_WARP = 2;
 constexpr int TCF_THREADS = 32 * (TCF_FIRST_SOFTMAX_WARP + TCF_SOFTMAX_WARPS);
-constexpr int TCF_COL_S = 0, TCF_COL_P = 128, TCF_COL_O = 192, TCF_TMEM_COLS = 256;
+constexpr int TCF_COL_S = 0, TCF_COL_P = 128, TCF_COL_O = 192, TCF_COL_L = 224, TCF_TMEM_COLS = 256;
 constexpr float TCF_LAZY = 8.0f;   // log2 of the largest probability tolerated before the running maximum is raised
 
 struct TcFwdArgs {
@@ -604,7 +610,7 @@ struct TcFwdArgs {
 template <int HD>
 __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwdArgs a) {
   using C = TcCfg<HD>;
-  static_assert(TCF_COL_O + HD <= TCF_TMEM_COLS, "O does not fit the TMEM allocation");
+  static_assert(TCF_COL_O + HD <= TCF_COL_L, "O does not fit the TMEM allocation");
   // two CTAs per SM leave no room for alignment slack: the dynamic window itself must be 1024-byte aligned (it is the
   // only shared memory of the kernel, so it starts at the CTA's base); checked, not assumed
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
@@ -616,7 +622,9 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
   const uint32_t sK = smem_u32(smem);
   const uint32_t sV = sK + kv_rows * C::ROWB;
   const uint32_t sQ = sV + kv_rows * C::ROWB;          // [2] 128-row blocks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kv_rows * C::ROWB + 2 * C::BLK_BYTES);
+  // 2 KB of bf16 1.0: the B operand of the row-sum product L += P 1 (any descriptor that stays inside reads ones)
+  const uint32_t sOnes = sQ + 2 * C::BLK_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kv_rows * C::ROWB + 2 * C::BLK_BYTES + 2048);
   uint64_t* q_full = bars;          // [2] loader -> issuer
   uint64_t* q_empty = bars + 2;     // [2] issuer (commit) -> loader
   uint64_t* s_full = bars + 4;      // [2] issuer (commit) -> softmax: S unit in TMEM
@@ -651,6 +659,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
   load_rows_async<HD>(sK, qb + a.D, a.ld_qkv, 0, kv_rows, S, threadIdx.x, TCF_THREADS);
   load_rows_async<HD>(sV, qb + 2 * a.D, a.ld_qkv, 0, kv_rows, S, threadIdx.x, TCF_THREADS);
   load_rows_async<HD>(sQ, qb, a.ld_qkv, 0, 128, S, threadIdx.x, TCF_THREADS);
+  for (int i = threadIdx.x; i < 2048 / 16; i += TCF_THREADS)
+    st_shared_v4(sOnes + i * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   cp_async_wait_all();
   fence_proxy_async();
   tc_fence_before();
@@ -672,54 +682,61 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    // iteration u: S(u) as soon as the softmax warps hold S(u-2) in registers, then O += P(u-1) V.
+    // The S stream runs two units ahead of the P V stream: S(u+2) is issued the moment the softmax warps hold S(u) in
+    // registers (both S buffers always in flight), O += P(u) V when P(u) has been written.
     constexpr uint32_t ID_PV = idesc_bf16(128, HD, 0, 1);     // A = P in TMEM, B = V rows MN-major
     constexpr uint32_t K16ROWS = (16 * C::ROWB) >> 4, UNIT16 = (64 * C::ROWB) >> 4, BLK16 = C::BLK_BYTES >> 4;
     const uint64_t kQ = make_desc(sQ, 0, C::SBO, C::LT), kK = make_desc(sK, 0, C::SBO, C::LT);
     const uint64_t mV = make_desc(sV, C::SBO, C::SBO, C::LT);
     const uint32_t id_s_full = idesc_bf16(128, 64, 0, 0), id_s_last = idesc_bf16(128, n_last, 0, 0);
+    // row sums on the tensor pipe: L[128 x 16] += P[128 x 16 keys] * ones[16 keys x 16] — every column of L is the
+    // row sum of the bf16 probabilities that also multiply V (one FADD per element less on the softmax warps)
+    constexpr uint32_t ID_L = idesc_bf16(128, 16, 0, 0);
+    const uint64_t kOnes = make_desc(sOnes, 128, 128, 0u);
     int si = 0, sj = 0;          // S stream position: query block, key unit
-    int pj = -1;                 // key unit of u-1
-    for (int u = 0; u <= U; ++u) {
-      if (u < U) {
-        const uint32_t b = (uint32_t)(u & 1);
-        if (sj == 0) {
-          mbar_wait(&q_full[si & 1], (uint32_t)((si >> 1) & 1));
-          tc_fence_after();
-        }
-        if (u >= 2) {
-          mbar_wait(&s_read[b], (uint32_t)(((u - 2) >> 1) & 1));
-          tc_fence_after();
-        }
-        const uint32_t qo = (uint32_t)(si & 1) * BLK16, ko = (uint32_t)sj * UNIT16;
-        if (elect_one_sync()) {
-          const uint32_t id = (sj == NU - 1) ? id_s_last : id_s_full;
-#pragma unroll
-          for (int k = 0; k < C::KSTEPS; ++k)
-            umma_bf16_ss(tmem + TCF_COL_S + b * 64, kQ + (qo + 2 * k), kK + (ko + 2 * k), id, k > 0 ? 1u : 0u);
-          umma_commit(&s_full[b]);
-          if (sj == NU - 1) umma_commit(&q_empty[si & 1]);    // last read of this Q block
-        }
-        __syncwarp();
-      }
-      if (u >= 1) {   // O += P(u-1) V
-        const int w = u - 1;
-        const uint32_t pb = (uint32_t)(w & 1);
-        mbar_wait(&p_full[pb], (uint32_t)((w >> 1) & 1));
+    auto issue_s = [&](int v) {
+      const uint32_t b = (uint32_t)(v & 1);
+      if (sj == 0) {
+        mbar_wait(&q_full[si & 1], (uint32_t)((si >> 1) & 1));
         tc_fence_after();
-        const int ksteps = (pj == NU - 1) ? (n_last >> 4) : 4;
-        const uint32_t vo = (uint32_t)pj * UNIT16;
-        if (elect_one_sync()) {
-          for (int k = 0; k < ksteps; ++k)
-            umma_bf16_ts(tmem + TCF_COL_O, tmem + TCF_COL_P + pb * 32 + k * 8, mV + (vo + k * K16ROWS), ID_PV,
-                         (pj > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&p_empty[pb]);
-          if (pj == NU - 1) umma_commit(o_full);
-        }
-        __syncwarp();
       }
-      pj = sj;
+      const uint32_t qo = (uint32_t)(si & 1) * BLK16, ko = (uint32_t)sj * UNIT16;
+      if (elect_one_sync()) {
+        const uint32_t id = (sj == NU - 1) ? id_s_last : id_s_full;
+#pragma unroll
+        for (int k = 0; k < C::KSTEPS; ++k)
+          umma_bf16_ss(tmem + TCF_COL_S + b * 64, kQ + (qo + 2 * k), kK + (ko + 2 * k), id, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[b]);
+        if (sj == NU - 1) umma_commit(&q_empty[si & 1]);    // last read of this Q block
+      }
+      __syncwarp();
       if (++sj == NU) { sj = 0; ++si; }
+    };
+    issue_s(0);
+    if (U > 1) issue_s(1);
+    int pj = 0;                  // key unit of the P V stream
+    for (int u = 0; u < U; ++u) {
+      const uint32_t b = (uint32_t)(u & 1);
+      if (u + 2 < U) {
+        mbar_wait(&s_read[b], (uint32_t)((u >> 1) & 1));
+        tc_fence_after();
+        issue_s(u + 2);
+      }
+      mbar_wait(&p_full[b], (uint32_t)((u >> 1) & 1));
+      tc_fence_after();
+      const int ksteps = (pj == NU - 1) ? (n_last >> 4) : 4;
+      const uint32_t vo = (uint32_t)pj * UNIT16;
+      if (elect_one_sync()) {
+        for (int k = 0; k < ksteps; ++k) {
+          umma_bf16_ts(tmem + TCF_COL_O, tmem + TCF_COL_P + b * 32 + k * 8, mV + (vo + k * K16ROWS), ID_PV,
+                       (pj > 0 || k > 0) ? 1u : 0u);
+          umma_bf16_ts(tmem + TCF_COL_L, tmem + TCF_COL_P + b * 32 + k * 8, kOnes, ID_L, (pj > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&p_empty[b]);
+        if (pj == NU - 1) umma_commit(o_full);
+      }
+      __syncwarp();
+      if (++pj == NU) pj = 0;
     }
   } else {
     // ============================ softmax warps ============================
@@ -729,7 +746,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
     bf16* ob = a.out + row_base * a.ld_o + h * HD;
     float* lp = a.lse2 + ((long long)seq * a.H + h) * S;
     const int valid_last = S - (NU - 1) * 64;       // valid keys of the last unit (1 .. 64)
-    float m_run = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float m_run = -INFINITY;
     uint32_t s0[32], s1[32];                        // scores of the current unit, keys 0-31 / 32-63
     mbar_wait(&s_full[0], 0);
     tc_fence_after();
@@ -748,8 +765,6 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
           if (key0 + c >= valid_last) p0 = 0.f;
           if (key0 + c + 1 >= valid_last) p1 = 0.f;
         }
-        l0 += p0;
-        l1 += p1;
         pw[c >> 1] = pack_bf16x2(p0, p1);
       }
     };
@@ -795,8 +810,11 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
 #pragma unroll
           for (int c = 0; c < HD; ++c) ro[c] = __float_as_uint(__uint_as_float(ro[c]) * f);
           tmem_st_32x32b_x32(tlane + TCF_COL_O, ro);
-          l0 *= f;
-          l1 *= f;
+          uint32_t rl[1];
+          tmem_ld_32x32b_x1(tlane + TCF_COL_L, rl);      // only column 0 of L is ever read back
+          tmem_ld_wait();
+          rl[0] = __float_as_uint(__uint_as_float(rl[0]) * f);
+          tmem_st_32x32b_x1(tlane + TCF_COL_L, rl);
         }
         m_run = m_upd;
       }
@@ -828,9 +846,11 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
         mbar_wait(o_full, (uint32_t)(i & 1));
         tc_fence_after();
         uint32_t ro[HD];
+        uint32_t rl[1];
         tmem_ld_n<HD>(tlane + TCF_COL_O, ro);
+        tmem_ld_32x32b_x1(tlane + TCF_COL_L, rl);
         tmem_ld_wait();   // (also completes the prefetch of the next unit's scores)
-        const float l = l0 + l1;
+        const float l = __uint_as_float(rl[0]);
         const float inv = 1.f / l;
         const int qr = i * 128 + row;
         if (qr < S) {
@@ -848,7 +868,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
         }
         // the first P V of the next query block (accumulate = 0 into O) is issued only after these warps have produced
         // its P, i.e. after the tcgen05.ld above has completed: no extra barrier needed
-        m_run = -INFINITY; l0 = 0.f; l1 = 0.f;
+        m_run = -INFINITY;
         jj = 0; ++i;
       } else {
         ++jj;
@@ -864,11 +884,374 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
   }
 }
 
+// =====================================================================================================
+// Persistent ping-pong variant of the forward: ONE CTA per SM that walks over (sequence, head) pairs, with TWO
+// softmax groups that take alternate query blocks of the head and hand a "MUFU token" back and forth (named barriers),
+// so that one group's exponentials always run under the other group's tcgen05.ld / st, barrier and max work.
+// Two co-resident CTAs cannot do that: measured (ncu), their softmax warps fall into a convoy — both in the
+// exponential phase (sharing the 16-lane MUFU) and then both outside it — and the MUFU pipe idles 40 % of the time.
+//   warp 0      K/V loader: TMA (SWIZZLE_64B boxes) of the NEXT head's K and V into the other shared-memory stage
+//   warp 1      Q loader of both groups (TMA, double-buffered 128-row blocks per group, in consumption order)
+//   warps 2, 3  MMA issuers of group A / B
+//   warps 4-7   softmax group A (TMEM columns 0-255), warps 8-11 softmax group B (columns 256-511)
+// (12 warps: the register file then allows 168 registers per thread)
+// Shared memory: 2 stages x (K | V) x kv_rows x 64 B + 2 groups x 2 x 8 KB of Q  (S = 708: 212 KB).
+// =====================================================================================================
+constexpr int TCP_FIRST_SOFTMAX_WARP = 4;
+constexpr int TCP_THREADS = 32 * (TCP_FIRST_SOFTMAX_WARP + 8);
+
+struct TcPpArgs {
+  CUtensorMap map128, map16;   // qkv [rows, 3D] bf16, boxes of 128 / 16 rows x HD columns, SWIZZLE_64B
+  bf16* out;
+  float* lse2;
+  long long ld_o;
+  int S, NB, NU, H, D, n_heads;   // n_heads = n_seq * H
+  int tokens;                     // 1: the two softmax groups alternate explicitly (MUFU token)
+  float scale_log2;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+
+template <int HD>
+__global__ void __launch_bounds__(TCP_THREADS, 1) attn_fwd_pp_kernel(const __grid_constant__ TcPpArgs a) {
+  using C = TcCfg<HD>;
+  extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = a.S, NB = a.NB, NU = a.NU;
+  const int n_last = (((S - (NU - 1) * 64) + 15) >> 4) << 4;   // MMA N of the last unit (16 .. 64)
+  const int kv_rows = (NU - 1) * 64 + n_last;
+  const uint32_t kv_bytes = (uint32_t)kv_rows * C::ROWB;
+  const uint32_t sKV = smem_u32(smem);                          // stage s: K at sKV + s*2*kv_bytes, V right after
+  const uint32_t sQ = sKV + 4 * kv_bytes;                       // group g, buffer b: sQ + (g*2 + b) * BLK_BYTES
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * kv_bytes + 4 * C::BLK_BYTES);
+  uint64_t* kv_full = bars;           // [2]
+  uint64_t* kv_empty = bars + 2;      // [2] both issuers commit
+  uint64_t* gb = bars + 4;            // per group 13 barriers
+  auto q_full = [&](int g, int b) { return gb + g * 13 + b; };
+  auto q_empty = [&](int g, int b) { return gb + g * 13 + 2 + b; };
+  auto s_full = [&](int g, int b) { return gb + g * 13 + 4 + b; };
+  auto s_read = [&](int g, int b) { return gb + g * 13 + 6 + b; };
+  auto p_full = [&](int g, int b) { return gb + g * 13 + 8 + b; };
+  auto p_empty = [&](int g, int b) { return gb + g * 13 + 10 + b; };
+  auto o_full = [&](int g) { return gb + g * 13 + 12; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 26);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 2);
+    }
+    for (int g = 0; g < 2; ++g) {
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(q_full(g, b), 1);
+        mbar_init(q_empty(g, b), 1);
+        mbar_init(s_full(g, b), 1);
+        mbar_init(s_read(g, b), 4);
+        mbar_init(p_full(g, b), 4);
+        mbar_init(p_empty(g, b), 1);
+      }
+      mbar_init(o_full(g), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // this CTA's heads: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int n_my = (a.n_heads - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // query blocks of a head: group g takes blocks g, g+2, ...
+  const int nbg0 = (NB + 1) >> 1, nbg1 = NB >> 1;
+
+  if (warp == 0) {
+    // ============================ K/V loader ============================
+    if (lane == 0) {
+      tma_prefetch_desc(&a.map128);
+      tma_prefetch_desc(&a.map16);
+      for (int k = 0; k < n_my; ++k) {
+        const int hh = blockIdx.x + k * gridDim.x, seq = hh / a.H, h = hh - seq * a.H;
+        const int st = k & 1;
+        if (k >= 2) mbar_wait_backoff(&kv_empty[st], (uint32_t)(((k >> 1) - 1) & 1), 1000);
+        mbar_arrive_expect_tx(&kv_full[st], 2 * kv_bytes);
+        const int row0 = seq * S;
+#pragma unroll 1
+        for (int m = 0; m < 2; ++m) {                           // K then V
+          uint8_t* dst = smem + (size_t)(st * 2 + m) * kv_bytes;
+          const int col = (m + 1) * a.D + h * HD;
+          int r = 0;
+          for (; r + 128 <= kv_rows; r += 128) tma_load_2d(dst + r * C::ROWB, &a.map128, &kv_full[st], col, row0 + r);
+          for (; r < kv_rows; r += 16) tma_load_2d(dst + r * C::ROWB, &a.map16, &kv_full[st], col, row0 + r);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ Q loader (both groups) ============================
+    // Blocks are requested in the order the groups consume them: A(t), B(t), A(t+1), ...  The groups advance in
+    // lockstep (token passing), so waiting for A's buffer never starves B of a block it can already use.
+    if (lane == 0) {
+      int n[2] = {0, 0};   // running count of Q blocks per group
+      for (int k = 0; k < n_my; ++k) {
+        const int hh = blockIdx.x + k * gridDim.x, seq = hh / a.H, h = hh - seq * a.H;
+        for (int i = 0; i < NB; ++i) {
+          const int g = i & 1, b = n[g] & 1;
+          if (n[g] >= 2) mbar_wait_backoff(q_empty(g, b), (uint32_t)(((n[g] >> 1) - 1) & 1), 500);
+          mbar_arrive_expect_tx(q_full(g, b), C::BLK_BYTES);
+          tma_load_2d(smem + 4 * kv_bytes + (size_t)(g * 2 + b) * C::BLK_BYTES, &a.map128, q_full(g, b), h * HD,
+                      seq * S + i * 128);
+          ++n[g];
+        }
+      }
+    }
+  } else if (warp == 2 || warp == 3) {
+    // ============================ MMA issuers ============================
+    const int g = warp - 2;
+    const int nbg = g == 0 ? nbg0 : nbg1;
+    const int UH = nbg * NU;                                   // units of this group per head
+    constexpr uint32_t ID_PV = idesc_bf16(128, HD, 0, 1);
+    constexpr uint32_t K16ROWS = (16 * C::ROWB) >> 4, UNIT16 = (64 * C::ROWB) >> 4, BLK16 = C::BLK_BYTES >> 4;
+    const uint64_t kQ = make_desc(sQ + g * 2 * C::BLK_BYTES, 0, C::SBO, C::LT);
+    const uint64_t kK = make_desc(sKV, 0, C::SBO, C::LT);
+    const uint64_t mV = make_desc(sKV + kv_bytes, C::SBO, C::SBO, C::LT);
+    const uint32_t stage16 = (2 * kv_bytes) >> 4;
+    const uint32_t id_s_full = idesc_bf16(128, 64, 0, 0), id_s_last = idesc_bf16(128, n_last, 0, 0);
+    const uint32_t tg = tmem + g * 256;
+    const long long U = (long long)n_my * UH;                  // units of this group over the CTA's lifetime
+    int sk = 0, sq = 0, sj = 0;   // S stream: head index k, running Q-block count, key unit
+    int sqh = 0;                  // Q blocks of the current head already started
+    auto issue_s = [&](long long v) {
+      const uint32_t b = (uint32_t)(v & 1);
+      if (sj == 0) {
+        if (sqh == 0) {
+          mbar_wait(&kv_full[sk & 1], (uint32_t)((sk >> 1) & 1));
+          tc_fence_after();
+        }
+        mbar_wait(q_full(g, sq & 1), (uint32_t)((sq >> 1) & 1));
+        tc_fence_after();
+      }
+      const uint32_t qo = (uint32_t)(sq & 1) * BLK16, ko = (uint32_t)(sk & 1) * stage16 + (uint32_t)sj * UNIT16;
+      if (elect_one_sync()) {
+        const uint32_t id = (sj == NU - 1) ? id_s_last : id_s_full;
+#pragma unroll
+        for (int k = 0; k < C::KSTEPS; ++k)
+          umma_bf16_ss(tg + TCF_COL_S + b * 64, kQ + (qo + 2 * k), kK + (ko + 2 * k), id, k > 0 ? 1u : 0u);
+        umma_commit(s_full(g, b));
+        if (sj == NU - 1) umma_commit(q_empty(g, sq & 1));
+      }
+      __syncwarp();
+      if (++sj == NU) {
+        sj = 0; ++sq;
+        if (++sqh == nbg) { sqh = 0; ++sk; }
+      }
+    };
+    if (U > 0) issue_s(0);
+    if (U > 1) issue_s(1);
+    int pk = 0, pqh = 0, pj = 0;
+    for (long long u = 0; u < U; ++u) {
+      const uint32_t b = (uint32_t)(u & 1);
+      if (u + 2 < U) {
+        mbar_wait(s_read(g, b), (uint32_t)((u >> 1) & 1));
+        tc_fence_after();
+        issue_s(u + 2);
+      }
+      mbar_wait(p_full(g, b), (uint32_t)((u >> 1) & 1));
+      tc_fence_after();
+      const int ksteps = (pj == NU - 1) ? (n_last >> 4) : 4;
+      const uint32_t vo = (uint32_t)(pk & 1) * stage16 + (uint32_t)pj * UNIT16;
+      const bool head_done = (pj == NU - 1) && (pqh == nbg - 1);
+      if (elect_one_sync()) {
+        for (int k = 0; k < ksteps; ++k)
+          umma_bf16_ts(tg + TCF_COL_O, tg + TCF_COL_P + b * 32 + k * 8, mV + (vo + k * K16ROWS), ID_PV,
+                       (pj > 0 || k > 0) ? 1u : 0u);
+        umma_commit(p_empty(g, b));
+        if (pj == NU - 1) umma_commit(o_full(g));
+        if (head_done) umma_commit(&kv_empty[pk & 1]);          // this group's last read of the stage
+      }
+      __syncwarp();
+      if (++pj == NU) {
+        pj = 0;
+        if (++pqh == nbg) { pqh = 0; ++pk; }
+      }
+    }
+    if (nbg == 0) {   // a group without query blocks (NB == 1) still has to release the K/V stages
+      for (int k = 0; k < n_my; ++k) {
+        mbar_wait(&kv_full[k & 1], (uint32_t)((k >> 1) & 1));
+        if (lane == 0) mbar_arrive(&kv_empty[k & 1]);
+      }
+    }
+  } else {
+    // ============================ softmax groups ============================
+    const int g = (warp - TCP_FIRST_SOFTMAX_WARP) >> 2;
+    const int nbg = g == 0 ? nbg0 : nbg1;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t tlane = tmem + g * 256 + ((uint32_t)(quarter * 32) << 16);
+    const int valid_last = S - (NU - 1) * 64;
+    const long long U = (long long)n_my * nbg * NU;
+    // token passing: group 0 exponentiates while group 1 does everything else, then they swap.  Both groups make
+    // the same number of exchanges (UX per head) even when they own different numbers of query blocks.
+    const int UX = nbg0 * NU;
+    const int my_bar = 1 + g, other_bar = 2 - g;
+    const bool tokens = a.tokens != 0;
+    if (tokens && g == 1) named_bar_arrive(1, 256);           // group 0 starts with the token
+    float m_run = -INFINITY, l0 = 0.f, l1 = 0.f;
+    uint32_t s0[32], s1[32];
+    if (U > 0) {
+      mbar_wait(s_full(g, 0), 0);
+      tc_fence_after();
+      tmem_ld_32x32b_x32(tlane + TCF_COL_S, s0);
+      tmem_ld_32x32b_x32(tlane + TCF_COL_S + 32, s1);
+    }
+    auto half_unit = [&](auto mask_tag, const uint32_t (&sr)[32], uint32_t (&pw)[16], int key0) {
+      constexpr bool MASKED = decltype(mask_tag)::value;
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        float p0 = exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run));
+        float p1 = exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -m_run));
+        if (MASKED) {
+          if (key0 + c >= valid_last) p0 = 0.f;
+          if (key0 + c + 1 >= valid_last) p1 = 0.f;
+        }
+        l0 += p0;
+        l1 += p1;
+        pw[c >> 1] = pack_bf16x2(p0, p1);
+      }
+    };
+    long long u = 0;
+    for (int k = 0; k < n_my; ++k) {
+      const int hh = blockIdx.x + k * gridDim.x, seq = hh / a.H, h = hh - seq * a.H;
+      bf16* ob = a.out + (long long)seq * S * a.ld_o + h * HD;
+      float* lp = a.lse2 + (long long)hh * S;
+      int x = 0;                                   // token exchanges done for this head
+      for (int t = 0; t < nbg; ++t) {
+        const int i = 2 * t + g;                   // query block
+        for (int jj = 0; jj < NU; ++jj, ++u, ++x) {
+          const uint32_t b = (uint32_t)(u & 1), bn = b ^ 1u;
+          tmem_ld_wait();                          // S(u) is in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_read(g, b));
+          const bool last = (jj == NU - 1);
+          float mx;
+          if (!last) {
+            float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              a0 = fmaxf(a0, fmaxf(__uint_as_float(s0[c]), __uint_as_float(s0[c + 1])));
+              a1 = fmaxf(a1, fmaxf(__uint_as_float(s0[c + 2]), __uint_as_float(s0[c + 3])));
+              a2 = fmaxf(a2, fmaxf(__uint_as_float(s1[c]), __uint_as_float(s1[c + 1])));
+              a3 = fmaxf(a3, fmaxf(__uint_as_float(s1[c + 2]), __uint_as_float(s1[c + 3])));
+            }
+            mx = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+          } else {
+            mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              if (c < valid_last) mx = fmaxf(mx, __uint_as_float(s0[c]));
+              if (c + 32 < valid_last) mx = fmaxf(mx, __uint_as_float(s1[c]));
+            }
+          }
+          const float m_new = mx * a.scale_log2;
+          const bool raise = m_new > m_run + TCF_LAZY;
+          if (__any_sync(0xffffffffu, raise)) {
+            const float m_upd = raise ? m_new : m_run;
+            if (jj > 0) {
+              const float f = exp2f(m_run - m_upd);
+              mbar_wait(p_empty(g, bn), (uint32_t)(((u - 1) >> 1) & 1));
+              tc_fence_after();
+              uint32_t ro[HD];
+              tmem_ld_n<HD>(tlane + TCF_COL_O, ro);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < HD; ++c) ro[c] = __float_as_uint(__uint_as_float(ro[c]) * f);
+              tmem_st_32x32b_x32(tlane + TCF_COL_O, ro);
+              l0 *= f;
+              l1 *= f;
+            }
+            m_run = m_upd;
+          }
+          // everything the exponential phase could block on is resolved BEFORE taking the token
+          if (u >= 2) {
+            mbar_wait(p_empty(g, b), (uint32_t)(((u >> 1) - 1) & 1));
+            tc_fence_after();
+          }
+          if (u + 1 < U) {
+            mbar_wait(s_full(g, bn), (uint32_t)(((u + 1) >> 1) & 1));
+            tc_fence_after();
+          }
+          uint32_t pw[16];
+          if (tokens) named_bar_sync(my_bar, 256);             // ---- take the MUFU token
+          if (last) half_unit(std::true_type{}, s0, pw, 0);
+          else half_unit(std::false_type{}, s0, pw, 0);
+          tmem_st_32x32b_x16(tlane + TCF_COL_P + b * 32, pw);
+          if (u + 1 < U) tmem_ld_32x32b_x32(tlane + TCF_COL_S + bn * 64, s0);
+          if (last) half_unit(std::true_type{}, s1, pw, 32);
+          else half_unit(std::false_type{}, s1, pw, 32);
+          if (tokens) named_bar_arrive(other_bar, 256);        // ---- pass it on
+          tmem_st_32x32b_x16(tlane + TCF_COL_P + b * 32 + 16, pw);
+          if (u + 1 < U) tmem_ld_32x32b_x32(tlane + TCF_COL_S + bn * 64 + 32, s1);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_full(g, b));
+          if (last) {
+            // ---- epilogue of query block i: O / l, log-sum-exp
+            const long long nq = (long long)k * nbg + t;
+            mbar_wait(o_full(g), (uint32_t)(nq & 1));
+            tc_fence_after();
+            uint32_t ro[HD];
+            tmem_ld_n<HD>(tlane + TCF_COL_O, ro);
+            tmem_ld_wait();
+            const float l = l0 + l1;
+            const float inv = 1.f / l;
+            const int qr = i * 128 + row;
+            if (qr < S) {
+              bf16* dst = ob + (long long)qr * a.ld_o;
+#pragma unroll
+              for (int c = 0; c < HD; c += 8) {
+                uint4 o;
+                o.x = pack_bf16x2(__uint_as_float(ro[c]) * inv, __uint_as_float(ro[c + 1]) * inv);
+                o.y = pack_bf16x2(__uint_as_float(ro[c + 2]) * inv, __uint_as_float(ro[c + 3]) * inv);
+                o.z = pack_bf16x2(__uint_as_float(ro[c + 4]) * inv, __uint_as_float(ro[c + 5]) * inv);
+                o.w = pack_bf16x2(__uint_as_float(ro[c + 6]) * inv, __uint_as_float(ro[c + 7]) * inv);
+                *reinterpret_cast<uint4*>(dst + c) = o;
+              }
+              lp[qr] = m_run + log2f(l);
+            }
+            m_run = -INFINITY; l0 = 0.f; l1 = 0.f;
+          }
+        }
+      }
+      for (; tokens && x < UX; ++x) {              // keep the exchange count equal (odd number of query blocks)
+        named_bar_sync(my_bar, 256);
+        named_bar_arrive(other_bar, 256);
+      }
+    }
+    if (tokens && g == 0) named_bar_sync(1, 256);             // absorb group 1's final hand-over
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 template <int HD>
 int launch_fwd(const TcFwdArgs& a, int n_seq, cudaStream_t stream) {
   using C = TcCfg<HD>;
   const int n_last = (((a.S - (a.NU - 1) * 64) + 15) >> 4) << 4;
-  const int smem = 2 * ((a.NU - 1) * 64 + n_last) * C::ROWB + 2 * C::BLK_BYTES + 256;
+  const int smem = 2 * ((a.NU - 1) * 64 + n_last) * C::ROWB + 2 * C::BLK_BYTES + 2048 + 256;
   static int smem_set = 0;
   if (smem > smem_set || getenv("AVS_TC_DEBUG")) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -933,9 +1316,42 @@ int avs_attention_bwd_tc(const void* qkv, long long ld_qkv, const void* dout, lo
 int avs_attention_fwd_tc(const void* qkv, long long ld_qkv, void* out, long long ld_o, float* lse2, int n_seq, int S,
                          int H, int head_dim, void* stream) {
   if (head_dim != 32 || S < 256 || S > 768) return -2;
+  static const int variant = getenv("AVS_ATTN_FWD_VARIANT") ? atoi(getenv("AVS_ATTN_FWD_VARIANT")) : 1;
+  const int NB = (S + 127) / 128, NU = (S + 63) / 64;
+  const float scale_log2 = rsqrtf((float)head_dim) * 1.4426950408889634f;
+  if (variant == 2) {
+    using C = TcCfg<32>;
+    TcPpArgs a = {};
+    const long long rows = (long long)n_seq * S;
+    int rc = avs_make_tmap_2d_bf16(&a.map128, qkv, rows, 3LL * H * head_dim, ld_qkv, head_dim, 128, 64);
+    if (rc) return rc;
+    if ((rc = avs_make_tmap_2d_bf16(&a.map16, qkv, rows, 3LL * H * head_dim, ld_qkv, head_dim, 16, 64))) return rc;
+    a.out = (bf16*)out; a.lse2 = lse2; a.ld_o = ld_o; a.S = S; a.NB = NB; a.NU = NU; a.H = H; a.D = H * head_dim;
+    a.n_heads = n_seq * H;
+    a.scale_log2 = scale_log2;
+    static const int tokens = getenv("AVS_ATTN_FWD_TOKENS") ? atoi(getenv("AVS_ATTN_FWD_TOKENS")) : 1;
+    a.tokens = tokens;
+    const int n_last = (((S - (NU - 1) * 64) + 15) >> 4) << 4;
+    const int kv_rows = (NU - 1) * 64 + n_last;
+    const int smem = 1024 + 4 * kv_rows * C::ROWB + 4 * C::BLK_BYTES + 512;
+    if (smem <= 227 * 1024) {
+      static int smem_set = 0;
+      if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_pp_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+          avs_set_error("avs_attention_fwd(tc): cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+          return (int)e;
+        }
+        smem_set = smem;
+      }
+      const int grid = min(avs_num_sms(), a.n_heads);
+      attn_fwd_pp_kernel<32><<<grid, TCP_THREADS, smem, (cudaStream_t)stream>>>(a);
+      return avs_check_launch("attn_fwd_pp_kernel");
+    }
+  }
   TcFwdArgs a = {};
   a.qkv = (const bf16*)qkv; a.out = (bf16*)out; a.lse2 = lse2;
-  a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.S = S; a.NB = (S + 127) / 128; a.NU = (S + 63) / 64; a.H = H; a.D = H * head_dim;
-  a.scale_log2 = rsqrtf((float)head_dim) * 1.4426950408889634f;
+  a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.S = S; a.NB = NB; a.NU = NU; a.H = H; a.D = H * head_dim;
+  a.scale_log2 = scale_log2;
   return launch_fwd<32>(a, n_seq, (cudaStream_t)stream);
 }

@@ -93,6 +93,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// For producers that wait a long time for a buffer to drain (persistent kernels): the plain loop above retries every
+// ~12 cycles and takes issue slots and mbarrier bandwidth from the compute warps of the same SM sub-partition.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns = 256) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 
 // ---- TMA ----
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

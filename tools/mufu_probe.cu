@@ -27,6 +27,48 @@ __global__ void probe(float* out, int iters, float seed, long long* cycles) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
 }
 
+// the softmax inner loop of the attention kernels: per element FFMA (scale, subtract max) -> EX2 -> (row sum FADD) ->
+// one F2FP per pair.  32 independent elements per iteration, like one tcgen05.ld chunk.
+template <bool SUM>
+__global__ void mix_probe(uint32_t* out, int iters, float seed, long long* cycles) {
+  float s[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s[i] = seed * 0.01f * (threadIdx.x + i);
+  float l0 = 0.f, l1 = 0.f;
+  uint32_t acc = 0;
+  const float scale = 1.0001f + seed * 1e-6f, m = 3.f * seed;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t pw[16];
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      float p0, p1;
+      asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(s[c], scale, -m)));
+      asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(s[c + 1], scale, -m)));
+      if (SUM) { l0 += p0; l1 += p1; }
+      asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pw[c >> 1]) : "f"(p1), "f"(p0));
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc ^= pw[c];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s[i] += 0.001f;           // new scores every iteration (1 FADD per element, like a max)
+  }
+  const long long t1 = clock64();
+  if (acc == 0x12345 || l0 + l1 == 0.12345f) out[threadIdx.x] = acc;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+
+template <bool SUM>
+void run_mix(const char* name, float* d, long long* dc, int warps_per_sm) {
+  const int iters = 2048, blocks = 148, threads = 32 * warps_per_sm;
+  mix_probe<SUM><<<blocks, threads>>>((uint32_t*)d, 16, 1.f, dc);
+  mix_probe<SUM><<<blocks, threads>>>((uint32_t*)d, iters, 1.f, dc);
+  cudaDeviceSynchronize();
+  long long c; cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
+  printf("%-22s warps/SM=%2d: %.1f cycles per EX2 per warp, %.1f EX2 lanes per clk per SM  (%s)\n", name, warps_per_sm,
+         (double)c / (iters * 32.0), (double)threads * iters * 32 / (double)c, cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int MODE>
 void run(const char* name, float* d, long long* dc, int warps_per_sm) {
   const int iters = 2048, blocks = 148, threads = 32 * warps_per_sm;
@@ -46,6 +88,10 @@ int main() {
     run<1>("fma", d, dc, w);
     run<2>("ex2 + fma", d, dc, w);
     run<3>("rcp.approx", d, dc, w);
+  }
+  for (int w : {4, 8, 16}) {
+    run_mix<true>("ffma+ex2+fadd+f2fp", d, dc, w);
+    run_mix<false>("ffma+ex2+f2fp", d, dc, w);
   }
   return 0;
 }
