@@ -584,15 +584,29 @@ int launch_bwd(const TcArgs& a, int n_seq, cudaStream_t stream) {
 //     of a query block and almost never afterwards, so there is no correction warp and no second pass.
 //   * P goes back to TENSOR MEMORY as packed bf16 and is the A operand of the P V product (tcgen05.mma with A in TMEM),
 //     so the probabilities never touch shared memory.
-//   * one CTA = one (sequence, head), 6 warps (loader, MMA issuer, 4 softmax warps = the 4 TMEM lane quarters),
-//     K and V of the whole head resident in swizzled shared memory (2 x 45 KB), Q blocks streamed (2 x 8 KB),
+//   * row sums on the tensor pipe too: L += P x ones (a 16-column product per k-step), so the softmax warps spend no
+//     FADD per element and the sum is taken over exactly the bf16 probabilities that multiply V.
+//   * one CTA = one (sequence, head), 10 warps: loader, MMA issuer, 8 softmax warps (the two warps of a TMEM lane
+//     quarter split the unit's 64 key columns and agree on the row maximum through shared memory + a 64-thread named
+//     barrier).  K and V of the whole head resident in swizzled shared memory (2 x 45 KB), Q blocks streamed (2 x 8 KB),
 //     256 TMEM columns: TWO CTAs PER SM (the occupancy API reports 1 for any kernel with tcgen05.alloc; the hardware
-//     co-schedules two 256-column CTAs — tools/tmem_occ_probe.cu), so one CTA's prologue / epilogue runs under the
-//     other's MUFU work.
+//     co-schedules two 256-column CTAs — tools/tmem_occ_probe.cu), i.e. 4 softmax warps per SM sub-partition: one warp
+//     alone reaches only 55-70 % of the EX2 rate with this instruction mix, two or more 86-97 % (tools/mufu_probe.cu).
+// Measured (S = 708, 4096 heads): 0.955 ms against 0.950 ms for the mma.sync kernel in isolation, 1.1 ms per training
+// step faster in the power-capped step.  Timing experiments: without the exponentials the kernel still takes 0.72 ms —
+// ~7.5 warp-instructions per score element (barrier handling and loop control amortised over only 32 elements per
+// thread and unit) make it issue-bound before it is MUFU-bound (MUFU floor 0.54 ms); 128-key units are the next step.
 // Work unit = 64 keys: S[b] (64 fp32 columns, double-buffered) -> P[b] (32 packed columns, double-buffered) -> O.
 // The last unit of a sequence only takes as many 16-key steps as it has valid keys (S = 708: N = 16).
 // =====================================================================================================
-constexpr int TCF_SOFTMAX_WARPS = 4;
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+
+constexpr int TCF_SOFTMAX_WARPS = 8;
 constexpr int TCF_FIRST_SOFTMAX_WARP = 2;
 constexpr int TCF_THREADS = 32 * (TCF_FIRST_SOFTMAX_WARP + TCF_SOFTMAX_WARPS);
 constexpr int TCF_COL_S = 0, TCF_COL_P = 128, TCF_COL_O = 192, TCF_COL_L = 224, TCF_TMEM_COLS = 256;
@@ -633,6 +647,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
   uint64_t* p_empty = bars + 10;    // [2] issuer (commit) -> softmax: P V of that unit has retired
   uint64_t* o_full = bars + 12;     // issuer (commit) -> softmax: O of a query block complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  float* s_mx = reinterpret_cast<float*>(bars + 16);   // [2][2][128] partial row maxima (unit parity, column half, row)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, seq = blockIdx.y;
@@ -740,123 +755,114 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
     }
   } else {
     // ============================ softmax warps ============================
+    // 8 warps: the two warps of a TMEM lane quarter split the unit's 64 key columns (32 each), so every SM
+    // sub-partition runs 4 softmax warps (2 per CTA x 2 CTAs).  One warp alone cannot keep the MUFU pipe busy with this
+    // instruction mix (tools/mufu_probe.cu: 55-70 % of the EX2 rate; two or more reach 86-97 %).
+    const int sw = warp - TCF_FIRST_SOFTMAX_WARP;
     const int quarter = warp & 3;                   // the TMEM lane quarter this warp may access
+    const int half = sw >> 2;                       // which 32 of the unit's 64 key columns
     const int row = quarter * 32 + lane;            // query row inside the block == TMEM lane
     const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
     bf16* ob = a.out + row_base * a.ld_o + h * HD;
     float* lp = a.lse2 + ((long long)seq * a.H + h) * S;
-    const int valid_last = S - (NU - 1) * 64;       // valid keys of the last unit (1 .. 64)
+    const int valid_last = S - (NU - 1) * 64 - half * 32;   // valid keys among this warp's 32 columns of the last unit
     float m_run = -INFINITY;
-    uint32_t s0[32], s1[32];                        // scores of the current unit, keys 0-31 / 32-63
-    mbar_wait(&s_full[0], 0);
-    tc_fence_after();
-    tmem_ld_32x32b_x32(tlane + TCF_COL_S, s0);
-    tmem_ld_32x32b_x32(tlane + TCF_COL_S + 32, s1);
-
-    // one 32-key half: exponentials, row sum, bf16 pairs.  MASKED only in the last unit of the sequence (keys at or
-    // beyond S): the interior units carry no per-element predicates
-    auto half_unit = [&](auto mask_tag, const uint32_t (&sr)[32], uint32_t (&pw)[16], int key0) {
-      constexpr bool MASKED = decltype(mask_tag)::value;
-#pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        float p0 = exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run));
-        float p1 = exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -m_run));
-        if (MASKED) {
-          if (key0 + c >= valid_last) p0 = 0.f;
-          if (key0 + c + 1 >= valid_last) p1 = 0.f;
-        }
-        pw[c >> 1] = pack_bf16x2(p0, p1);
-      }
-    };
     int jj = 0, i = 0;
     for (int u = 0; u < U; ++u) {
-      const uint32_t b = (uint32_t)(u & 1), pb = b, bn = b ^ 1u;
-      tmem_ld_wait();                                  // S(u) is in registers
+      const uint32_t b = (uint32_t)(u & 1);
+      mbar_wait(&s_full[b], (uint32_t)((u >> 1) & 1));
+      tc_fence_after();
+      uint32_t sr[32];
+      tmem_ld_32x32b_x32(tlane + TCF_COL_S + b * 64 + half * 32, sr);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_read[b]);
       const bool last = (jj == NU - 1);
-      // ---- running maximum (lazy): raw-score max of the unit's valid keys
+      // ---- running maximum (lazy), agreed between the two warps that share this row
       float mx;
       if (!last) {
-        float a0 = -INFINITY, a1 = -INFINITY;
+        float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          a0 = fmaxf(a0, fmaxf(__uint_as_float(s0[c]), __uint_as_float(s0[c + 1])));
-          a1 = fmaxf(a1, fmaxf(__uint_as_float(s1[c]), __uint_as_float(s1[c + 1])));
+        for (int c = 0; c < 32; c += 8) {
+          a0 = fmaxf(a0, fmaxf(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])));
+          a1 = fmaxf(a1, fmaxf(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])));
+          a2 = fmaxf(a2, fmaxf(__uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5])));
+          a3 = fmaxf(a3, fmaxf(__uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7])));
         }
-        mx = fmaxf(a0, a1);
+        mx = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
       } else {
         mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          if (c < valid_last) mx = fmaxf(mx, __uint_as_float(s0[c]));
-          if (c + 32 < valid_last) mx = fmaxf(mx, __uint_as_float(s1[c]));
-        }
+        for (int c = 0; c < 32; ++c)
+          if (c < valid_last) mx = fmaxf(mx, __uint_as_float(sr[c]));
       }
+      s_mx[(u & 1) * 256 + half * 128 + row] = mx;
+      named_bar_sync(1 + quarter, 64);                 // the two warps of this lane quarter
+      mx = fmaxf(mx, s_mx[(u & 1) * 256 + (half ^ 1) * 128 + row]);
       const float m_new = mx * a.scale_log2;            // scale > 0 commutes with max
       const bool raise = m_new > m_run + TCF_LAZY;      // always true in the first unit of a query block (m_run = -inf)
       if (__any_sync(0xffffffffu, raise)) {
         const float m_upd = raise ? m_new : m_run;
-        if (jj > 0) {
-          // O and l were accumulated against the old maximum: rescale (factor 1 for the rows that keep theirs).
+        if (jj > 0 && half == 0) {
+          // O and L were accumulated against the old maximum: rescale (factor 1 for the rows that keep theirs).
           // Every P V product issued so far must have retired before O is read: the latest one signals p_empty.
           const float f = exp2f(m_run - m_upd);
-          mbar_wait(&p_empty[bn], (uint32_t)(((u - 1) >> 1) & 1));
+          mbar_wait(&p_empty[b ^ 1u], (uint32_t)(((u - 1) >> 1) & 1));
           tc_fence_after();
-          uint32_t ro[HD];
+          uint32_t ro[HD], rl[1];
           tmem_ld_n<HD>(tlane + TCF_COL_O, ro);
+          tmem_ld_32x32b_x1(tlane + TCF_COL_L, rl);      // only column 0 of L is ever read back
           tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < HD; ++c) ro[c] = __float_as_uint(__uint_as_float(ro[c]) * f);
-          tmem_st_32x32b_x32(tlane + TCF_COL_O, ro);
-          uint32_t rl[1];
-          tmem_ld_32x32b_x1(tlane + TCF_COL_L, rl);      // only column 0 of L is ever read back
-          tmem_ld_wait();
           rl[0] = __float_as_uint(__uint_as_float(rl[0]) * f);
+          tmem_st_32x32b_x32(tlane + TCF_COL_O, ro);
           tmem_st_32x32b_x1(tlane + TCF_COL_L, rl);
         }
         m_run = m_upd;
       }
       uint32_t pw[16];
-      // ---- half 0: keys 0 .. 31 of the unit
-      if (last) half_unit(std::true_type{}, s0, pw, 0);
-      else half_unit(std::false_type{}, s0, pw, 0);
+      if (!last) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 2)
+          pw[c >> 1] = pack_bf16x2(exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run)),
+                                   exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -m_run)));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float p0 = exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run));
+          float p1 = exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -m_run));
+          if (c >= valid_last) p0 = 0.f;
+          if (c + 1 >= valid_last) p1 = 0.f;
+          pw[c >> 1] = pack_bf16x2(p0, p1);
+        }
+      }
       if (u >= 2) {
-        mbar_wait(&p_empty[pb], (uint32_t)(((u >> 1) - 1) & 1));
+        mbar_wait(&p_empty[b], (uint32_t)(((u >> 1) - 1) & 1));
         tc_fence_after();
       }
-      tmem_st_32x32b_x16(tlane + TCF_COL_P + pb * 32, pw);
-      if (u + 1 < U) {      // the registers of this half take the same half of S(u+1) while half 1 is computed
-        mbar_wait(&s_full[bn], (uint32_t)(((u + 1) >> 1) & 1));
-        tc_fence_after();
-        tmem_ld_32x32b_x32(tlane + TCF_COL_S + bn * 64, s0);
-      }
-      // ---- half 1: keys 32 .. 63
-      if (last) half_unit(std::true_type{}, s1, pw, 32);
-      else half_unit(std::false_type{}, s1, pw, 32);
-      tmem_st_32x32b_x16(tlane + TCF_COL_P + pb * 32 + 16, pw);
-      if (u + 1 < U) tmem_ld_32x32b_x32(tlane + TCF_COL_S + bn * 64 + 32, s1);
+      tmem_st_32x32b_x16(tlane + TCF_COL_P + b * 32 + half * 16, pw);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[pb]);
+      if (lane == 0) mbar_arrive(&p_full[b]);
       if (last) {
-        // ---- epilogue of query block i: O / l, log-sum-exp
+        // ---- epilogue of query block i: O / l, log-sum-exp (each warp stores half of the head_dim columns)
         mbar_wait(o_full, (uint32_t)(i & 1));
         tc_fence_after();
-        uint32_t ro[HD];
-        uint32_t rl[1];
-        tmem_ld_n<HD>(tlane + TCF_COL_O, ro);
+        constexpr int EC = HD / 2;
+        uint32_t ro[EC], rl[1];
+        tmem_ld_n<EC>(tlane + TCF_COL_O + half * EC, ro);
         tmem_ld_32x32b_x1(tlane + TCF_COL_L, rl);
-        tmem_ld_wait();   // (also completes the prefetch of the next unit's scores)
+        tmem_ld_wait();
         const float l = __uint_as_float(rl[0]);
         const float inv = 1.f / l;
         const int qr = i * 128 + row;
         if (qr < S) {
-          bf16* dst = ob + (long long)qr * a.ld_o;
+          bf16* dst = ob + (long long)qr * a.ld_o + half * EC;
 #pragma unroll
-          for (int c = 0; c < HD; c += 8) {
+          for (int c = 0; c < EC; c += 8) {
             uint4 o;
             o.x = pack_bf16x2(__uint_as_float(ro[c]) * inv, __uint_as_float(ro[c + 1]) * inv);
             o.y = pack_bf16x2(__uint_as_float(ro[c + 2]) * inv, __uint_as_float(ro[c + 3]) * inv);
@@ -864,10 +870,10 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
             o.w = pack_bf16x2(__uint_as_float(ro[c + 6]) * inv, __uint_as_float(ro[c + 7]) * inv);
             *reinterpret_cast<uint4*>(dst + c) = o;
           }
-          lp[qr] = m_run + log2f(l);
+          if (half == 0) lp[qr] = m_run + log2f(l);
         }
-        // the first P V of the next query block (accumulate = 0 into O) is issued only after these warps have produced
-        // its P, i.e. after the tcgen05.ld above has completed: no extra barrier needed
+        // the first P V of the next query block (accumulate = 0 into O / L) is issued only after all 8 warps have
+        // produced its P, i.e. after the tcgen05.ld above has completed in each of them: no extra barrier needed
         m_run = -INFINITY;
         jj = 0; ++i;
       } else {
@@ -910,12 +916,6 @@ struct TcPpArgs {
   float scale_log2;
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int count) {
-  asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory");
-}
 
 template <int HD>
 __global__ void __launch_bounds__(TCP_THREADS, 1) attn_fwd_pp_kernel(const __grid_constant__ TcPpArgs a) {
@@ -1251,7 +1251,7 @@ template <int HD>
 int launch_fwd(const TcFwdArgs& a, int n_seq, cudaStream_t stream) {
   using C = TcCfg<HD>;
   const int n_last = (((a.S - (a.NU - 1) * 64) + 15) >> 4) << 4;
-  const int smem = 2 * ((a.NU - 1) * 64 + n_last) * C::ROWB + 2 * C::BLK_BYTES + 2048 + 256;
+  const int smem = 2 * ((a.NU - 1) * 64 + n_last) * C::ROWB + 2 * C::BLK_BYTES + 2048 + 128 + 2048;
   static int smem_set = 0;
   if (smem > smem_set || getenv("AVS_TC_DEBUG")) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
