@@ -609,7 +609,7 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
 constexpr int TCF_SOFTMAX_WARPS = 8;
 constexpr int TCF_FIRST_SOFTMAX_WARP = 2;
 constexpr int TCF_THREADS = 32 * (TCF_FIRST_SOFTMAX_WARP + TCF_SOFTMAX_WARPS);
-constexpr int TCF_COL_S = 0, TCF_COL_P = 128, TCF_COL_O = 192, TCF_COL_L = 224, TCF_TMEM_COLS = 256;
+constexpr int TCF_COL_S = 0, TCF_COL_P = 128, TCF_COL_O = 192, TCF_COL_L = 224, TCF_TMEM_COLS = 256;   // S 128 | P 64 | O 32 | L 16
 constexpr float TCF_LAZY = 8.0f;   // log2 of the largest probability tolerated before the running maximum is raised
 
 struct TcFwdArgs {
@@ -630,9 +630,9 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
   uint8_t* smem = tc_smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  const int S = a.S, NB = a.NB, NU = a.NU;
-  const int n_last = (((S - (NU - 1) * 64) + 15) >> 4) << 4;   // MMA N of the last unit (16 .. 64)
-  const int kv_rows = (NU - 1) * 64 + n_last;                   // rows the MMAs touch (multiple of 16: tiles stay 1 KB aligned)
+  const int S = a.S, NB = a.NB, NU = a.NU;                      // NU = 128-key units
+  const int n_last = (((S - (NU - 1) * 128) + 15) >> 4) << 4;  // MMA N of the last unit (16 .. 128)
+  const int kv_rows = (NU - 1) * 128 + n_last;                  // rows the MMAs touch (multiple of 16: tiles stay 1 KB aligned)
   const uint32_t sK = smem_u32(smem);
   const uint32_t sV = sK + kv_rows * C::ROWB;
   const uint32_t sQ = sV + kv_rows * C::ROWB;          // [2] 128-row blocks
@@ -641,12 +641,12 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kv_rows * C::ROWB + 2 * C::BLK_BYTES + 2048);
   uint64_t* q_full = bars;          // [2] loader -> issuer
   uint64_t* q_empty = bars + 2;     // [2] issuer (commit) -> loader
-  uint64_t* s_full = bars + 4;      // [2] issuer (commit) -> softmax: S unit in TMEM
-  uint64_t* s_read = bars + 6;      // [2] softmax -> issuer: S unit is in registers
-  uint64_t* p_full = bars + 8;      // [2] softmax -> issuer: P unit written to TMEM
-  uint64_t* p_empty = bars + 10;    // [2] issuer (commit) -> softmax: P V of that unit has retired
-  uint64_t* o_full = bars + 12;     // issuer (commit) -> softmax: O of a query block complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* s_full = bars + 4;      // issuer (commit) -> softmax: S unit in TMEM
+  uint64_t* s_read = bars + 5;      // softmax -> issuer: every warp has made its last read of the S unit
+  uint64_t* p_full = bars + 6;      // softmax -> issuer: P unit written to TMEM
+  uint64_t* p_empty = bars + 7;     // issuer (commit) -> softmax: P V of that unit has retired
+  uint64_t* o_full = bars + 8;      // issuer (commit) -> softmax: O of a query block complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   float* s_mx = reinterpret_cast<float*>(bars + 16);   // [2][2][128] partial row maxima (unit parity, column half, row)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -658,11 +658,11 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_read[i], TCF_SOFTMAX_WARPS);
-      mbar_init(&p_full[i], TCF_SOFTMAX_WARPS);
-      mbar_init(&p_empty[i], 1);
     }
+    mbar_init(s_full, 1);
+    mbar_init(s_read, TCF_SOFTMAX_WARPS);
+    mbar_init(p_full, TCF_SOFTMAX_WARPS);
+    mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
     fence_mbar_init();
   }
@@ -697,20 +697,19 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    // The S stream runs two units ahead of the P V stream: S(u+2) is issued the moment the softmax warps hold S(u) in
-    // registers (both S buffers always in flight), O += P(u) V when P(u) has been written.
+    // S and P are single-buffered: with 128-key units the softmax work on unit u (>= 600 cycles) covers both the
+    // S(u+1) product, issued as soon as the warps have made their last read of S(u), and the retirement of P(u-1) V.
     constexpr uint32_t ID_PV = idesc_bf16(128, HD, 0, 1);     // A = P in TMEM, B = V rows MN-major
-    constexpr uint32_t K16ROWS = (16 * C::ROWB) >> 4, UNIT16 = (64 * C::ROWB) >> 4, BLK16 = C::BLK_BYTES >> 4;
+    constexpr uint32_t K16ROWS = (16 * C::ROWB) >> 4, UNIT16 = (128 * C::ROWB) >> 4, BLK16 = C::BLK_BYTES >> 4;
     const uint64_t kQ = make_desc(sQ, 0, C::SBO, C::LT), kK = make_desc(sK, 0, C::SBO, C::LT);
     const uint64_t mV = make_desc(sV, C::SBO, C::SBO, C::LT);
-    const uint32_t id_s_full = idesc_bf16(128, 64, 0, 0), id_s_last = idesc_bf16(128, n_last, 0, 0);
+    const uint32_t id_s_full = idesc_bf16(128, 128, 0, 0), id_s_last = idesc_bf16(128, n_last, 0, 0);
     // row sums on the tensor pipe: L[128 x 16] += P[128 x 16 keys] * ones[16 keys x 16] — every column of L is the
     // row sum of the bf16 probabilities that also multiply V (one FADD per element less on the softmax warps)
     constexpr uint32_t ID_L = idesc_bf16(128, 16, 0, 0);
     const uint64_t kOnes = make_desc(sOnes, 128, 128, 0u);
     int si = 0, sj = 0;          // S stream position: query block, key unit
-    auto issue_s = [&](int v) {
-      const uint32_t b = (uint32_t)(v & 1);
+    auto issue_s = [&]() {
       if (sj == 0) {
         mbar_wait(&q_full[si & 1], (uint32_t)((si >> 1) & 1));
         tc_fence_after();
@@ -720,34 +719,33 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
         const uint32_t id = (sj == NU - 1) ? id_s_last : id_s_full;
 #pragma unroll
         for (int k = 0; k < C::KSTEPS; ++k)
-          umma_bf16_ss(tmem + TCF_COL_S + b * 64, kQ + (qo + 2 * k), kK + (ko + 2 * k), id, k > 0 ? 1u : 0u);
-        umma_commit(&s_full[b]);
+          umma_bf16_ss(tmem + TCF_COL_S, kQ + (qo + 2 * k), kK + (ko + 2 * k), id, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
         if (sj == NU - 1) umma_commit(&q_empty[si & 1]);    // last read of this Q block
       }
       __syncwarp();
       if (++sj == NU) { sj = 0; ++si; }
     };
-    issue_s(0);
-    if (U > 1) issue_s(1);
+    issue_s();
     int pj = 0;                  // key unit of the P V stream
     for (int u = 0; u < U; ++u) {
-      const uint32_t b = (uint32_t)(u & 1);
-      if (u + 2 < U) {
-        mbar_wait(&s_read[b], (uint32_t)((u >> 1) & 1));
+      const uint32_t par = (uint32_t)(u & 1);
+      if (u + 1 < U) {
+        mbar_wait(s_read, par);
         tc_fence_after();
-        issue_s(u + 2);
+        issue_s();
       }
-      mbar_wait(&p_full[b], (uint32_t)((u >> 1) & 1));
+      mbar_wait(p_full, par);
       tc_fence_after();
-      const int ksteps = (pj == NU - 1) ? (n_last >> 4) : 4;
+      const int ksteps = (pj == NU - 1) ? (n_last >> 4) : 8;
       const uint32_t vo = (uint32_t)pj * UNIT16;
       if (elect_one_sync()) {
         for (int k = 0; k < ksteps; ++k) {
-          umma_bf16_ts(tmem + TCF_COL_O, tmem + TCF_COL_P + b * 32 + k * 8, mV + (vo + k * K16ROWS), ID_PV,
+          umma_bf16_ts(tmem + TCF_COL_O, tmem + TCF_COL_P + k * 8, mV + (vo + k * K16ROWS), ID_PV,
                        (pj > 0 || k > 0) ? 1u : 0u);
-          umma_bf16_ts(tmem + TCF_COL_L, tmem + TCF_COL_P + b * 32 + k * 8, kOnes, ID_L, (pj > 0 || k > 0) ? 1u : 0u);
+          umma_bf16_ts(tmem + TCF_COL_L, tmem + TCF_COL_P + k * 8, kOnes, ID_L, (pj > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&p_empty[b]);
+        umma_commit(p_empty);
         if (pj == NU - 1) umma_commit(o_full);
       }
       __syncwarp();
@@ -755,61 +753,66 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
     }
   } else {
     // ============================ softmax warps ============================
-    // 8 warps: the two warps of a TMEM lane quarter split the unit's 64 key columns (32 each), so every SM
+    // 8 warps: the two warps of a TMEM lane quarter split the unit's 128 key columns (64 each), so every SM
     // sub-partition runs 4 softmax warps (2 per CTA x 2 CTAs).  One warp alone cannot keep the MUFU pipe busy with this
     // instruction mix (tools/mufu_probe.cu: 55-70 % of the EX2 rate; two or more reach 86-97 %).
+    // Each unit is read from TMEM twice in 32-column chunks — once for the row maximum, once for the exponentials —
+    // which keeps the scores out of long-lived registers (tcgen05.ld is one instruction per 32 elements).
     const int sw = warp - TCF_FIRST_SOFTMAX_WARP;
     const int quarter = warp & 3;                   // the TMEM lane quarter this warp may access
-    const int half = sw >> 2;                       // which 32 of the unit's 64 key columns
+    const int half = sw >> 2;                       // which 64 of the unit's 128 key columns
     const int row = quarter * 32 + lane;            // query row inside the block == TMEM lane
     const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t tS = tlane + TCF_COL_S + half * 64, tP = tlane + TCF_COL_P + half * 32;
     bf16* ob = a.out + row_base * a.ld_o + h * HD;
     float* lp = a.lse2 + ((long long)seq * a.H + h) * S;
-    const int valid_last = S - (NU - 1) * 64 - half * 32;   // valid keys among this warp's 32 columns of the last unit
+    const int valid_last = S - (NU - 1) * 128 - half * 64;   // valid keys among this warp's 64 columns of the last unit
     float m_run = -INFINITY;
     int jj = 0, i = 0;
     for (int u = 0; u < U; ++u) {
-      const uint32_t b = (uint32_t)(u & 1);
-      mbar_wait(&s_full[b], (uint32_t)((u >> 1) & 1));
-      tc_fence_after();
-      uint32_t sr[32];
-      tmem_ld_32x32b_x32(tlane + TCF_COL_S + b * 64 + half * 32, sr);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_read[b]);
+      const uint32_t par = (uint32_t)(u & 1);
       const bool last = (jj == NU - 1);
-      // ---- running maximum (lazy), agreed between the two warps that share this row
-      float mx;
-      if (!last) {
-        float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+      mbar_wait(s_full, par);
+      tc_fence_after();
+      // ---- pass A: row maximum of this warp's 64 columns
+      float mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 32; c += 8) {
-          a0 = fmaxf(a0, fmaxf(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])));
-          a1 = fmaxf(a1, fmaxf(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])));
-          a2 = fmaxf(a2, fmaxf(__uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5])));
-          a3 = fmaxf(a3, fmaxf(__uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7])));
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t sr[32];
+        tmem_ld_32x32b_x32(tS + ch * 32, sr);
+        tmem_ld_wait();
+        if (!last) {
+          float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            a0 = fmaxf(a0, fmaxf(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])));
+            a1 = fmaxf(a1, fmaxf(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])));
+            a2 = fmaxf(a2, fmaxf(__uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5])));
+            a3 = fmaxf(a3, fmaxf(__uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7])));
+          }
+          mx = fmaxf(mx, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (ch * 32 + c < valid_last) mx = fmaxf(mx, __uint_as_float(sr[c]));
         }
-        mx = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-      } else {
-        mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c < valid_last) mx = fmaxf(mx, __uint_as_float(sr[c]));
       }
-      s_mx[(u & 1) * 256 + half * 128 + row] = mx;
+      // ---- running maximum (lazy), agreed between the two warps that share this row
+      s_mx[par * 256 + half * 128 + row] = mx;
       named_bar_sync(1 + quarter, 64);                 // the two warps of this lane quarter
-      mx = fmaxf(mx, s_mx[(u & 1) * 256 + (half ^ 1) * 128 + row]);
+      mx = fmaxf(mx, s_mx[par * 256 + (half ^ 1) * 128 + row]);
       const float m_new = mx * a.scale_log2;            // scale > 0 commutes with max
       const bool raise = m_new > m_run + TCF_LAZY;      // always true in the first unit of a query block (m_run = -inf)
+      // P(u-1) V (and with it every earlier product into O / L) must have retired before P is overwritten or O rescaled
+      if (u >= 1) {
+        mbar_wait(p_empty, (uint32_t)((u - 1) & 1));
+        tc_fence_after();
+      }
       if (__any_sync(0xffffffffu, raise)) {
         const float m_upd = raise ? m_new : m_run;
         if (jj > 0 && half == 0) {
-          // O and L were accumulated against the old maximum: rescale (factor 1 for the rows that keep theirs).
-          // Every P V product issued so far must have retired before O is read: the latest one signals p_empty.
+          // O and L were accumulated against the old maximum: rescale (factor 1 for the rows that keep theirs)
           const float f = exp2f(m_run - m_upd);
-          mbar_wait(&p_empty[b ^ 1u], (uint32_t)(((u - 1) >> 1) & 1));
-          tc_fence_after();
           uint32_t ro[HD], rl[1];
           tmem_ld_n<HD>(tlane + TCF_COL_O, ro);
           tmem_ld_32x32b_x1(tlane + TCF_COL_L, rl);      // only column 0 of L is ever read back
@@ -822,31 +825,38 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
         }
         m_run = m_upd;
       }
-      uint32_t pw[16];
-      if (!last) {
+      // ---- pass B: P = exp2(S * scale - max) -> bf16 pairs -> TMEM
 #pragma unroll
-        for (int c = 0; c < 32; c += 2)
-          pw[c >> 1] = pack_bf16x2(exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run)),
-                                   exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -m_run)));
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float p0 = exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run));
-          float p1 = exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -m_run));
-          if (c >= valid_last) p0 = 0.f;
-          if (c + 1 >= valid_last) p1 = 0.f;
-          pw[c >> 1] = pack_bf16x2(p0, p1);
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t sr[32], pw[16];
+        tmem_ld_32x32b_x32(tS + ch * 32, sr);
+        tmem_ld_wait();
+        if (ch == 1) {                                  // last read of S(u): the issuer may overwrite the buffer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_read);
         }
+        if (!last) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 2)
+            pw[c >> 1] = pack_bf16x2(exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run)),
+                                     exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -m_run)));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float p0 = exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run));
+            float p1 = exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -m_run));
+            if (ch * 32 + c >= valid_last) p0 = 0.f;
+            if (ch * 32 + c + 1 >= valid_last) p1 = 0.f;
+            pw[c >> 1] = pack_bf16x2(p0, p1);
+          }
+        }
+        tmem_st_32x32b_x16(tP + ch * 16, pw);
       }
-      if (u >= 2) {
-        mbar_wait(&p_empty[b], (uint32_t)(((u >> 1) - 1) & 1));
-        tc_fence_after();
-      }
-      tmem_st_32x32b_x16(tlane + TCF_COL_P + b * 32 + half * 16, pw);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[b]);
+      if (lane == 0) mbar_arrive(p_full);
       if (last) {
         // ---- epilogue of query block i: O / l, log-sum-exp (each warp stores half of the head_dim columns)
         mbar_wait(o_full, (uint32_t)(i & 1));
@@ -1250,8 +1260,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) attn_fwd_pp_kernel(const __gri
 template <int HD>
 int launch_fwd(const TcFwdArgs& a, int n_seq, cudaStream_t stream) {
   using C = TcCfg<HD>;
-  const int n_last = (((a.S - (a.NU - 1) * 64) + 15) >> 4) << 4;
-  const int smem = 2 * ((a.NU - 1) * 64 + n_last) * C::ROWB + 2 * C::BLK_BYTES + 2048 + 128 + 2048;
+  const int n_last = (((a.S - (a.NU - 1) * 128) + 15) >> 4) << 4;
+  const int smem = 2 * ((a.NU - 1) * 128 + n_last) * C::ROWB + 2 * C::BLK_BYTES + 2048 + 128 + 2048;
   static int smem_set = 0;
   if (smem > smem_set || getenv("AVS_TC_DEBUG")) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1351,7 +1361,7 @@ int avs_attention_fwd_tc(const void* qkv, long long ld_qkv, void* out, long long
   }
   TcFwdArgs a = {};
   a.qkv = (const bf16*)qkv; a.out = (bf16*)out; a.lse2 = lse2;
-  a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.S = S; a.NB = NB; a.NU = NU; a.H = H; a.D = H * head_dim;
+  a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.S = S; a.NB = NB; a.NU = (S + 127) / 128; a.H = H; a.D = H * head_dim;   // 128-key units
   a.scale_log2 = scale_log2;
   return launch_fwd<32>(a, n_seq, (cudaStream_t)stream);
 }
