@@ -587,17 +587,18 @@ int launch_bwd(const TcArgs& a, int n_seq, cudaStream_t stream) {
 //   * row sums on the tensor pipe too: L += P x ones (a 16-column product per k-step), so the softmax warps spend no
 //     FADD per element and the sum is taken over exactly the bf16 probabilities that multiply V.
 //   * one CTA = one (sequence, head), 10 warps: loader, MMA issuer, 8 softmax warps (the two warps of a TMEM lane
-//     quarter split the unit's 64 key columns and agree on the row maximum through shared memory + a 64-thread named
+//     quarter split the unit's 128 key columns and agree on the row maximum through shared memory + a 64-thread named
 //     barrier).  K and V of the whole head resident in swizzled shared memory (2 x 45 KB), Q blocks streamed (2 x 8 KB),
 //     256 TMEM columns: TWO CTAs PER SM (the occupancy API reports 1 for any kernel with tcgen05.alloc; the hardware
 //     co-schedules two 256-column CTAs — tools/tmem_occ_probe.cu), i.e. 4 softmax warps per SM sub-partition: one warp
 //     alone reaches only 55-70 % of the EX2 rate with this instruction mix, two or more 86-97 % (tools/mufu_probe.cu).
-// Measured (S = 708, 4096 heads): 0.955 ms against 0.950 ms for the mma.sync kernel in isolation, 1.1 ms per training
-// step faster in the power-capped step.  Timing experiments: without the exponentials the kernel still takes 0.72 ms —
-// ~7.5 warp-instructions per score element (barrier handling and loop control amortised over only 32 elements per
-// thread and unit) make it issue-bound before it is MUFU-bound (MUFU floor 0.54 ms); 128-key units are the next step.
-// Work unit = 64 keys: S[b] (64 fp32 columns, double-buffered) -> P[b] (32 packed columns, double-buffered) -> O.
-// The last unit of a sequence only takes as many 16-key steps as it has valid keys (S = 708: N = 16).
+// Measured (S = 708, 4096 heads): 0.92 ms against 0.95 ms for the mma.sync kernel.  Timing experiments on the 64-key-unit
+// predecessor: without the exponentials it still took 0.72 ms — ~7.5 warp-instructions per score element (barrier
+// handling and loop control amortised over 32 elements per thread and unit) made it issue-bound before it is MUFU-bound
+// (MUFU floor 0.54 ms); hence 128-key units, read from TMEM twice (maximum, then exponentials) in 32-column chunks.
+// Work unit = 128 keys: S (128 fp32 columns) -> P (64 packed columns) -> O, L; S and P single-buffered (the softmax work
+// on a unit covers the next S product and the retirement of the previous P V).  The last unit of a sequence only takes
+// as many 16-key steps as it has valid keys (S = 708: N = 80).
 // =====================================================================================================
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
