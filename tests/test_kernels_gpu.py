@@ -215,7 +215,10 @@ def test_layernorm_rowmap_and_pool_grad():
 
 # ------------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("n_seq,S,H,hd", [(3, 49, 12, 64), (2, 128, 12, 64), (2, 177, 12, 64), (2, 708, 16, 32),
-                                          (1, 64, 2, 32), (2, 1, 2, 64)])
+                                          (1, 64, 2, 32), (2, 1, 2, 64),
+                                          # tcgen05 forward range (head_dim 32, 256 <= S <= 768): unit / block edges
+                                          (1, 256, 4, 32), (3, 257, 2, 32), (2, 300, 2, 32), (1, 511, 2, 32),
+                                          (1, 640, 2, 32), (2, 768, 2, 32)])
 def test_attention_fwd_bwd(n_seq, S, H, hd):
     D = H * hd
     qkv = rnd(n_seq * S, 3 * D, dtype=torch.bfloat16)
