@@ -24,8 +24,6 @@
 
 namespace {
 
-constexpr int ATT_WARPS = 8;
-constexpr int ATT_THREADS = ATT_WARPS * 32;
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -59,11 +57,11 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
 
 // Whole-head load: rows [0,S) of a [*, ld] bf16 matrix (HD columns starting at src) -> swizzled smem tile; rows
 // [S, S_pad) are zero-filled.  Asynchronous (cp.async); caller waits + __syncthreads.
-template <int HD>
+template <int HD, int NTHREADS>
 __device__ __forceinline__ void load_head_async(uint32_t tile, const bf16* __restrict__ src, long long ld, int S,
                                                 int S_pad) {
   constexpr int CPR = HD / 8;
-  for (int i = threadIdx.x; i < S_pad * CPR; i += ATT_THREADS) {
+  for (int i = threadIdx.x; i < S_pad * CPR; i += NTHREADS) {
     const int r = i / CPR, c = i % CPR;
     const uint32_t dst = tile + tile_off<HD>(r, c);
     if (r < S) cp_async16(dst, src + (long long)r * ld + c * 8);
@@ -149,8 +147,9 @@ struct AttnArgs {
 };
 
 // ------------------------------------------------ forward ------------------------------------------------
-template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const AttnArgs a) {
+// WARPS = 8 normally; 4 for sequences of at most 64 tokens (4 x 16-row tiles), so that no warp of a resident CTA idles
+template <int HD, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 256 / (WARPS * 32) * 2) attn_fwd_kernel(const AttnArgs a) {
   constexpr int NT = 8;  // 64 keys per inner block
   extern __shared__ __align__(128) uint8_t att_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -159,15 +158,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const AttnArgs
   const long long row_base = (long long)seq * S;
   const bf16* qb = a.qkv + row_base * a.ld_qkv + h * HD;
   const uint32_t sK = smem_u32(att_smem), sV = sK + S_pad * HD * 2;
-  load_head_async<HD>(sK, qb + a.D, a.ld_qkv, S, S_pad);
-  load_head_async<HD>(sV, qb + 2 * a.D, a.ld_qkv, S, S_pad);
+  load_head_async<HD, WARPS * 32>(sK, qb + a.D, a.ld_qkv, S, S_pad);
+  load_head_async<HD, WARPS * 32>(sV, qb + 2 * a.D, a.ld_qkv, S, S_pad);
   cp_async_wait_all();
   __syncthreads();
 
   bf16* ob = a.out + row_base * a.ld_o + h * HD;
   float* lp = a.lse2 + ((long long)seq * a.H + h) * S;
   const int n_qt = (S + 15) >> 4;
-  for (int qt = warp; qt < n_qt; qt += ATT_WARPS) {
+  for (int qt = warp; qt < n_qt; qt += WARPS) {
     uint32_t qf[HD / 16][4];
     load_a_frags_global<HD>(qf, qb, a.ld_qkv, qt * 16, S, lane);
     float o[HD / 8][4];
@@ -289,8 +288,9 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
 
 // ------------------------------------------------ backward: dQ ------------------------------------------------
 // warp owns 16 queries; K and V of the head resident in smem; dQ = sum_blocks dS * K
-template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_dq_kernel(const AttnArgs a) {
+// WARPS = 8 normally; 4 for sequences of at most 64 tokens (4 x 16-row tiles), so that no warp of a resident CTA idles
+template <int HD, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 256 / (WARPS * 32) * 2) attn_bwd_dq_kernel(const AttnArgs a) {
   constexpr int NT = (HD == 64) ? 4 : 8;  // keys per inner block / 8 (register budget: 128/thread)
   extern __shared__ __align__(128) uint8_t att_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -300,15 +300,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_dq_kernel(const AttnA
   const bf16* qb = a.qkv + row_base * a.ld_qkv + h * HD;
   const bf16* dob = a.dout + row_base * a.ld_o + h * HD;
   const uint32_t sK = smem_u32(att_smem), sV = sK + S_pad * HD * 2;
-  load_head_async<HD>(sK, qb + a.D, a.ld_qkv, S, S_pad);
-  load_head_async<HD>(sV, qb + 2 * a.D, a.ld_qkv, S, S_pad);
+  load_head_async<HD, WARPS * 32>(sK, qb + a.D, a.ld_qkv, S, S_pad);
+  load_head_async<HD, WARPS * 32>(sV, qb + 2 * a.D, a.ld_qkv, S, S_pad);
   cp_async_wait_all();
   __syncthreads();
 
   const long long sb = ((long long)seq * a.H + h) * S;
   bf16* dqb = a.dqkv + row_base * a.ld_qkv + h * HD;
   const int n_qt = (S + 15) >> 4;
-  for (int qt = warp; qt < n_qt; qt += ATT_WARPS) {
+  for (int qt = warp; qt < n_qt; qt += WARPS) {
     uint32_t qf[HD / 16][4], dof[HD / 16][4];
     load_a_frags_global<HD>(qf, qb, a.ld_qkv, qt * 16, S, lane);
     load_a_frags_global<HD>(dof, dob, a.ld_o, qt * 16, S, lane);
@@ -351,8 +351,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_dq_kernel(const AttnA
 
 // ------------------------------------------------ backward: dK, dV ------------------------------------------------
 // warp owns 16 keys; Q and dO of the head (+ lse, delta) resident in smem
-template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_dkv_kernel(const AttnArgs a) {
+// WARPS = 8 normally; 4 for sequences of at most 64 tokens (4 x 16-row tiles), so that no warp of a resident CTA idles
+template <int HD, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 256 / (WARPS * 32) * 2) attn_bwd_dkv_kernel(const AttnArgs a) {
   constexpr int NT = (HD == 64) ? 4 : 8;  // queries per inner block / 8
   extern __shared__ __align__(128) uint8_t att_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -364,10 +365,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_dkv_kernel(const Attn
   const uint32_t sQ = smem_u32(att_smem), sDO = sQ + S_pad * HD * 2;
   float* s_lse = reinterpret_cast<float*>(att_smem + 2 * S_pad * HD * 2);
   float* s_delta = s_lse + S_pad;
-  load_head_async<HD>(sQ, qb, a.ld_qkv, S, S_pad);
-  load_head_async<HD>(sDO, dob, a.ld_o, S, S_pad);
+  load_head_async<HD, WARPS * 32>(sQ, qb, a.ld_qkv, S, S_pad);
+  load_head_async<HD, WARPS * 32>(sDO, dob, a.ld_o, S, S_pad);
   const long long sb = ((long long)seq * a.H + h) * S;
-  for (int i = threadIdx.x; i < S_pad; i += ATT_THREADS) {
+  for (int i = threadIdx.x; i < S_pad; i += WARPS * 32) {
     s_lse[i] = i < S ? a.lse2[sb + i] : INFINITY;  // padded queries: p = exp2(-inf) = 0
     s_delta[i] = i < S ? a.delta[sb + i] : 0.f;
   }
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_dkv_kernel(const Attn
   bf16* dkb = a.dqkv + row_base * a.ld_qkv + a.D + h * HD;
   bf16* dvb = a.dqkv + row_base * a.ld_qkv + 2 * a.D + h * HD;
   const int n_kt = (S + 15) >> 4;
-  for (int kt = warp; kt < n_kt; kt += ATT_WARPS) {
+  for (int kt = warp; kt < n_kt; kt += WARPS) {
     uint32_t kf[HD / 16][4], vf[HD / 16][4];
     load_a_frags_global<HD>(kf, qb + a.D, a.ld_qkv, kt * 16, S, lane);
     load_a_frags_global<HD>(vf, qb + 2 * a.D, a.ld_qkv, kt * 16, S, lane);
@@ -476,13 +477,18 @@ extern "C" int avs_attention_fwd(const void* qkv, long long ld_qkv, void* out, l
   const int smem = 2 * a.S_pad * head_dim * 2;
   dim3 grid(H, n_seq);
   int rc;
+  const bool small = S <= 64;                       // 4 query tiles: 4-warp CTAs, twice as many resident per SM
+#define AVS_LAUNCH_FWD(HD_, W_)                                                                      \
+  do {                                                                                               \
+    if ((rc = set_smem(attn_fwd_kernel<HD_, W_>, smem, "avs_attention_fwd"))) return rc;             \
+    attn_fwd_kernel<HD_, W_><<<grid, W_ * 32, smem, (cudaStream_t)stream>>>(a);                      \
+  } while (0)
   if (head_dim == 64) {
-    if ((rc = set_smem(attn_fwd_kernel<64>, smem, "avs_attention_fwd"))) return rc;
-    attn_fwd_kernel<64><<<grid, ATT_THREADS, smem, (cudaStream_t)stream>>>(a);
+    if (small) AVS_LAUNCH_FWD(64, 4); else AVS_LAUNCH_FWD(64, 8);
   } else {
-    if ((rc = set_smem(attn_fwd_kernel<32>, smem, "avs_attention_fwd"))) return rc;
-    attn_fwd_kernel<32><<<grid, ATT_THREADS, smem, (cudaStream_t)stream>>>(a);
+    if (small) AVS_LAUNCH_FWD(32, 4); else AVS_LAUNCH_FWD(32, 8);
   }
+#undef AVS_LAUNCH_FWD
   return avs_check_launch("attn_fwd_kernel");
 }
 
@@ -514,19 +520,21 @@ extern "C" int avs_attention_bwd(const void* qkv, long long ld_qkv, const void* 
   const int smem_dq = 2 * a.S_pad * head_dim * 2;
   const int smem_dkv = smem_dq + 2 * a.S_pad * 4;
   dim3 grid(H, n_seq);
+  const bool small = S <= 64;                       // 4 tiles: 4-warp CTAs, twice as many resident per SM
+#define AVS_LAUNCH_BWD(HD_, W_)                                                                      \
+  do {                                                                                               \
+    if ((rc = set_smem(attn_bwd_dkv_kernel<HD_, W_>, smem_dkv, "avs_attention_bwd"))) return rc;     \
+    if ((rc = set_smem(attn_bwd_dq_kernel<HD_, W_>, smem_dq, "avs_attention_bwd"))) return rc;       \
+    attn_bwd_dkv_kernel<HD_, W_><<<grid, W_ * 32, smem_dkv, stream>>>(a);                            \
+    if ((rc = avs_check_launch("attn_bwd_dkv_kernel"))) return rc;                                   \
+    attn_bwd_dq_kernel<HD_, W_><<<grid, W_ * 32, smem_dq, stream>>>(a);                              \
+  } while (0)
   if (head_dim == 64) {
-    if ((rc = set_smem(attn_bwd_dkv_kernel<64>, smem_dkv, "avs_attention_bwd"))) return rc;
-    if ((rc = set_smem(attn_bwd_dq_kernel<64>, smem_dq, "avs_attention_bwd"))) return rc;
-    attn_bwd_dkv_kernel<64><<<grid, ATT_THREADS, smem_dkv, stream>>>(a);
-    if ((rc = avs_check_launch("attn_bwd_dkv_kernel"))) return rc;
-    attn_bwd_dq_kernel<64><<<grid, ATT_THREADS, smem_dq, stream>>>(a);
+    if (small) AVS_LAUNCH_BWD(64, 4); else AVS_LAUNCH_BWD(64, 8);
   } else {
-    if ((rc = set_smem(attn_bwd_dkv_kernel<32>, smem_dkv, "avs_attention_bwd"))) return rc;
-    if ((rc = set_smem(attn_bwd_dq_kernel<32>, smem_dq, "avs_attention_bwd"))) return rc;
-    attn_bwd_dkv_kernel<32><<<grid, ATT_THREADS, smem_dkv, stream>>>(a);
-    if ((rc = avs_check_launch("attn_bwd_dkv_kernel"))) return rc;
-    attn_bwd_dq_kernel<32><<<grid, ATT_THREADS, smem_dq, stream>>>(a);
+    if (small) AVS_LAUNCH_BWD(32, 4); else AVS_LAUNCH_BWD(32, 8);
   }
+#undef AVS_LAUNCH_BWD
   if ((rc = avs_check_launch("attn_bwd_dq_kernel"))) return rc;
   // qkv-bias gradient: the tcgen05 kernel accumulates it in its epilogues; this path takes one more pass over dQKV
   if (dbias != nullptr) return avs_colsum_bf16(dqkv, ld_qkv, dbias, n_seq * S, 3 * a.D, 1.0f, stream_);
