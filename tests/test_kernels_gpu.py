@@ -339,3 +339,33 @@ def test_colsum_and_cast():
     ops.scatter_add_rows(d2, idx, table, 2.0)
     ref = torch.zeros(16, 64, device=DEV).index_add_(0, idx.long(), 2.0 * d2.float())
     assert torch.allclose(table, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_attention_fwd_persistent_pingpong_variant():
+    """The experimental persistent forward (attn_fwd_pp_kernel: one CTA per SM, two softmax groups passing a MUFU token,
+    TMA-fed K/V double-buffered across heads) is selected by an environment variable read once per process, so it is
+    checked in a child process against torch's SDPA on the decoder shape."""
+    import subprocess
+    import sys
+    code = r'''
+import torch, torch.nn.functional as F
+from avsiam_b200 import ops
+torch.manual_seed(0)
+n_seq, S, H, hd = 3, 708, 16, 32
+D = H * hd
+qkv = (torch.randn(n_seq * S, 3 * D, device="cuda") * 0.7).to(torch.bfloat16)
+out = torch.empty(n_seq * S, D, dtype=torch.bfloat16, device="cuda")
+lse = torch.empty(n_seq, H, S, dtype=torch.float32, device="cuda")
+ops.attention_fwd(qkv, out, lse, n_seq, S, H, hd)
+q, k, v = (qkv.float().view(n_seq, S, 3, H, hd).permute(2, 0, 3, 1, 4))
+ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(n_seq * S, D)
+err = float((out.float() - ref).norm() / ref.norm())
+assert err < 1e-2, err
+ref_lse = torch.logsumexp((q @ k.transpose(-1, -2)) * hd ** -0.5, dim=-1) * 1.4426950408889634   # log2 domain
+assert float((lse - ref_lse).abs().max()) < 2e-2
+print("ok", err)
+'''
+    env = dict(os.environ, AVS_ATTN_FWD_VARIANT="2")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
