@@ -251,6 +251,39 @@ def test_attention_fwd_bwd(n_seq, S, H, hd):
         assert e < 2e-2, (name, e)   # bf16 P / dS operands in the tensor-core products
 
 
+@pytest.mark.parametrize("S", [708, 400])
+def test_attention_fwd_rising_scores_rescale_path(S):
+    """Scores that keep growing along the key axis (by far more than the 2^8 slack of the lazy running maximum) force
+    the tcgen05 forward to raise its maximum and rescale O and the row sums in tensor memory in EVERY unit; sharp and
+    flat rows are mixed so that lanes with and without a raise share a warp."""
+    n_seq, H, hd = 2, 4, 32
+    D = H * hd
+    g = torch.Generator(device="cpu").manual_seed(11)
+    q = torch.randn(n_seq, S, H, hd, generator=g)
+    k = torch.randn(n_seq, S, H, hd, generator=g)
+    v = torch.randn(n_seq, S, H, hd, generator=g)
+    ramp = torch.linspace(0.2, 6.0, S).view(1, S, 1, 1)             # later keys are longer ...
+    k = k * ramp
+    q[:, ::3] = q[:, ::3] * 4.0                                       # ... and every third query row is sharp
+    k[:, :, :, 0] += ramp[..., 0] * 3.0                               # a shared direction makes the growth systematic
+    q[:, :, :, 0] = q[:, :, :, 0].abs() + 1.0
+    qkv = torch.stack([q, k, v], 2).reshape(n_seq * S, 3 * D).to(torch.bfloat16).to(DEV)
+    out = torch.empty(n_seq * S, D, dtype=torch.bfloat16, device=DEV)
+    lse2 = torch.empty(n_seq, H, S, device=DEV)
+    ops.attention_fwd(qkv, out, lse2, n_seq, S, H, hd)
+    q5 = qkv.float().reshape(n_seq, S, 3, H, hd).permute(2, 0, 3, 1, 4)
+    att = (q5[0] @ q5[1].transpose(-2, -1)) * hd ** -0.5
+    # the premise of the test: the running row maximum is raised by more than 8 (log2) after the first 128-key unit
+    first = att[..., :128].max(-1).values
+    assert float(((att.max(-1).values - first) / math.log(2) > 8).float().mean()) > 0.5
+    ref = (att.softmax(-1) @ q5[2]).transpose(1, 2).reshape(n_seq * S, D)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < 8e-3
+    ref_lse2 = torch.logsumexp(att, -1) / math.log(2)
+    err = (lse2 - ref_lse2).abs()
+    assert float(err.max()) < 6e-3, (float(err.max()), float(err.mean()))   # row sums are taken over the bf16-rounded P
+
+
 # ------------------------------------------------------------------------------------------------ losses
 def test_mae_loss_fwd_bwd():
     d = O.VIT_B
