@@ -582,6 +582,9 @@ int launch_bwd(const TcArgs& a, int n_seq, cudaStream_t stream) {
 //     new block exceeds it by more than 2^8 (probabilities then stay below 256, exact in the final O / l); raising it
 //     rescales O in tensor memory (tcgen05.ld / st by the owning thread).  That happens in the first one or two units
 //     of a query block and almost never afterwards, so there is no correction warp and no second pass.
+//   * when the Cauchy-Schwarz bound |q_i| max_j |k_j| of a query block's scores is small (<= 60 in the log2 domain) it
+//     replaces the maximum altogether: exp2(score - bound) cannot underflow, so the maximum pass, the exchange between
+//     the two warps of a row and the rescaling all disappear (the common case; the lazy maximum is the general one).
 //   * P goes back to TENSOR MEMORY as packed bf16 and is the A operand of the P V product (tcgen05.mma with A in TMEM),
 //     so the probabilities never touch shared memory.
 //   * row sums on the tensor pipe too: L += P x ones (a 16-column product per k-step), so the softmax warps spend no
@@ -592,7 +595,7 @@ int launch_bwd(const TcArgs& a, int n_seq, cudaStream_t stream) {
 //     256 TMEM columns: TWO CTAs PER SM (the occupancy API reports 1 for any kernel with tcgen05.alloc; the hardware
 //     co-schedules two 256-column CTAs — tools/tmem_occ_probe.cu), i.e. 4 softmax warps per SM sub-partition: one warp
 //     alone reaches only 55-70 % of the EX2 rate with this instruction mix, two or more 86-97 % (tools/mufu_probe.cu).
-// Measured (S = 708, 4096 heads): 0.92 ms against 0.95 ms for the mma.sync kernel.  Timing experiments on the 64-key-unit
+// Measured (S = 708, 4096 heads): 0.89 ms against 0.95 ms for the mma.sync kernel.  Timing experiments on the 64-key-unit
 // predecessor: without the exponentials it still took 0.72 ms — ~7.5 warp-instructions per score element (barrier
 // handling and loop control amortised over 32 elements per thread and unit) made it issue-bound before it is MUFU-bound
 // (MUFU floor 0.54 ms); hence 128-key units, read from TMEM twice (maximum, then exponentials) in 32-column chunks.
@@ -612,6 +615,7 @@ constexpr int TCF_FIRST_SOFTMAX_WARP = 2;
 constexpr int TCF_THREADS = 32 * (TCF_FIRST_SOFTMAX_WARP + TCF_SOFTMAX_WARPS);
 constexpr int TCF_COL_S = 0, TCF_COL_P = 128, TCF_COL_O = 192, TCF_COL_L = 224, TCF_TMEM_COLS = 256;   // S 128 | P 64 | O 32 | L 16
 constexpr float TCF_LAZY = 8.0f;   // log2 of the largest probability tolerated before the running maximum is raised
+constexpr float TCF_BOUND_MAX = 60.0f;   // largest score bound (log2 domain) for the no-maximum fast path: 2^-120 is normal
 
 struct TcFwdArgs {
   const bf16* qkv;
@@ -646,6 +650,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
   uint64_t* o_full = bars + 8;      // issuer (commit) -> softmax: O of a query block complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   float* s_mx = reinterpret_cast<float*>(bars + 16);   // [2][2][128] partial row maxima (unit parity, column half, row)
+  uint32_t* s_k2max = reinterpret_cast<uint32_t*>(bars + 10);   // bits of max_j |k_j|^2 (non-negative floats order as integers)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, seq = blockIdx.y;
@@ -668,12 +673,36 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
     tmem_alloc(tmem_slot, TCF_TMEM_COLS);
     tmem_relinquish();
   }
+  if (threadIdx.x == 0) *s_k2max = 0u;
+  __syncthreads();   // (orders the initialisation before every warp's atomicMax below)
   // K, V of the whole head and the first Q block: one cooperative load, one exposed HBM round trip
   load_rows_async<HD>(sK, qb + a.D, a.ld_qkv, 0, kv_rows, S, threadIdx.x, TCF_THREADS);
   load_rows_async<HD>(sV, qb + 2 * a.D, a.ld_qkv, 0, kv_rows, S, threadIdx.x, TCF_THREADS);
   load_rows_async<HD>(sQ, qb, a.ld_qkv, 0, 128, S, threadIdx.x, TCF_THREADS);
   for (int i = threadIdx.x; i < 2048 / 16; i += TCF_THREADS)
     st_shared_v4(sOnes + i * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  // Cauchy-Schwarz bound of every score of the head: |q_i . k_j| <= |q_i| max_j |k_j|.  When the bound is small enough
+  // that exp2(score - bound) cannot underflow (see the softmax warps), it replaces the running row maximum and the
+  // whole maximum pass.  The K rows read here are the ones the cp.async above has just requested (L2 hits).
+  {
+    float k2 = 0.f;
+    for (int r = threadIdx.x; r < S; r += TCF_THREADS) {
+      const uint4* kr = reinterpret_cast<const uint4*>(qb + a.D + (long long)r * a.ld_qkv);
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < HD / 8; ++c) {
+        const uint4 v = __ldg(kr + c);
+        float2 f;
+        f = unpack_bf16x2(v.x); acc = fmaf(f.x, f.x, fmaf(f.y, f.y, acc));
+        f = unpack_bf16x2(v.y); acc = fmaf(f.x, f.x, fmaf(f.y, f.y, acc));
+        f = unpack_bf16x2(v.z); acc = fmaf(f.x, f.x, fmaf(f.y, f.y, acc));
+        f = unpack_bf16x2(v.w); acc = fmaf(f.x, f.x, fmaf(f.y, f.y, acc));
+      }
+      k2 = fmaxf(k2, acc);
+    }
+    k2 = warp_max(k2);
+    if (lane == 0) atomicMax(s_k2max, __float_as_uint(k2));
+  }
   cp_async_wait_all();
   fence_proxy_async();
   tc_fence_before();
@@ -766,12 +795,43 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
     float* lp = a.lse2 + ((long long)seq * a.H + h) * S;
     const int valid_last = S - (NU - 1) * 128 - half * 64;   // valid keys among this warp's 64 columns of the last unit
     float m_run = -INFINITY;
+    const float k2max = __uint_as_float(*s_k2max);
+    // Fast path of a query block: every row of this lane quarter has a score bound B = |q| max|k| * scale (log2 domain)
+    // of at most TCF_BOUND_MAX.  All scores then lie in [-B, B], so exp2(score - B) >= 2^(-2 B) stays a normal fp32 /
+    // bf16 number and B can stand in for the row maximum: no maximum pass, no exchange, no rescaling.  The decision
+    // depends only on the rows of the lane quarter, so the two warps that share them always agree.
+    auto block_bound = [&](int blk) {
+      const int qr = blk * 128 + row;
+      float q2 = 0.f;
+      if (qr < S) {
+        const uint4* qrow = reinterpret_cast<const uint4*>(qb + (long long)qr * a.ld_qkv);
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) {
+          const uint4 v = __ldg(qrow + c);
+          float2 f;
+          f = unpack_bf16x2(v.x); q2 = fmaf(f.x, f.x, fmaf(f.y, f.y, q2));
+          f = unpack_bf16x2(v.y); q2 = fmaf(f.x, f.x, fmaf(f.y, f.y, q2));
+          f = unpack_bf16x2(v.z); q2 = fmaf(f.x, f.x, fmaf(f.y, f.y, q2));
+          f = unpack_bf16x2(v.w); q2 = fmaf(f.x, f.x, fmaf(f.y, f.y, q2));
+        }
+      }
+      return sqrtf(q2 * k2max) * a.scale_log2 * 1.0001f + 1e-3f;     // margin for the fp32 rounding of the products
+    };
+    float bound = block_bound(0);
+    bool fast = __all_sync(0xffffffffu, bound <= TCF_BOUND_MAX);
+    if (fast) m_run = bound;
     int jj = 0, i = 0;
     for (int u = 0; u < U; ++u) {
       const uint32_t par = (uint32_t)(u & 1);
       const bool last = (jj == NU - 1);
       mbar_wait(s_full, par);
       tc_fence_after();
+      if (fast) {
+        if (u >= 1) {   // P(u-1) V must have retired before P is overwritten
+          mbar_wait(p_empty, (uint32_t)((u - 1) & 1));
+          tc_fence_after();
+        }
+      } else {
       // ---- pass A: row maximum of this warp's 64 columns
       float mx = -INFINITY;
 #pragma unroll
@@ -823,6 +883,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
         }
         m_run = m_upd;
       }
+      }   // !fast
       // ---- pass B: P = exp2(S * scale - max) -> bf16 pairs -> TMEM
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
@@ -882,8 +943,13 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
         }
         // the first P V of the next query block (accumulate = 0 into O / L) is issued only after all 8 warps have
         // produced its P, i.e. after the tcgen05.ld above has completed in each of them: no extra barrier needed
-        m_run = -INFINITY;
         jj = 0; ++i;
+        m_run = -INFINITY;
+        if (i < NB) {
+          bound = block_bound(i);
+          fast = __all_sync(0xffffffffu, bound <= TCF_BOUND_MAX);
+          if (fast) m_run = bound;
+        }
       } else {
         ++jj;
       }
