@@ -826,12 +826,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
       const bool last = (jj == NU - 1);
       mbar_wait(s_full, par);
       tc_fence_after();
-      if (fast) {
-        if (u >= 1) {   // P(u-1) V must have retired before P is overwritten
-          mbar_wait(p_empty, (uint32_t)((u - 1) & 1));
-          tc_fence_after();
-        }
-      } else {
+      if (!fast) {
       // ---- pass A: row maximum of this warp's 64 columns
       float mx = -INFINITY;
 #pragma unroll
@@ -884,10 +879,12 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
         m_run = m_upd;
       }
       }   // !fast
-      // ---- pass B: P = exp2(S * scale - max) -> bf16 pairs -> TMEM
+      // ---- pass B: P = exp2(S * scale - max) -> bf16 pairs -> TMEM.  P is single-buffered: on the fast path the wait
+      // for P(u-1) V to retire comes only after this unit's exponentials, which hide the product's latency.
+      uint32_t pw[2][16];
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
-        uint32_t sr[32], pw[16];
+        uint32_t sr[32];
         tmem_ld_32x32b_x32(tS + ch * 32, sr);
         tmem_ld_wait();
         if (ch == 1) {                                  // last read of S(u): the issuer may overwrite the buffer
@@ -898,8 +895,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
         if (!last) {
 #pragma unroll
           for (int c = 0; c < 32; c += 2)
-            pw[c >> 1] = pack_bf16x2(exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run)),
-                                     exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -m_run)));
+            pw[ch][c >> 1] = pack_bf16x2(exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run)),
+                                         exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -m_run)));
         } else {
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
@@ -907,11 +904,16 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
             float p1 = exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -m_run));
             if (ch * 32 + c >= valid_last) p0 = 0.f;
             if (ch * 32 + c + 1 >= valid_last) p1 = 0.f;
-            pw[c >> 1] = pack_bf16x2(p0, p1);
+            pw[ch][c >> 1] = pack_bf16x2(p0, p1);
           }
         }
-        tmem_st_32x32b_x16(tP + ch * 16, pw);
       }
+      if (fast && u >= 1) {   // P(u-1) V must have retired before P is overwritten
+        mbar_wait(p_empty, (uint32_t)((u - 1) & 1));
+        tc_fence_after();
+      }
+      tmem_st_32x32b_x16(tP, pw[0]);
+      tmem_st_32x32b_x16(tP + 16, pw[1]);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
