@@ -595,7 +595,7 @@ int launch_bwd(const TcArgs& a, int n_seq, cudaStream_t stream) {
 //     256 TMEM columns: TWO CTAs PER SM (the occupancy API reports 1 for any kernel with tcgen05.alloc; the hardware
 //     co-schedules two 256-column CTAs — tools/tmem_occ_probe.cu), i.e. 4 softmax warps per SM sub-partition: one warp
 //     alone reaches only 55-70 % of the EX2 rate with this instruction mix, two or more 86-97 % (tools/mufu_probe.cu).
-// Measured (S = 708, 4096 heads): 0.89 ms against 0.95 ms for the mma.sync kernel.  Timing experiments on the 64-key-unit
+// Measured (S = 708, 4096 heads): 0.835 ms against 0.95 ms for the mma.sync kernel (0.882 ms with every exponential on MUFU).  Timing experiments on the 64-key-unit
 // predecessor: without the exponentials it still took 0.72 ms — ~7.5 warp-instructions per score element (barrier
 // handling and loop control amortised over 32 elements per thread and unit) made it issue-bound before it is MUFU-bound
 // (MUFU floor 0.54 ms); hence 128-key units, read from TMEM twice (maximum, then exponentials) in 32-column chunks.
@@ -614,7 +614,23 @@ constexpr int TCF_SOFTMAX_WARPS = 8;
 constexpr int TCF_FIRST_SOFTMAX_WARP = 2;
 constexpr int TCF_THREADS = 32 * (TCF_FIRST_SOFTMAX_WARP + TCF_SOFTMAX_WARPS);
 constexpr int TCF_COL_S = 0, TCF_COL_P = 128, TCF_COL_O = 192, TCF_COL_L = 224, TCF_TMEM_COLS = 256;   // S 128 | P 64 | O 32 | L 16
+// 2^x on the FMA / ALU pipes for -126 < x <= 0 (Cody-Waite split + degree-3 polynomial, relative error 7.7e-5 — well
+// below the bf16 rounding of P): x = xi + xf with xi = round(x) taken from the low mantissa bits of x + 1.5 * 2^23,
+// 2^xf from the polynomial, and xi added straight into the exponent field.  8 instructions instead of one MUFU.EX2:
+// used for a fraction of the elements, because MUFU issues only 16 lanes per clock per SM.
+__device__ __forceinline__ float exp2_poly(float x) {
+  const float t = x + 12582912.0f;
+  const float xf = x - (t - 12582912.0f);
+  float p = 0.05508868396282196f;
+  p = fmaf(p, xf, 0.24260404706001282f);
+  p = fmaf(p, xf, 0.6932762265205383f);
+  p = fmaf(p, xf, 0.9999289512634277f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 constexpr float TCF_LAZY = 8.0f;   // log2 of the largest probability tolerated before the running maximum is raised
+#ifndef TCF_POLY_EVERY
+#define TCF_POLY_EVERY 4   // every 4th pair of exponentials on the FMA pipe (0 = all on MUFU)
+#endif
 constexpr float TCF_BOUND_MAX = 60.0f;   // largest score bound (log2 domain) for the no-maximum fast path: 2^-120 is normal
 
 struct TcFwdArgs {
@@ -892,7 +908,16 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
           __syncwarp();
           if (lane == 0) mbar_arrive(s_read);
         }
-        if (!last) {
+        if (!last && fast && TCF_POLY_EVERY > 0) {
+          // fast path: exponents lie in [-120, 0], so every TCF_POLY_EVERY-th pair can take the polynomial
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const float x0 = fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run);
+            const float x1 = fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -m_run);
+            if (((c >> 1) % TCF_POLY_EVERY) == TCF_POLY_EVERY - 1) pw[ch][c >> 1] = pack_bf16x2(exp2_poly(x0), exp2_poly(x1));
+            else pw[ch][c >> 1] = pack_bf16x2(exp2f(x0), exp2f(x1));
+          }
+        } else if (!last) {
 #pragma unroll
           for (int c = 0; c < 32; c += 2)
             pw[ch][c >> 1] = pack_bf16x2(exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run)),
