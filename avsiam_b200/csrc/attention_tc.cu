@@ -123,6 +123,20 @@ __device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) {
   return d;
 }
 
+// 2^x on the FMA / ALU pipes for -126 < x <= 0 (Cody-Waite split + degree-3 polynomial, relative error 7.7e-5 — well
+// below the bf16 rounding of P): x = xi + xf with xi = round(x) taken from the low mantissa bits of x + 1.5 * 2^23,
+// 2^xf from the polynomial, and xi added straight into the exponent field.  8 instructions instead of one MUFU.EX2:
+// used for a fraction of the elements, because MUFU issues only 16 lanes per clock per SM.
+__device__ __forceinline__ float exp2_poly(float x) {
+  const float t = x + 12582912.0f;
+  const float xf = x - (t - 12582912.0f);
+  float p = 0.05508868396282196f;
+  p = fmaf(p, xf, 0.24260404706001282f);
+  p = fmaf(p, xf, 0.6932762265205383f);
+  p = fmaf(p, xf, 0.9999289512634277f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+constexpr float TCF_LAZY = 8.0f;   // log2 of the largest probability tolerated before the running maximum is raised
 template <int HD>
 struct TcCfg {
   static constexpr int ROWB = HD * 2;                    // bytes per row of a Q/K/V/dO tile
@@ -470,6 +484,8 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
           float4 ls;
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
                        : "=f"(ls.x), "=f"(ls.y), "=f"(ls.z), "=f"(ls.w) : "r"(s_lse_u + qoff + c * 4));
+          // (moving a quarter of these exponentials to the FMA-pipe polynomial of the forward kernel was measured:
+          //  1.585 -> 1.655 ms — the backward's softmax warps are bound by instruction issue, not by the MUFU pipe)
           float p0 = exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -ls.x));
           float p1 = exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -ls.y));
           float p2 = exp2f(fmaf(__uint_as_float(sr[c + 2]), a.scale_log2, -ls.z));
@@ -614,20 +630,6 @@ constexpr int TCF_SOFTMAX_WARPS = 8;
 constexpr int TCF_FIRST_SOFTMAX_WARP = 2;
 constexpr int TCF_THREADS = 32 * (TCF_FIRST_SOFTMAX_WARP + TCF_SOFTMAX_WARPS);
 constexpr int TCF_COL_S = 0, TCF_COL_P = 128, TCF_COL_O = 192, TCF_COL_L = 224, TCF_TMEM_COLS = 256;   // S 128 | P 64 | O 32 | L 16
-// 2^x on the FMA / ALU pipes for -126 < x <= 0 (Cody-Waite split + degree-3 polynomial, relative error 7.7e-5 — well
-// below the bf16 rounding of P): x = xi + xf with xi = round(x) taken from the low mantissa bits of x + 1.5 * 2^23,
-// 2^xf from the polynomial, and xi added straight into the exponent field.  8 instructions instead of one MUFU.EX2:
-// used for a fraction of the elements, because MUFU issues only 16 lanes per clock per SM.
-__device__ __forceinline__ float exp2_poly(float x) {
-  const float t = x + 12582912.0f;
-  const float xf = x - (t - 12582912.0f);
-  float p = 0.05508868396282196f;
-  p = fmaf(p, xf, 0.24260404706001282f);
-  p = fmaf(p, xf, 0.6932762265205383f);
-  p = fmaf(p, xf, 0.9999289512634277f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-constexpr float TCF_LAZY = 8.0f;   // log2 of the largest probability tolerated before the running maximum is raised
 #ifndef TCF_POLY_EVERY
 #define TCF_POLY_EVERY 4   // every 4th pair of exponentials on the FMA pipe (0 = all on MUFU)
 #endif
