@@ -910,7 +910,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
           __syncwarp();
           if (lane == 0) mbar_arrive(s_read);
         }
-        if (!last && fast && TCF_POLY_EVERY > 0) {
+        const bool whole = !last || ch * 32 + 32 <= valid_last;   // every column of this chunk is a valid key
+        if (whole && fast && TCF_POLY_EVERY > 0) {
           // fast path: exponents lie in [-120, 0], so every TCF_POLY_EVERY-th pair can take the polynomial
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
@@ -919,19 +920,29 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
             if (((c >> 1) % TCF_POLY_EVERY) == TCF_POLY_EVERY - 1) pw[ch][c >> 1] = pack_bf16x2(exp2_poly(x0), exp2_poly(x1));
             else pw[ch][c >> 1] = pack_bf16x2(exp2f(x0), exp2f(x1));
           }
-        } else if (!last) {
+        } else if (whole) {
 #pragma unroll
           for (int c = 0; c < 32; c += 2)
             pw[ch][c >> 1] = pack_bf16x2(exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run)),
                                          exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -m_run)));
         } else {
+          // last unit of the sequence: 16-column groups without a valid key cost no exponentials (S = 708: the second
+          // warp of a row has 4 valid keys among its 64 columns)
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            float p0 = exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run));
-            float p1 = exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -m_run));
-            if (ch * 32 + c >= valid_last) p0 = 0.f;
-            if (ch * 32 + c + 1 >= valid_last) p1 = 0.f;
-            pw[ch][c >> 1] = pack_bf16x2(p0, p1);
+          for (int g16 = 0; g16 < 2; ++g16) {
+            if (ch * 32 + g16 * 16 < valid_last) {
+#pragma unroll
+              for (int c = g16 * 16; c < g16 * 16 + 16; c += 2) {
+                float p0 = exp2f(fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run));
+                float p1 = exp2f(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -m_run));
+                if (ch * 32 + c >= valid_last) p0 = 0.f;
+                if (ch * 32 + c + 1 >= valid_last) p1 = 0.f;
+                pw[ch][c >> 1] = pack_bf16x2(p0, p1);
+              }
+            } else {
+#pragma unroll
+              for (int c = g16 * 8; c < g16 * 8 + 8; ++c) pw[ch][c] = 0u;
+            }
           }
         }
       }
