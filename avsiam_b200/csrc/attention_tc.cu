@@ -611,7 +611,7 @@ int launch_bwd(const TcArgs& a, int n_seq, cudaStream_t stream) {
 //     256 TMEM columns: TWO CTAs PER SM (the occupancy API reports 1 for any kernel with tcgen05.alloc; the hardware
 //     co-schedules two 256-column CTAs — tools/tmem_occ_probe.cu), i.e. 4 softmax warps per SM sub-partition: one warp
 //     alone reaches only 55-70 % of the EX2 rate with this instruction mix, two or more 86-97 % (tools/mufu_probe.cu).
-// Measured (S = 708, 4096 heads): 0.835 ms against 0.95 ms for the mma.sync kernel (0.882 ms with every exponential on MUFU).  Timing experiments on the 64-key-unit
+// Measured (S = 708, 4096 heads): 0.775 ms against 0.95 ms for the mma.sync kernel (0.82 ms with every exponential on MUFU).  Timing experiments on the 64-key-unit
 // predecessor: without the exponentials it still took 0.72 ms — ~7.5 warp-instructions per score element (barrier
 // handling and loop control amortised over 32 elements per thread and unit) made it issue-bound before it is MUFU-bound
 // (MUFU floor 0.54 ms); hence 128-key units, read from TMEM twice (maximum, then exponentials) in 32-column chunks.
