@@ -199,43 +199,49 @@ extern "C" int avs_patchify_video(const float* img, const int32_t* ids, const in
 //   out[b, Ta + j] = (irv[b,j] < kv ? x[b, ka + irv[b,j]] : mask_token) + pos_v[j] + mod_v      j in [0,Tv)
 // x: bf16 [B, ka+kv, D] (decoder_embed output), out: bf16 [B, Ta+Tv, D]; fp32 parameters.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void decoder_restore_fwd_kernel(const bf16* __restrict__ x, const int* __restrict__ ira,
-                                           const int* __restrict__ irv, const float* __restrict__ mask_token,
-                                           const float* __restrict__ pos_a, const float* __restrict__ pos_v,
-                                           const float* __restrict__ mod_a, const float* __restrict__ mod_v,
-                                           bf16* __restrict__ out, int Ta, int Tv, int ka, int kv, int D,
-                                           long long total8) {
-  const int per_row = D / 8;
+// one warp per output row: the row's source / position decode happens once per warp in 32-bit arithmetic (the first
+// version spent its time in 64-bit divisions per 16-byte chunk: 0.93 TB/s), lanes stride over the 16-byte chunks
+__global__ void __launch_bounds__(256) decoder_restore_fwd_kernel(
+    const bf16* __restrict__ x, const int* __restrict__ ira, const int* __restrict__ irv,
+    const float* __restrict__ mask_token, const float* __restrict__ pos_a, const float* __restrict__ pos_v,
+    const float* __restrict__ mod_a, const float* __restrict__ mod_v, bf16* __restrict__ out, int Ta, int Tv, int ka,
+    int kv, int D, int rows) {
   const int S = Ta + Tv, K = ka + kv;
-  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total8;
-       g += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(g % per_row) * 8;
-    const long long r = g / per_row;
-    const int b = (int)(r / S), j = (int)(r % S);
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const int b = r / S, j = r - b * S;
     const bool is_a = j < Ta;
     const int jj = is_a ? j : j - Ta;
     const int src = is_a ? ira[(size_t)b * Ta + jj] : irv[(size_t)b * Tv + jj];
-    const int keep = is_a ? ka : kv;
-    const float* pos = (is_a ? pos_a : pos_v) + (size_t)jj * D + c;
-    const float* mod = (is_a ? mod_a : mod_v) + c;
-    float v[8];
-    if (src < keep) {
-      const uint4 u = *reinterpret_cast<const uint4*>(x + ((size_t)b * K + (is_a ? 0 : ka) + src) * D + c);
-      float2 f;
-      f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
-      f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
-      f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
-      f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = mask_token[c + i];
+    const bool kept = src < (is_a ? ka : kv);
+    const bf16* xr = x + ((size_t)b * K + (is_a ? 0 : ka) + (kept ? src : 0)) * D;
+    const float* pos = (is_a ? pos_a : pos_v) + (size_t)jj * D;
+    const float* mod = is_a ? mod_a : mod_v;
+    bf16* orow = out + (size_t)r * D;
+    for (int c = lane * 8; c < D; c += 256) {
+      float v[8];
+      if (kept) {
+        const uint4 u = *reinterpret_cast<const uint4*>(xr + c);
+        float2 f;
+        f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+        f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+        f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+        f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+      } else {
+        const float4 m0 = *reinterpret_cast<const float4*>(mask_token + c);
+        const float4 m1 = *reinterpret_cast<const float4*>(mask_token + c + 4);
+        v[0] = m0.x; v[1] = m0.y; v[2] = m0.z; v[3] = m0.w; v[4] = m1.x; v[5] = m1.y; v[6] = m1.z; v[7] = m1.w;
+      }
+      const float4 p0 = *reinterpret_cast<const float4*>(pos + c), p1 = *reinterpret_cast<const float4*>(pos + c + 4);
+      const float4 d0 = *reinterpret_cast<const float4*>(mod + c), d1 = *reinterpret_cast<const float4*>(mod + c + 4);
+      // (v + (pos + mod)) in the order of the first version: results stay bit-identical
+      v[0] += p0.x + d0.x; v[1] += p0.y + d0.y; v[2] += p0.z + d0.z; v[3] += p0.w + d0.w;
+      v[4] += p1.x + d1.x; v[5] += p1.y + d1.y; v[6] += p1.z + d1.z; v[7] += p1.w + d1.w;
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(orow + c) = o;
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += pos[i] + mod[i];
-    uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(out + (size_t)r * D + c) = o;
   }
 }
 
@@ -246,25 +252,32 @@ extern "C" int avs_decoder_restore_fwd(const void* x, const int32_t* ids_restore
   AVS_REQUIRE(x && ids_restore_a && ids_restore_v && mask_token && pos_a && pos_v && mod_a && mod_v && out,
               "avs_decoder_restore_fwd: null pointer");
   AVS_REQUIRE(D % 8 == 0, "avs_decoder_restore_fwd: D must be a multiple of 8");
-  const long long total8 = (long long)B * (Ta + Tv) * (D / 8);
-  if (total8 == 0) return 0;
-  const int blocks = (int)min((long long)avs_num_sms() * 8, ceil_div_ll(total8, 256));
+  AVS_REQUIRE((long long)B * (Ta + Tv) < (1ll << 31), "avs_decoder_restore_fwd: too many rows");
+  AVS_REQUIRE(((uintptr_t)mask_token & 15) == 0 && ((uintptr_t)pos_a & 15) == 0 && ((uintptr_t)pos_v & 15) == 0 &&
+                  ((uintptr_t)mod_a & 15) == 0 && ((uintptr_t)mod_v & 15) == 0,
+              "avs_decoder_restore_fwd: fp32 parameters must be 16-byte aligned");
+  const int rows = B * (Ta + Tv);
+  if (rows == 0) return 0;
+  const int blocks = min(avs_num_sms() * 8, ceil_div(rows, 8));
   decoder_restore_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)x, ids_restore_a, ids_restore_v, mask_token, pos_a, pos_v, mod_a, mod_v, (bf16*)out, Ta, Tv, keep_a,
-      keep_v, D, total8);
+      keep_v, D, rows);
   return avs_check_launch("decoder_restore_fwd_kernel");
 }
 
 // Backward of the restore. One CTA per position j (grid = Ta+Tv), looping over the batch:
 //   dx[b, src]   = dout[b, j]                     where src = ids_restore[b,j] < keep     (pure scatter, unique)
-//   dpos[j]     += sum_b dout[b,j]                (deterministic, no atomics)
+//   dpos[j]     += sum_b dout[b,j]                (fp32 atomics, one per batch slice)
 //   dmask_token += sum over masked (b,j)          (fp32 atomics, one per CTA per column)
 //   dmod_{a,v}  += sum over (b,j) of the modality (fp32 atomics)
-__global__ void decoder_restore_bwd_kernel(const bf16* __restrict__ dout, const int* __restrict__ ira,
-                                           const int* __restrict__ irv, bf16* __restrict__ dx,
-                                           float* __restrict__ dmask_token, float* __restrict__ dpos_a,
-                                           float* __restrict__ dpos_v, float* __restrict__ dmod_a,
-                                           float* __restrict__ dmod_v, int B, int Ta, int Tv, int ka, int kv, int D) {
+// grid (position j, batch slice): every thread owns 8 columns (16-byte loads / stores) and walks its slice of the batch
+// with 4 independent loads in flight; the per-position sums of the slices are combined with fp32 atomics (the first
+// version walked the whole batch serially with 4-byte accesses).
+constexpr int RB_SLICES = 4;
+__global__ void __launch_bounds__(64) decoder_restore_bwd_kernel(
+    const bf16* __restrict__ dout, const int* __restrict__ ira, const int* __restrict__ irv, bf16* __restrict__ dx,
+    float* __restrict__ dmask_token, float* __restrict__ dpos_a, float* __restrict__ dpos_v,
+    float* __restrict__ dmod_a, float* __restrict__ dmod_v, int B, int Ta, int Tv, int ka, int kv, int D) {
   const int j = blockIdx.x;
   const int S = Ta + Tv, K = ka + kv;
   const bool is_a = j < Ta;
@@ -272,24 +285,47 @@ __global__ void decoder_restore_bwd_kernel(const bf16* __restrict__ dout, const 
   const int keep = is_a ? ka : kv;
   const int* ir = is_a ? ira + jj : irv + jj;
   const int irs = is_a ? Ta : Tv;
-  for (int c = threadIdx.x * 2; c < D; c += blockDim.x * 2) {
-    float sp0 = 0.f, sp1 = 0.f, sm0 = 0.f, sm1 = 0.f;
-    for (int b = 0; b < B; ++b) {
-      const uint32_t u = *reinterpret_cast<const uint32_t*>(dout + ((size_t)b * S + j) * D + c);
-      const float2 f = unpack_bf16x2(u);
-      sp0 += f.x; sp1 += f.y;
-      const int src = ir[(size_t)b * irs];
-      if (src < keep) {
-        *reinterpret_cast<uint32_t*>(dx + ((size_t)b * K + (is_a ? 0 : ka) + src) * D + c) = u;
-      } else {
-        sm0 += f.x; sm1 += f.y;
+  const int per = (B + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * per, b1 = min(B, b0 + per);
+  for (int c = threadIdx.x * 8; c < D; c += blockDim.x * 8) {
+    float sp[8], sm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sp[i] = sm[i] = 0.f;
+    for (int b = b0; b < b1; b += 4) {
+      uint4 u[4];
+      int src[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool ok = b + k < b1;
+        u[k] = ok ? *reinterpret_cast<const uint4*>(dout + ((size_t)(b + k) * S + j) * D + c) : make_uint4(0, 0, 0, 0);
+        src[k] = ok ? ir[(size_t)(b + k) * irs] : keep;          // out-of-range rows count as "masked" zeros
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float v[8];
+        float2 f;
+        f = unpack_bf16x2(u[k].x); v[0] = f.x; v[1] = f.y;
+        f = unpack_bf16x2(u[k].y); v[2] = f.x; v[3] = f.y;
+        f = unpack_bf16x2(u[k].z); v[4] = f.x; v[5] = f.y;
+        f = unpack_bf16x2(u[k].w); v[6] = f.x; v[7] = f.y;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sp[i] += v[i];
+        if (src[k] < keep) {
+          *reinterpret_cast<uint4*>(dx + ((size_t)(b + k) * K + (is_a ? 0 : ka) + src[k]) * D + c) = u[k];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sm[i] += v[i];
+        }
       }
     }
     float* dpos = (is_a ? dpos_a : dpos_v) + (size_t)jj * D + c;
-    dpos[0] += sp0; dpos[1] += sp1;
     float* dmod = (is_a ? dmod_a : dmod_v) + c;
-    atomicAdd(dmod, sp0); atomicAdd(dmod + 1, sp1);
-    atomicAdd(dmask_token + c, sm0); atomicAdd(dmask_token + c + 1, sm1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(dpos + i, sp[i]);
+      atomicAdd(dmod + i, sp[i]);
+      atomicAdd(dmask_token + c + i, sm[i]);
+    }
   }
 }
 
@@ -299,9 +335,9 @@ extern "C" int avs_decoder_restore_bwd(const void* dout, const int32_t* ids_rest
                                        void* stream) {
   AVS_REQUIRE(dout && ids_restore_a && ids_restore_v && dx && dmask_token && dpos_a && dpos_v && dmod_a && dmod_v,
               "avs_decoder_restore_bwd: null pointer");
-  AVS_REQUIRE(D % 2 == 0, "avs_decoder_restore_bwd: D must be even");
+  AVS_REQUIRE(D % 8 == 0, "avs_decoder_restore_bwd: D must be a multiple of 8");
   if (B == 0 || Ta + Tv == 0) return 0;
-  decoder_restore_bwd_kernel<<<Ta + Tv, 256, 0, (cudaStream_t)stream>>>(
+  decoder_restore_bwd_kernel<<<dim3(Ta + Tv, RB_SLICES), 64, 0, (cudaStream_t)stream>>>(
       (const bf16*)dout, ids_restore_a, ids_restore_v, (bf16*)dx, dmask_token, dpos_a, dpos_v, dmod_a, dmod_v, B, Ta,
       Tv, keep_a, keep_v, D);
   return avs_check_launch("decoder_restore_bwd_kernel");

@@ -20,18 +20,24 @@ struct MaeGeom {
   int P;       // elements per patch
 };
 
-__device__ __forceinline__ float mae_target(const float* __restrict__ in, const MaeGeom& g, int b, int tok, int e) {
-  const int r = tok / g.gw, c = tok % g.gw;
+// PS = patch size known at compile time (16 for every AVSiam model: divisions become shifts / multiply-shifts, which is
+// what this kernel's time went into) or 0 for the generic path.  (r, c) = the token's position in the token grid.
+template <int PS>
+__device__ __forceinline__ float mae_target(const float* __restrict__ in, const MaeGeom& g, int b, int r, int c, int e) {
+  const int p = PS > 0 ? PS : g.p;
   if (g.kind == 0) {
-    const int pf = e / g.p, pt = e % g.p;  // r = f block, c = t block
-    return __ldg(in + ((size_t)b * g.d0 + (size_t)c * g.p + pt) * g.d1 + r * g.p + pf);
+    const int pf = e / p, pt = e % p;  // r = f block, c = t block
+    return __ldg(in + ((size_t)b * g.d0 + (size_t)c * p + pt) * g.d1 + r * p + pf);
+  } else if (PS > 0 && g.C == 3) {
+    const int ch = e % 3, q = (e / 3) % p, pp = e / (3 * p);
+    return __ldg(in + (((size_t)b * 3 + ch) * g.d0 + (size_t)r * p + pp) * g.d1 + (size_t)c * p + q);
   } else {
-    const int ch = e % g.C, q = (e / g.C) % g.p, pp = e / (g.C * g.p);
-    return __ldg(in + (((size_t)b * g.C + ch) * g.d0 + (size_t)r * g.p + pp) * g.d1 + (size_t)c * g.p + q);
+    const int ch = e % g.C, q = (e / g.C) % p, pp = e / (g.C * p);
+    return __ldg(in + (((size_t)b * g.C + ch) * g.d0 + (size_t)r * p + pp) * g.d1 + (size_t)c * p + q);
   }
 }
 
-template <bool BWD>
+template <bool BWD, int PS>
 __global__ void __launch_bounds__(256) mae_loss_kernel(const bf16* __restrict__ pred, const float* __restrict__ in,
                                                        const float* __restrict__ mask, MaeGeom g, int rows,
                                                        float inv_n_masked, float* __restrict__ loss,
@@ -39,17 +45,18 @@ __global__ void __launch_bounds__(256) mae_loss_kernel(const bf16* __restrict__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float local = 0.f;
   const float up = BWD ? (upstream ? *upstream : 1.0f) * 2.0f * inv_n_masked / g.P : 0.f;
-  for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
+  for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
     const float m = mask[r];
-    const int b = (int)(r / g.T), tok = (int)(r % g.T);
+    const int b = r / g.T, tok = r - b * g.T;
+    const int tr = tok / g.gw, tc = tok - tr * g.gw;
     if (m == 0.f) {
       if (BWD)
-        for (int e = lane * 8; e < g.P; e += 256) *reinterpret_cast<uint4*>(dpred + r * g.P + e) = make_uint4(0, 0, 0, 0);
+        for (int e = lane * 8; e < g.P; e += 256) *reinterpret_cast<uint4*>(dpred + (size_t)r * g.P + e) = make_uint4(0, 0, 0, 0);
       continue;
     }
     float acc = 0.f;
     for (int e = lane * 8; e < g.P; e += 256) {
-      const uint4 u = *reinterpret_cast<const uint4*>(pred + r * g.P + e);
+      const uint4 u = *reinterpret_cast<const uint4*>(pred + (size_t)r * g.P + e);
       float pv[8];
       float2 f;
       f = unpack_bf16x2(u.x); pv[0] = f.x; pv[1] = f.y;
@@ -59,14 +66,14 @@ __global__ void __launch_bounds__(256) mae_loss_kernel(const bf16* __restrict__ 
       float d[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        d[j] = pv[j] - mae_target(in, g, b, tok, e + j);
+        d[j] = pv[j] - mae_target<PS>(in, g, b, tr, tc, e + j);
         acc += d[j] * d[j];
       }
       if (BWD) {
         uint4 o;
         o.x = pack_bf16x2(d[0] * up * m, d[1] * up * m); o.y = pack_bf16x2(d[2] * up * m, d[3] * up * m);
         o.z = pack_bf16x2(d[4] * up * m, d[5] * up * m); o.w = pack_bf16x2(d[6] * up * m, d[7] * up * m);
-        *reinterpret_cast<uint4*>(dpred + r * g.P + e) = o;
+        *reinterpret_cast<uint4*>(dpred + (size_t)r * g.P + e) = o;
       }
     }
     if (!BWD) {
@@ -111,9 +118,13 @@ extern "C" int avs_mae_loss_fwd(const void* pred, const float* input, const floa
   if (mae_geom(g, kind, patch, C, d0, d1)) return -1;
   const int rows = B * g.T;
   if (rows == 0) return 0;
-  const int blocks = min(avs_num_sms() * 4, ceil_div(rows, 8));
-  mae_loss_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)pred, input, mask, g, rows,
-                                                                   1.0f / n_masked, loss_accum, nullptr, nullptr);
+  const int blocks = min(avs_num_sms() * 8, ceil_div(rows, 8));
+  if (patch == 16)
+    mae_loss_kernel<false, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)pred, input, mask, g, rows,
+                                                                         1.0f / n_masked, loss_accum, nullptr, nullptr);
+  else
+    mae_loss_kernel<false, 0><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)pred, input, mask, g, rows,
+                                                                        1.0f / n_masked, loss_accum, nullptr, nullptr);
   return avs_check_launch("mae_loss_kernel<fwd>");
 }
 
@@ -126,9 +137,13 @@ extern "C" int avs_mae_loss_bwd(const void* pred, const float* input, const floa
   if (mae_geom(g, kind, patch, C, d0, d1)) return -1;
   const int rows = B * g.T;
   if (rows == 0) return 0;
-  const int blocks = min(avs_num_sms() * 4, ceil_div(rows, 8));
-  mae_loss_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)pred, input, mask, g, rows,
-                                                                  1.0f / n_masked, nullptr, upstream, (bf16*)dpred);
+  const int blocks = min(avs_num_sms() * 8, ceil_div(rows, 8));
+  if (patch == 16)
+    mae_loss_kernel<true, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)pred, input, mask, g, rows,
+                                                                        1.0f / n_masked, nullptr, upstream, (bf16*)dpred);
+  else
+    mae_loss_kernel<true, 0><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)pred, input, mask, g, rows,
+                                                                       1.0f / n_masked, nullptr, upstream, (bf16*)dpred);
   return avs_check_launch("mae_loss_kernel<bwd>");
 }
 
