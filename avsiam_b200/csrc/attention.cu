@@ -260,17 +260,19 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
   const int cpr = H * LPH;                          // 16-byte chunks per row
   const long long total = rows * cpr;
   // total is a multiple of LPH and the stride is a multiple of 32, so all lanes of a shuffle group stay together
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((total + 31) & ~31LL);
-       i += (long long)gridDim.x * blockDim.x) {
+  // (32-bit index arithmetic: the launcher checks rows * chunks < 2^31; 64-bit divisions were most of this kernel's
+  //  instructions)
+  const int total_i = (int)total;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ((total_i + 31) & ~31); i += gridDim.x * blockDim.x) {
     float acc = 0.f;
-    const bool ok = i < total;
-    long long row = 0;
+    const bool ok = i < total_i;
+    int row = 0;
     int c = 0;
     if (ok) {
       row = i / cpr;
-      c = (int)(i % cpr);
-      const uint4 x = *reinterpret_cast<const uint4*>(o + row * ld_o + c * 8);
-      const uint4 y = *reinterpret_cast<const uint4*>(dout + row * ld_o + c * 8);
+      c = i - row * cpr;
+      const uint4 x = *reinterpret_cast<const uint4*>(o + (long long)row * ld_o + c * 8);
+      const uint4 y = *reinterpret_cast<const uint4*>(dout + (long long)row * ld_o + c * 8);
       float2 a, b;
       a = unpack_bf16x2(x.x); b = unpack_bf16x2(y.x); acc += a.x * b.x + a.y * b.y;
       a = unpack_bf16x2(x.y); b = unpack_bf16x2(y.y); acc += a.x * b.x + a.y * b.y;
@@ -281,7 +283,8 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
     for (int off = LPH / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (ok && (c % LPH) == 0) {
       const int h = c / LPH;
-      delta[((row / S) * H + h) * S + (row % S)] = acc;
+      const int sq = row / S;
+      delta[((long long)sq * H + h) * S + (row - sq * S)] = acc;
     }
   }
 }
@@ -508,6 +511,7 @@ extern "C" int avs_attention_bwd(const void* qkv, long long ld_qkv, const void* 
   a.scale_log2 = a.scale * 1.4426950408889634f;
   const long long rows = (long long)n_seq * S;
   const long long chunks = rows * H * (head_dim / 8);
+  AVS_REQUIRE(chunks + 32 < (1ll << 31), "avs_attention_bwd: too many rows for the delta pre-pass");
   const int dblocks = (int)min((long long)avs_num_sms() * 8, ceil_div_ll(chunks, 256));
   if (head_dim == 64) attn_delta_kernel<64><<<dblocks, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, ld_o, S, H, rows);
   else attn_delta_kernel<32><<<dblocks, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, ld_o, S, H, rows);

@@ -9,8 +9,12 @@
 #include "../../include/avsiam_b200.h"
 #include "common.cuh"
 
+// rows are counted in int (M < 2^31): the division runs in 32 bits (a 64-bit division costs ~80 instructions, and
+// these kernels are issue-bound)
 __device__ __forceinline__ long long map_row(long long r, int S, int stride, int off) {
-  return (S > 0 && stride > 0) ? (r / S) * (long long)stride + off + (r % S) : r;
+  if (!(S > 0 && stride > 0)) return r;
+  const int ri = (int)r, q = ri / S;
+  return (long long)q * stride + off + (ri - q * S);
 }
 
 __device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
@@ -165,7 +169,7 @@ __global__ void __launch_bounds__(TPR * RG, (TPR * RG > 192) ? 2 : 3) layernorm_
       mean[k] = 0.f; rstd[k] = 0.f; xrow[k] = 0; seq[k] = 0;
       if (ok[k]) {
         xrow[k] = map_row(r, S, x_stride, x_off);
-        seq[k] = S > 0 ? r / S : 0;
+        seq[k] = S > 0 ? (int)r / S : 0;
         xv[k] = *reinterpret_cast<const uint4*>(x + xrow[k] * D + ci * 8);
         if (dy != nullptr) dv[k] = *reinterpret_cast<const uint4*>(dy + map_row(r, S, y_stride, y_off) * D + ci * 8);
         if (resid != nullptr) rv[k] = *reinterpret_cast<const uint4*>(resid + xrow[k] * D + ci * 8);
