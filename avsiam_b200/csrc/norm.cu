@@ -122,6 +122,11 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
 // column sum of the produced dx = bias gradient of the Linear that feeds this residual stream) are therefore
 // 3 x 8 registers per thread instead of 3 x D/32, and x / dy / resid stay packed in bf16 until used.
 constexpr int LNB_R = 2;
+constexpr int LNB_STAGES = 3;   // iterations of x / dy / resid chunks in flight per thread (cp.async ring)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
   float2 f;
@@ -132,7 +137,7 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
 }
 
 template <int TPR, int RG>
-__global__ void __launch_bounds__(TPR * RG, (TPR * RG > 192) ? 2 : 3) layernorm_bwd_kernel(
+__global__ void __launch_bounds__(TPR * RG, 2) layernorm_bwd_kernel(
     const bf16* __restrict__ dy, const float* __restrict__ dpool, float pool_scale, const bf16* __restrict__ x,
     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
     const bf16* __restrict__ resid, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -155,14 +160,41 @@ __global__ void __launch_bounds__(TPR * RG, (TPR * RG > 192) ? 2 : 3) layernorm_
   for (int j = 0; j < 8; ++j) ag[j] = ab[j] = ad[j] = 0.f;
   const float inv_d = 1.0f / D;
 
+  // The x / dy / resid chunks travel through a per-thread cp.async ring in shared memory, LNB_STAGES iterations deep:
+  // every thread copies and later reads only ITS OWN 16-byte slots, so the pipeline needs no barrier — each thread waits
+  // on its own cp.async groups — and the loads of the next iterations stay in flight during the reductions of this
+  // one (with plain loads the kernel alternated between a burst of loads and a compute phase: ~3 TB/s).
+  extern __shared__ uint4 ln_ring[];    // [LNB_STAGES][LNB_R][3][NT]
+  const long long step = (long long)gridDim.x * (RG * LNB_R);
+  auto issue = [&](long long base, int stage) {
+#pragma unroll
+    for (int k = 0; k < LNB_R; ++k) {
+      const long long r = base + k * RG + rg;
+      if (r < M) {
+        const long long xr = map_row(r, S, x_stride, x_off);
+        uint4* slot = ln_ring + ((size_t)(stage * LNB_R + k) * 3) * NT + t;
+        cp_async16(slot, x + xr * D + ci * 8);
+        if (dy != nullptr) cp_async16(slot + NT, dy + map_row(r, S, y_stride, y_off) * D + ci * 8);
+        if (resid != nullptr) cp_async16(slot + 2 * NT, resid + xr * D + ci * 8);
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  const long long base0 = (long long)blockIdx.x * (RG * LNB_R);
+#pragma unroll
+  for (int st = 0; st < LNB_STAGES - 1; ++st) issue(base0 + st * step, st);   // (groups past M are empty)
+
   int it = 0;
-  for (long long base = (long long)blockIdx.x * (RG * LNB_R); base < M; base += (long long)gridDim.x * (RG * LNB_R), ++it) {
+  for (long long base = base0; base < M; base += step, ++it) {
+    issue(base + (LNB_STAGES - 1) * step, (it + LNB_STAGES - 1) % LNB_STAGES);
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(LNB_STAGES - 1) : "memory");
+    const int stage = it % LNB_STAGES;
     uint4 xv[LNB_R], dv[LNB_R], rv[LNB_R];
     float mean[LNB_R], rstd[LNB_R], s1[LNB_R], s2[LNB_R];
     long long xrow[LNB_R], seq[LNB_R];
     bool ok[LNB_R];
 #pragma unroll
-    for (int k = 0; k < LNB_R; ++k) {                 // issue every load of the LNB_R rows up front
+    for (int k = 0; k < LNB_R; ++k) {
       const long long r = base + k * RG + rg;
       ok[k] = r < M;
       xv[k] = dv[k] = rv[k] = make_uint4(0, 0, 0, 0);
@@ -170,9 +202,10 @@ __global__ void __launch_bounds__(TPR * RG, (TPR * RG > 192) ? 2 : 3) layernorm_
       if (ok[k]) {
         xrow[k] = map_row(r, S, x_stride, x_off);
         seq[k] = S > 0 ? (int)r / S : 0;
-        xv[k] = *reinterpret_cast<const uint4*>(x + xrow[k] * D + ci * 8);
-        if (dy != nullptr) dv[k] = *reinterpret_cast<const uint4*>(dy + map_row(r, S, y_stride, y_off) * D + ci * 8);
-        if (resid != nullptr) rv[k] = *reinterpret_cast<const uint4*>(resid + xrow[k] * D + ci * 8);
+        const uint4* slot = ln_ring + ((size_t)(stage * LNB_R + k) * 3) * NT + t;
+        xv[k] = slot[0];
+        if (dy != nullptr) dv[k] = slot[NT];
+        if (resid != nullptr) rv[k] = slot[2 * NT];
         mean[k] = mean_in[r];
         rstd[k] = rstd_in[r];
       }
@@ -302,9 +335,15 @@ static void launch_ln_bwd(const void* dy, const float* dpool, float pool_scale, 
                           float* dbeta, float* dbias, int M, int seq_len, int x_seq_stride, int x_off,
                           int y_seq_stride, int y_off, cudaStream_t stream) {
   const int rows_per_cta = RG * LNB_R;
-  const int ctas_per_sm = (TPR * RG > 192) ? 2 : 3;
+  const int ctas_per_sm = 2;
   const int blocks = min(avs_num_sms() * ctas_per_sm, ceil_div(M, rows_per_cta));
-  layernorm_bwd_kernel<TPR, RG><<<blocks, TPR * RG, 0, stream>>>(
+  const int ring = LNB_STAGES * LNB_R * 3 * TPR * RG * 16;
+  static bool ring_set = false;   // per instantiation (static + dynamic shared memory can exceed the 48 KB default)
+  if (!ring_set) {
+    cudaFuncSetAttribute(layernorm_bwd_kernel<TPR, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring);
+    ring_set = true;
+  }
+  layernorm_bwd_kernel<TPR, RG><<<blocks, TPR * RG, ring, stream>>>(
       (const bf16*)dy, dpool, pool_scale, (const bf16*)x, mean, rstd, gamma, (const bf16*)resid, (bf16*)dx, dgamma,
       dbeta, dbias, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off);
 }
