@@ -246,7 +246,9 @@ __global__ void __launch_bounds__(TPR * RG, 2) layernorm_bwd_kernel(
 #pragma unroll
           for (int k = 0; k < LNB_R; ++k) { red[b][k][0][warp] = s1[k]; red[b][k][1][warp] = s2[k]; }
         }
-        __syncthreads();
+        // only the WPG warps of this row group exchange partial sums: a named barrier per group lets the RG groups of
+        // the CTA drift apart instead of all waiting for each other in every iteration
+        asm volatile("bar.sync %0, %1;\n" ::"r"(1 + rg), "r"(TPR) : "memory");
 #pragma unroll
         for (int k = 0; k < LNB_R; ++k) {
           float t1 = 0.f, t2 = 0.f;
