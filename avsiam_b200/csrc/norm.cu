@@ -8,6 +8,7 @@
 //   y_row(r) = (r / S) * y_seq_stride + y_off + (r % S)     (S == 0 => identity)
 #include "../../include/avsiam_b200.h"
 #include "common.cuh"
+#include <stdlib.h>
 
 // rows are counted in int (M < 2^31): the division runs in 32 bits (a 64-bit division costs ~80 instructions, and
 // these kernels are issue-bound)
@@ -305,6 +306,118 @@ __global__ void __launch_bounds__(TPR * RG, 2) layernorm_bwd_kernel(
   }
 }
 
+// Forward for the transformer widths (512 / 768 / 1024), with the backward's thread mapping: every thread owns ONE
+// 16-byte chunk of a row (gamma / beta for its 8 columns stay in registers for the whole kernel), a row is covered by
+// TPR consecutive threads, LNF_R rows per row group and iteration, x travels through a per-thread cp.async ring
+// LNF_STAGES iterations deep, and the two reductions (mean, centred second moment) synchronise only the WPG warps of a
+// row group through a named barrier.
+constexpr int LNF_R = 2, LNF_STAGES = 4;
+template <int TPR, int RG>
+__global__ void __launch_bounds__(TPR * RG, 2) layernorm_fwd_rg_kernel(
+    const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+    bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int S, int x_stride,
+    int x_off, int y_stride, int y_off) {
+  constexpr int NT = TPR * RG, NW = NT / 32, D = TPR * 8, WPG = TPR / 32;
+  static_assert(TPR % 32 == 0 && WPG >= 2, "row groups must be whole warps");
+  extern __shared__ uint4 lnf_ring[];   // [LNF_STAGES][LNF_R][NT]
+  __shared__ float red[2][LNF_R][NW];
+  const int t = threadIdx.x, rg = t / TPR, ci = t % TPR, warp = t >> 5, lane = t & 31;
+  float g[8], b[8];
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + ci * 8), g1 = *reinterpret_cast<const float4*>(gamma + ci * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + ci * 8), b1 = *reinterpret_cast<const float4*>(beta + ci * 8 + 4);
+    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+  }
+  const long long step = (long long)gridDim.x * (RG * LNF_R);
+  auto issue = [&](long long base, int stage) {
+#pragma unroll
+    for (int k = 0; k < LNF_R; ++k) {
+      const long long r = base + k * RG + rg;
+      if (r < M) cp_async16(lnf_ring + (size_t)(stage * LNF_R + k) * NT + t, x + map_row(r, S, x_stride, x_off) * D + ci * 8);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  const long long base0 = (long long)blockIdx.x * (RG * LNF_R);
+#pragma unroll
+  for (int st = 0; st < LNF_STAGES - 1; ++st) issue(base0 + st * step, st);
+  const float inv_d = 1.0f / D;
+  int it = 0;
+  for (long long base = base0; base < M; base += step, ++it) {
+    issue(base + (LNF_STAGES - 1) * step, (it + LNF_STAGES - 1) % LNF_STAGES);
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(LNF_STAGES - 1) : "memory");
+    const int stage = it % LNF_STAGES;
+    float v[LNF_R][8], s[LNF_R];
+#pragma unroll
+    for (int k = 0; k < LNF_R; ++k) {
+      const long long r = base + k * RG + rg;
+      const uint4 u = (r < M) ? lnf_ring[(size_t)(stage * LNF_R + k) * NT + t] : make_uint4(0, 0, 0, 0);
+      unpack8(u, v[k]);
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a += v[k][j];
+      s[k] = warp_sum(a);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < LNF_R; ++k) red[0][k][warp] = s[k];
+    }
+    asm volatile("bar.sync %0, %1;\n" ::"r"(1 + rg), "r"(TPR) : "memory");
+    float mean[LNF_R], q[LNF_R];
+#pragma unroll
+    for (int k = 0; k < LNF_R; ++k) {
+      float tsum = 0.f;
+#pragma unroll
+      for (int w = 0; w < WPG; ++w) tsum += red[0][k][rg * WPG + w];
+      mean[k] = tsum * inv_d;
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[k][j] - mean[k];
+        a = fmaf(d, d, a);
+      }
+      q[k] = warp_sum(a);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < LNF_R; ++k) red[1][k][warp] = q[k];
+    }
+    asm volatile("bar.sync %0, %1;\n" ::"r"(1 + rg), "r"(TPR) : "memory");
+#pragma unroll
+    for (int k = 0; k < LNF_R; ++k) {
+      const long long r = base + k * RG + rg;
+      if (r >= M) continue;
+      float tq = 0.f;
+#pragma unroll
+      for (int w = 0; w < WPG; ++w) tq += red[1][k][rg * WPG + w];
+      const float rstd = rsqrtf(tq * inv_d + eps);
+      if (ci == 0) {
+        mean_out[r] = mean[k];
+        rstd_out[r] = rstd;
+      }
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[k][j] - mean[k]) * rstd * g[j] + b[j];
+      store8(y + map_row(r, S, y_stride, y_off) * D + ci * 8, o);
+    }
+  }
+}
+
+template <int TPR, int RG>
+static void launch_ln_fwd_rg(const void* x, const float* gamma, const float* beta, float eps, void* y, float* mean,
+                             float* rstd, int M, int S, int x_stride, int x_off, int y_stride, int y_off,
+                             cudaStream_t stream) {
+  const int ring = LNF_STAGES * LNF_R * TPR * RG * 16;
+  static bool ring_set = false;
+  if (!ring_set) {
+    cudaFuncSetAttribute(layernorm_fwd_rg_kernel<TPR, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring);
+    ring_set = true;
+  }
+  const int blocks = min(avs_num_sms() * 2, ceil_div(M, RG * LNF_R));
+  layernorm_fwd_rg_kernel<TPR, RG><<<blocks, TPR * RG, ring, stream>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, mean,
+                                                                      rstd, M, S, x_stride, x_off, y_stride, y_off);
+}
+
 static int ln_nch(int D) { return (D + 255) / 256; }
 
 extern "C" int avs_layernorm_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y,
@@ -315,6 +428,13 @@ extern "C" int avs_layernorm_fwd(const void* x, const float* gamma, const float*
   AVS_REQUIRE(D % 8 == 0 && D <= 2048, "avs_layernorm_fwd: D must be a multiple of 8 and <= 2048 (got %d)", D);
   AVS_REQUIRE(((uintptr_t)gamma & 15) == 0 && ((uintptr_t)beta & 15) == 0, "avs_layernorm_fwd: gamma/beta 16-byte alignment");
   if (M == 0) return 0;
+  static const bool rg_path = !(getenv("AVS_LN_FWD_RG") && atoi(getenv("AVS_LN_FWD_RG")) == 0);
+  if (rg_path && (D == 512 || D == 768 || D == 1024)) {
+    if (D == 512) launch_ln_fwd_rg<64, 4>(x, gamma, beta, eps, y, mean, rstd, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off, stream);
+    else if (D == 768) launch_ln_fwd_rg<96, 2>(x, gamma, beta, eps, y, mean, rstd, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off, stream);
+    else launch_ln_fwd_rg<128, 2>(x, gamma, beta, eps, y, mean, rstd, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off, stream);
+    return avs_check_launch("layernorm_fwd_rg_kernel");
+  }
   const int blocks = min(avs_num_sms() * 8, ceil_div(M, 8));
 #define LN_FWD(N)                                                                                              \
   layernorm_fwd_kernel<N><<<blocks, 256, 0, stream>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, mean, rstd, M, D, \
