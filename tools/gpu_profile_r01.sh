@@ -10,4 +10,5 @@ timeout 200 python tools/loss_parity_report.py 2>&1 | grep "^case" > gpurun_out/
 timeout 120 python tools/attn_bench.py > gpurun_out/r01_attn_bench.log 2>&1
 timeout 120 python tools/gemm_bench.py > gpurun_out/r01_gemm_bench.log 2>&1
 timeout 120 python tools/augment_bench.py > gpurun_out/r01_augment_bench.log 2>&1
+timeout 100 python tools/ln_bench.py > gpurun_out/r01_ln_bench.log 2>&1
 tail -1 gpurun_out/r01_bench.log | cut -c1-300; cat gpurun_out/r01_tests.log
