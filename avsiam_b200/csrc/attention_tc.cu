@@ -598,7 +598,7 @@ int launch_bwd(const TcArgs& a, int n_seq, cudaStream_t stream) {
 //     new block exceeds it by more than 2^8 (probabilities then stay below 256, exact in the final O / l); raising it
 //     rescales O in tensor memory (tcgen05.ld / st by the owning thread).  That happens in the first one or two units
 //     of a query block and almost never afterwards, so there is no correction warp and no second pass.
-//   * when the Cauchy-Schwarz bound |q_i| max_j |k_j| of a query block's scores is small (<= 60 in the log2 domain) it
+//   * when the Cauchy-Schwarz bound |q_i| max_j |k_j| of a query block's scores is small (<= 40 in the log2 domain) it
 //     replaces the maximum altogether: exp2(score - bound) cannot underflow, so the maximum pass, the exchange between
 //     the two warps of a row and the rescaling all disappear (the common case; the lazy maximum is the general one).
 //   * P goes back to TENSOR MEMORY as packed bf16 and is the A operand of the P V product (tcgen05.mma with A in TMEM),
@@ -633,7 +633,9 @@ constexpr int TCF_COL_S = 0, TCF_COL_P = 128, TCF_COL_O = 192, TCF_COL_L = 224, 
 #ifndef TCF_POLY_EVERY
 #define TCF_POLY_EVERY 4   // every 4th pair of exponentials on the FMA pipe (0 = all on MUFU)
 #endif
-constexpr float TCF_BOUND_MAX = 60.0f;   // largest score bound (log2 domain) for the no-maximum fast path: 2^-120 is normal
+// largest score bound (log2 domain) for the no-maximum fast path: probabilities stay >= 2^-80, so that even their
+// products with small V entries and the fp32 accumulators of O stay far from the denormal range
+constexpr float TCF_BOUND_MAX = 40.0f;
 
 struct TcFwdArgs {
   const bf16* qkv;
@@ -816,7 +818,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
     const float k2max = __uint_as_float(*s_k2max);
     // Fast path of a query block: every row of this lane quarter has a score bound B = |q| max|k| * scale (log2 domain)
     // of at most TCF_BOUND_MAX.  All scores then lie in [-B, B], so exp2(score - B) >= 2^(-2 B) stays a normal fp32 /
-    // bf16 number and B can stand in for the row maximum: no maximum pass, no exchange, no rescaling.  The decision
+    // bf16 number (with margin for the products with V) and B can stand in for the row maximum: no maximum pass, no exchange, no rescaling.  The decision
     // depends only on the rows of the lane quarter, so the two warps that share them always agree.
     auto block_bound = [&](int blk) {
       const int qr = blk * 128 + row;
@@ -912,7 +914,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 2) attn_fwd_tc_kernel(const TcFwd
         }
         const bool whole = !last || ch * 32 + 32 <= valid_last;   // every column of this chunk is a valid key
         if (whole && fast && TCF_POLY_EVERY > 0) {
-          // fast path: exponents lie in [-120, 0], so every TCF_POLY_EVERY-th pair can take the polynomial
+          // fast path: exponents lie in [-80, 0], so every TCF_POLY_EVERY-th pair can take the polynomial
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
             const float x0 = fmaf(__uint_as_float(sr[c]), a.scale_log2, -m_run);
