@@ -284,6 +284,31 @@ def test_attention_fwd_rising_scores_rescale_path(S):
     assert float(err.max()) < 6e-3, (float(err.max()), float(err.mean()))   # row sums are taken over the bf16-rounded P
 
 
+def test_attention_fwd_mixed_bound_and_exact_blocks():
+    """Query blocks whose Cauchy-Schwarz score bound is small take the no-maximum path of the tcgen05 forward, the others
+    the lazy-maximum path: alternate them inside one head (and inside one lane quarter's neighbourhood) and compare."""
+    n_seq, S, H, hd = 2, 708, 2, 32
+    D = H * hd
+    g = torch.Generator(device="cpu").manual_seed(5)
+    q = torch.randn(n_seq, S, H, hd, generator=g) * 0.5
+    k = torch.randn(n_seq, S, H, hd, generator=g)
+    v = torch.randn(n_seq, S, H, hd, generator=g)
+    q[:, 128:256] *= 40.0            # query block 1: bound far above the limit
+    q[:, 300:310] *= 60.0            # a few rows of block 2 (one lane quarter exact, the others fast)
+    q[:, 640:] *= 25.0               # the ragged last block
+    qkv = torch.stack([q, k, v], 2).reshape(n_seq * S, 3 * D).to(torch.bfloat16).to(DEV)
+    out = torch.empty(n_seq * S, D, dtype=torch.bfloat16, device=DEV)
+    lse2 = torch.empty(n_seq, H, S, device=DEV)
+    ops.attention_fwd(qkv, out, lse2, n_seq, S, H, hd)
+    q5 = qkv.float().reshape(n_seq, S, 3, H, hd).permute(2, 0, 3, 1, 4)
+    att = (q5[0] @ q5[1].transpose(-2, -1)) * hd ** -0.5
+    ref = (att.softmax(-1) @ q5[2]).transpose(1, 2).reshape(n_seq * S, D)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < 8e-3
+    err = (lse2 - torch.logsumexp(att, -1) / math.log(2)).abs()
+    assert float(err.max()) < 6e-3, float(err.max())
+
+
 # ------------------------------------------------------------------------------------------------ losses
 def test_mae_loss_fwd_bwd():
     d = O.VIT_B
