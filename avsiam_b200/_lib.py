@@ -25,6 +25,7 @@ class GemmEpilogue(Structure):
         ("rowadd", c_void_p),
         ("rowidx", c_void_p),
         ("rowadd_rows", c_int),
+        ("colsum", c_void_p),
     ]
 
 

@@ -100,23 +100,6 @@ __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t (&r)[N]
   else tmem_st_32x32b_x8(taddr, r);
 }
 
-// Column sums over the 32 rows a warp holds (one row per lane, N columns per lane): recursive halving, so N = 16
-// costs 16 shuffles instead of 80.  On return lane L holds the sum of column  (N == 32 ? L : (L >> 1) & 15)  in v[0].
-template <int N>
-__device__ __forceinline__ void warp_colsum(float (&v)[N], int lane) {
-#pragma unroll
-  for (int n = N / 2, o = 16; n >= 1; n >>= 1, o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < n; ++i) {
-      const float send = up ? v[i] : v[i + n];
-      const float keep = up ? v[i + n] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-    }
-  }
-  if (N == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
 __device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) {
   uint32_t d;
   asm("mul.rn.bf16x2 %0, %1, %2;\n" : "=r"(d) : "r"(a), "r"(b));

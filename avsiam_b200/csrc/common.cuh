@@ -259,6 +259,23 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return fmaf(x * fmaf(-s, s, s), r, s);
 }
 
+// Column sums over the 32 rows a warp holds (one row per lane, N columns per lane): recursive halving, so N = 16
+// costs 16 shuffles instead of 80.  On return lane L holds the sum of column  (N == 32 ? L : (L >> 1) & 15)  in v[0].
+template <int N>
+__device__ __forceinline__ void warp_colsum(float (&v)[N], int lane) {
+#pragma unroll
+  for (int n = N / 2, o = 16; n >= 1; n >>= 1, o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = up ? v[i] : v[i + n];
+      const float keep = up ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  if (N == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 // ---- TMA store / bulk-group plumbing (epilogues) ----
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(

@@ -90,6 +90,7 @@ extern "C" int avs_gemm_bf16(const void* A, long long lda, int a_major, const vo
   if (epi->flags & AVS_EPI_DGELU) AVS_REQUIRE(epi->aux_in != nullptr, "avs_gemm_bf16: DGELU needs aux_in");
   if (epi->bias) AVS_REQUIRE((reinterpret_cast<uintptr_t>(epi->bias) & 15) == 0, "avs_gemm_bf16: bias alignment");
   if (epi->rowadd) AVS_REQUIRE(epi->rowadd_rows > 0, "avs_gemm_bf16: rowadd_rows must be > 0");
+  AVS_REQUIRE(!epi->colsum || !out_f32, "avs_gemm_bf16: colsum needs a bf16 output");
 
   const int BN = (N > 128) ? 256 : 128;
   const int m_tiles = ceil_div(M, GEMM_BLOCK_M), n_tiles = ceil_div(N, BN);
@@ -168,6 +169,7 @@ extern "C" int avs_gemm_bf16(const void* A, long long lda, int a_major, const vo
   args.epi.rowadd = epi->rowadd;
   args.epi.rowidx = epi->rowidx;
   args.epi.rowadd_rows = epi->rowadd_rows;
+  args.epi.colsum = epi->colsum;
 
   const int num_tiles = m_tiles * n_tiles * split_k;
   const int grid = num_tiles < sms ? num_tiles : sms;

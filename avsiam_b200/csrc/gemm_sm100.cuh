@@ -38,6 +38,7 @@ struct GemmEpilogue {
   const float* rowadd;  // [rowadd_rows, N] fp32 table or null  (positional embedding)
   const int* rowidx;    // [M] int32 row index into rowadd, or null => m % rowadd_rows
   int rowadd_rows;
+  float* colsum;        // [N] fp32 or null: += column sums of the output (bf16 / TMA epilogue only)
 };
 
 struct GemmArgs {
@@ -66,7 +67,7 @@ constexpr int GEMM_EPI_BUF = 32 * GEMM_EPI_CHUNK * 2;  // one [32 rows x 32 cols
 // unit turns each box row into one L2 write request, so 64-byte rows (the 32-column tiles of v2) made the stores —
 // 2048 row requests per 128x256 tile — the bound of every bf16-output GEMM (ncu: MMA warp polling tmem_empty).
 constexpr int GEMM_OUT_BUF = 32 * 64 * 2;
-constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
+constexpr int GEMM_SMEM_LIMIT = 226 * 1024;   // dynamic part; 1 KB of static shared memory holds the column-sum accumulators
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -276,6 +277,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // ============================ epilogue (8 warps) ============================
     // warp w may only touch TMEM lanes 32*(w%4)..+32; the two warps sharing a quarter split the tile's columns.
     const int ew = warp - 2;
+    // column sums of the output (the bias gradient of the upstream Linear), accumulated per CTA and tile in shared
+    // memory and flushed with one global atomic per column and tile
+    __shared__ float s_colsum[256];
+    if (args.epi.colsum != nullptr) {
+      s_colsum[ew * 32 + lane] = 0.f;
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    }
     const int quarter = warp & 3;
     const int half = ew >> 2;
     constexpr int CH = BLOCK_N / (2 * GEMM_EPI_CHUNK);  // chunks per warp per tile
@@ -417,6 +425,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               f = unpack_bf16x2(in4[j].w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
             }
           }
+          if (ep.colsum != nullptr) {
+            float cs[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cs[j] = row_ok ? v[j] : 0.f;
+            warp_colsum<32>(cs, lane);                  // lane L now holds the sum of column L over the warp's 32 rows
+            if (nc + lane < args.N) atomicAdd(&s_colsum[ccol + lane], cs[0]);
+          }
           uint4 o[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -464,6 +479,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
         }
+      }
+      if (ep.colsum != nullptr) {
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");      // every epilogue warp has added its rows of this tile
+        const int et = ew * 32 + lane;
+        if (et < BLOCK_N && n0 + et < args.N) {
+          atomicAdd(ep.colsum + n0 + et, s_colsum[et]);
+          s_colsum[et] = 0.f;
+        }
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;

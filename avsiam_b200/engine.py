@@ -16,6 +16,8 @@ from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
+import os
+
 import torch
 
 from . import ops
@@ -166,6 +168,7 @@ class Engine:
         self.P = arena
         self.d = dims
         self.dev = arena.device
+        self.fuse_fc1_bias = os.environ.get("AVS_FUSE_FC1_BIAS", "1") != "0"   # A/B switch
 
     # -------------------------------------------------------------------------------------------- helpers
     def _empty(self, *shape, dtype=BF16) -> torch.Tensor:
@@ -181,10 +184,13 @@ class Engine:
 
     def _linear_bwd(self, dy: torch.Tensor, x_in: torch.Tensor, wname: str, bname: str, M: int, n_out: int, k_in: int,
                     dx_out: Optional[torch.Tensor], dgelu_aux: Optional[torch.Tensor] = None, alpha: float = 1.0,
-                    skip_bias: bool = False):
-        """dgrad (optional), wgrad and bias-grad of y = x W^T + b. No transposes: see gemm_sm100.cuh."""
+                    skip_bias: bool = False, dx_colsum: Optional[torch.Tensor] = None):
+        """dgrad (optional), wgrad and bias-grad of y = x W^T + b. No transposes: see gemm_sm100.cuh.
+        `dx_colsum` (fp32 [k_in]): += column sums of dx, accumulated in the dgrad GEMM's epilogue — the bias gradient of
+        the Linear whose output gradient dx is (fc1, when this is fc2's dgrad with the dGELU epilogue)."""
         if dx_out is not None:
-            ops.gemm(dy, self._w2d(wname), dx_out, M, k_in, n_out, b_major=MAJOR_MN, dgelu_aux=dgelu_aux)
+            ops.gemm(dy, self._w2d(wname), dx_out, M, k_in, n_out, b_major=MAJOR_MN, dgelu_aux=dgelu_aux,
+                     colsum=dx_colsum)
         ops.gemm(dy, x_in, self._g2d(wname), n_out, k_in, M, a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
                  split_k=0, alpha=alpha)
         if not skip_bias:
@@ -277,10 +283,13 @@ class Engine:
             def bwd():
                 dx2 = out.g
                 dh = self._empty(M, Hid)
+                fuse = self.fuse_fc1_bias
                 self._linear_bwd(dx2, hact, pfx + "mlp.fc2.weight", pfx + "mlp.fc2.bias", M, D, Hid, dh, dgelu_aux=hpre,
-                                 skip_bias=out.sink_done)
+                                 skip_bias=out.sink_done,
+                                 dx_colsum=self.P.grad(pfx + "mlp.fc1.bias") if fuse else None)
                 dln2 = self._empty(M, D)
-                self._linear_bwd(dh, ln2, pfx + "mlp.fc1.weight", pfx + "mlp.fc1.bias", M, Hid, D, dln2)
+                # fc1.bias gradient = column sums of dh: taken in the dGELU epilogue above instead of a pass over dh
+                self._linear_bwd(dh, ln2, pfx + "mlp.fc1.weight", pfx + "mlp.fc1.bias", M, Hid, D, dln2, skip_bias=fuse)
                 del dh
                 dx1 = self._empty(M, D)
                 # LN2 backward writes dx1 = d(x1) and its column sums = gradient of proj.bias in the same pass

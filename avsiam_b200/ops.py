@@ -47,7 +47,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, M: int, N: int, K:
          b_major: int = MAJOR_K, bias: Optional[torch.Tensor] = None, gelu: bool = False,
          aux_out: Optional[torch.Tensor] = None, dgelu_aux: Optional[torch.Tensor] = None,
          resid: Optional[torch.Tensor] = None, rowadd: Optional[torch.Tensor] = None,
-         rowidx: Optional[torch.Tensor] = None, alpha: float = 1.0, accumulate: bool = False, split_k: int = 1):
+         rowidx: Optional[torch.Tensor] = None, alpha: float = 1.0, accumulate: bool = False, split_k: int = 1,
+         colsum: Optional[torch.Tensor] = None):
     """out[M,N] = epi(sum_k A(m,k) B(n,k)); see avs_gemm_bf16. `a`/`b` are 2-D bf16 views (row pitch = stride(0))."""
     _chk(a, BF16, "gemm.a", contiguous=False)
     _chk(b, BF16, "gemm.b", contiguous=False)
@@ -79,6 +80,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, M: int, N: int, K:
         ep.rowadd, ep.rowadd_rows = rowadd.data_ptr(), rowadd.shape[0]
         if rowidx is not None:
             ep.rowidx = _chk(rowidx, I32, "gemm.rowidx").data_ptr()
+    if colsum is not None:   # fp32 [N] += column sums of `out` (bias gradient of the Linear that consumes `out` as dy)
+        ep.colsum = _chk(colsum, F32, "gemm.colsum").data_ptr()
     ep.flags = flags
     rc = _lib.lib().avs_gemm_bf16(a.data_ptr(), lda, a_major, b.data_ptr(), ldb, b_major, out.data_ptr(), ldc, M, N, K,
                                   ctypes.byref(ep), split_k, _stream())

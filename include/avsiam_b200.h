@@ -55,6 +55,8 @@ typedef struct {
   const float* rowadd;    /* fp32 [rowadd_rows, N] or NULL : v += rowadd[rowidx ? rowidx[m] : m % rowadd_rows] */
   const int32_t* rowidx;  /* [M] or NULL */
   int rowadd_rows;
+  float* colsum;          /* fp32 [N] or NULL : += column sums of the bf16-path output (bias gradient of the Linear
+                             that produced this GEMM's dy), accumulated in the epilogue — bf16 outputs only */
 } avs_gemm_epilogue_t;
 
 int avs_gemm_bf16(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major, void* C,

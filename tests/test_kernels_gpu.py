@@ -309,6 +309,24 @@ def test_attention_fwd_mixed_bound_and_exact_blocks():
     assert float(err.max()) < 6e-3, float(err.max())
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 512, 256), (4133, 2048, 512), (300, 200, 128)])
+def test_gemm_fused_colsum_of_dgelu_output(M, N, K):
+    """The dGELU-epilogue GEMM (fc2's dgrad) also accumulates the column sums of its output = the fc1 bias gradient
+    (ragged M and N tails, several tiles per CTA, accumulation into a non-zero buffer)."""
+    a = rnd(M, K, dtype=torch.bfloat16)
+    w = rnd(K, N, dtype=torch.bfloat16) * K ** -0.5          # MN-major B: out[m, n] = sum_k a[m, k] w[k, n]
+    z = rnd(M, N, dtype=torch.bfloat16)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    cs = torch.full((N,), 3.0, device=DEV)
+    ops.gemm(a, w, out, M, N, K, b_major=ops.MAJOR_MN, dgelu_aux=z, colsum=cs)
+    plain = torch.empty_like(out)
+    ops.gemm(a, w, plain, M, N, K, b_major=ops.MAJOR_MN, dgelu_aux=z)
+    assert torch.equal(out, plain)                            # the output itself is untouched
+    ref = 3.0 + out.float().sum(0)
+    scale = float(out.float().abs().sum(0).max())
+    assert float((cs - ref).abs().max()) <= 4e-3 * scale + 1e-3   # fp32 sums of the pre-rounding values
+
+
 # ------------------------------------------------------------------------------------------------ losses
 def test_mae_loss_fwd_bwd():
     d = O.VIT_B
