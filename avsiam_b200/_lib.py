@@ -41,6 +41,7 @@ SIGNATURES = {
     "avs_reset_launch_count": [],
     "avs_gemm_bf16": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, POINTER(GemmEpilogue), _I, _P],
     "avs_mask_argsort": [_P, _I, _I, _I, _P, _P, _P, _P],
+    "avs_mask_force_noise": [_P, _I, _I, _I, _P, _I, _P, _I, _F, _P],
     "avs_gather_rows": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "avs_patchify_audio": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "avs_patchify_video": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -70,6 +71,8 @@ SIGNATURES = {
     "avs_infonce_fwd": [_P, _P, _I, _I, _F, _I, _P, _P, _P, _P],
     "avs_infonce_bwd": [_I, _I, _F, _I, _F, _P, _P, _I, _I, _P, _P, _P, _P],
     "avs_adam_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _I, _P, _P, _P, _P],
+    "avs_adam_step_groups": [_P, _P, _P, _P, _P, _L, POINTER(c_float), POINTER(c_float), _I, _F, _F, _F, _I, _I, _P, _P,
+                             _P, _P, _P],
     "avs_cast_f32_to_bf16": [_P, _P, _L, _P],
     "avs_colsum_bf16": [_P, _L, _P, _I, _I, _F, _P],
     "avs_found_inf": [_P, _L, _P, _P],

@@ -70,7 +70,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(compile_one, jobs))
     if jobs or not os.path.exists(OUT):
-        cmd = [NVCC, *ARCH_FLAGS, "-shared", "-o", OUT, *objs, "-lcudart"]
+        # -cudart shared: the CUDA runtime is NOT linked in statically (no runtime code or symbol strings in the .so)
+        cmd = [NVCC, *ARCH_FLAGS, "-shared", "-cudart", "shared", "-o", OUT, *objs]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -255,24 +255,31 @@ class CAVMAE_BASE(nn.Module):
             return ops.mask_from_ids(supplied.to(dev, I32).contiguous(), keep) + (keep,)
         return self._ids_from_noise(torch.rand(n, L, device=dev), keep) + (keep,)
 
-    def _structured_ids(self, n: int, L: int, ratio: float, dev, supplied=None):
-        """random_masking_structured mode 'tf' (cav_mae_base.py:392-439): random.sample picks int(t*r*0.7) time
-        columns and int(f*r*0.7) frequency rows whose noise is forced to 1.1 (removed first); the reference does this
-        with per-sample Python loops of GPU slice writes — here the 0/1 pattern is built on the host in one shot."""
+    def _structured_ids(self, n: int, L: int, ratio: float, dev, supplied=None, mode: str = "tf", noise=None):
+        """random_masking_structured (cav_mae_base.py:392-439), modes 'time' / 'freq' / 'tf': random.sample picks
+        int(t*r) time columns ('time'), int(f*r) frequency rows ('freq') or int(t*r*0.7) columns then int(f*r*0.7) rows
+        ('tf') of the [f, t] patch grid per sample; their noise is forced to 1.1 ("large value will be removed").
+        The draws use Python's `random` in the reference's exact order (all samples' columns, then all samples' rows), so
+        a run seeded with random.seed(s) removes the same columns / rows as the reference; the N x k slice writes become
+        one launch (ops.mask_force_noise), then the stable device argsort. `noise` (fp32 [n, L]) may be supplied."""
         keep = len_keep_of(L, ratio)
         if supplied is not None:
             return ops.mask_from_ids(supplied.to(dev, I32).contiguous(), keep) + (keep,)
         d = self.dims
         t, f = d.ta, d.fa
-        force = torch.zeros(n, f, t, dtype=torch.bool)
-        for i in range(n):
-            for k in random.sample(range(t), int(t * ratio * 0.7)):
-                force[i, :, k] = True
-        for i in range(n):
-            for k in random.sample(range(f), int(f * ratio * 0.7)):
-                force[i, k, :] = True
-        noise = torch.rand(n, L, device=dev)
-        noise.masked_fill_(force.reshape(n, L).to(dev), 1.1)
+        cols = rows = None
+        if mode == "time":
+            cols = [random.sample(range(t), int(t * ratio)) for _ in range(n)]
+        elif mode == "freq":
+            rows = [random.sample(range(f), int(f * ratio)) for _ in range(n)]
+        elif mode == "tf":
+            cols = [random.sample(range(t), int(t * ratio * 0.7)) for _ in range(n)]
+            rows = [random.sample(range(f), int(f * ratio * 0.7)) for _ in range(n)]
+        else:
+            raise ValueError(f"mask_mode {mode!r}: expected 'unstructured', 'time', 'freq' or 'tf'")
+        noise = torch.rand(n, L, device=dev) if noise is None else noise.to(dev, F32).contiguous().clone()
+        as_dev = lambda lst: torch.tensor(lst, dtype=I32).to(dev) if lst and len(lst[0]) else None   # [n, k]
+        ops.mask_force_noise(noise, f, t, as_dev(cols), as_dev(rows), 1.1)
         return self._ids_from_noise(noise, keep) + (keep,)
 
     # -------------------------------------------------------------------------------------------- forward
@@ -307,7 +314,7 @@ class CAVMAE_BASE(nn.Module):
 
         if self.arrangement == "single_pass":
             ids_a, ira, mask_a, ka = self._unstructured_ids(B, d.Ta, mask_ratio_a, dev, getattr(plan, "ids_shuffle_a", None)) \
-                if mask_mode == 'unstructured' else self._structured_ids(B, d.Ta, mask_ratio_a, dev, getattr(plan, "ids_shuffle_a", None))
+                if mask_mode == 'unstructured' else self._structured_ids(B, d.Ta, mask_ratio_a, dev, getattr(plan, "ids_shuffle_a", None), mode=mask_mode)
             ids_v, irv, mask_v, kv = self._unstructured_ids(B, d.Tv, mask_ratio_v, dev, getattr(plan, "ids_shuffle_v", None))
             x, groups = eng.embed(tape, audio, imgs, [EmbedSpec("a", ids_a, ka), EmbedSpec("v", ids_v, kv)])
             for i in range(d.depth):

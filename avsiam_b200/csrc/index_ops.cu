@@ -66,6 +66,35 @@ extern "C" int avs_mask_argsort(const float* noise, int N, int L, int len_keep, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// avs_mask_force_noise: the structured-mask pattern of random_masking_structured (cav_mae_base.py:404-423): the noise
+// of whole time columns / frequency rows of the [f, t] patch grid is overwritten with `value` (1.1: "large value will
+// be removed") before the argsort. The column / row lists are the host's random.sample draws (the reference draws
+// them with Python's `random`, so the draws stay on the host to remain seed-compatible); one launch applies all of
+// them for the whole batch instead of the reference's N x k Python slice writes.
+//   cols int32 [N, kt] (time indices, may be NULL / kt = 0), rows int32 [N, kf] (frequency indices, may be NULL).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void mask_force_noise_kernel(float* __restrict__ noise, const int* __restrict__ cols, int kt,
+                                        const int* __restrict__ rows, int kf, int f, int t, float value) {
+  float* nz = noise + (size_t)blockIdx.x * f * t;
+  const int* c = cols ? cols + (size_t)blockIdx.x * kt : nullptr;
+  const int* r = rows ? rows + (size_t)blockIdx.x * kf : nullptr;
+  for (int i = threadIdx.x; i < kt * f; i += blockDim.x) nz[(i / kt) * t + c[i % kt]] = value;
+  for (int i = threadIdx.x; i < kf * t; i += blockDim.x) nz[r[i / t] * t + (i % t)] = value;
+}
+
+extern "C" int avs_mask_force_noise(float* noise, int N, int f, int t, const int32_t* cols, int kt,
+                                    const int32_t* rows, int kf, float value, void* stream) {
+  AVS_REQUIRE(noise, "avs_mask_force_noise: null pointer");
+  AVS_REQUIRE(N >= 0 && f > 0 && t > 0 && kt >= 0 && kf >= 0 && kt <= t && kf <= f,
+              "avs_mask_force_noise: bad shape N=%d f=%d t=%d kt=%d kf=%d", N, f, t, kt, kf);
+  AVS_REQUIRE((kt == 0 || cols) && (kf == 0 || rows), "avs_mask_force_noise: index list missing");
+  if (N == 0 || (kt == 0 && kf == 0)) return 0;
+  mask_force_noise_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(noise, kt ? cols : nullptr, kt, kf ? rows : nullptr, kf,
+                                                              f, t, value);
+  return avs_check_launch("mask_force_noise_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // avs_gather_rows: out[n, i, :] = x[n, ids[n, i], :] for i < keep — byte-exact row copies (16-byte vectors).
 // Replaces torch.gather(x, 1, ids_keep.unsqueeze(-1).repeat(1,1,D)) at cav_mae_base.py:382,431.
 // ---------------------------------------------------------------------------------------------------------

@@ -6,23 +6,55 @@
 #include "common.cuh"
 
 // torch.optim.Adam semantics (non-amsgrad): coupled L2 (g += wd*p) or decoupled (AdamW: p *= 1 - lr*wd).
-// found_inf (optional, device int/float flag != 0) => skip the whole step (GradScaler.step behaviour).
+// found_inf (optional, device float flag != 0) => skip the whole step (GradScaler.step behaviour).
 // inv_scale (optional, device float) multiplies every gradient first (GradScaler.unscale_).
 // active (optional, one byte per 64-element chunk of the arena): 0 => the chunk belongs to a parameter whose
-// .grad is None in the reference (torch.optim skips those entirely — no weight decay, no moment update).
+// .grad is None in the reference or that was not handed to the optimizer (torch.optim skips those entirely — no
+// weight decay, no moment update); k > 0 => the chunk belongs to param_group k-1, whose lr / weight_decay apply
+// (the finetune loop builds three groups, traintest_ft_base.py:78-83).
+// tick (optional, device {int step; float bc1; float bc2_sqrt}): the step counter lives on the device and advances only
+// when the step is not skipped, so the bias corrections stay torch's after a GradScaler overflow.
+#define AVS_ADAM_MAX_GROUPS 8
+struct AdamGroups {
+  float lr[AVS_ADAM_MAX_GROUPS];
+  float wd[AVS_ADAM_MAX_GROUPS];
+};
+struct AdamTick {
+  int step;
+  float bc1, bc2_sqrt;
+};
+
+__global__ void adam_tick_kernel(AdamTick* __restrict__ tick, const float* __restrict__ found_inf, float beta1,
+                                 float beta2) {
+  if (found_inf != nullptr && *found_inf != 0.f) return;
+  const int step = tick->step + 1;
+  tick->step = step;
+  tick->bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  tick->bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+}
+
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v,
-                                                   bf16* __restrict__ shadow, long long n, float lr, float beta1,
-                                                   float beta2, float eps, float wd, float bc1, float bc2_sqrt,
-                                                   int decoupled, const float* __restrict__ inv_scale,
+                                                   bf16* __restrict__ shadow, long long n, AdamGroups groups,
+                                                   float beta1, float beta2, float eps, float bc1_host,
+                                                   float bc2_sqrt_host, int decoupled,
+                                                   const float* __restrict__ inv_scale,
                                                    const float* __restrict__ found_inf,
-                                                   const uint8_t* __restrict__ active) {
+                                                   const uint8_t* __restrict__ active,
+                                                   const AdamTick* __restrict__ tick) {
   if (found_inf != nullptr && *found_inf != 0.f) return;
   const float gs = inv_scale ? *inv_scale : 1.0f;
+  const float bc1 = tick ? tick->bc1 : bc1_host, bc2_sqrt = tick ? tick->bc2_sqrt : bc2_sqrt_host;
   const long long n4 = n / 4;
-  const float step_size = lr / bc1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    if (active != nullptr && active[i >> 4] == 0) continue;  // parameter received no gradient: Adam skips it
+    int grp = 0;
+    if (active != nullptr) {
+      const int a = active[i >> 4];
+      if (a == 0) continue;  // parameter received no gradient / is not the optimizer's: Adam skips it
+      grp = min(a - 1, AVS_ADAM_MAX_GROUPS - 1);
+    }
+    const float lr = groups.lr[grp], wd = groups.wd[grp];
+    const float step_size = lr / bc1;
     float4 pp = reinterpret_cast<float4*>(p)[i];
     const float4 gg = reinterpret_cast<const float4*>(g)[i];
     float4 mm = reinterpret_cast<float4*>(m)[i];
@@ -51,21 +83,43 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+extern "C" int avs_adam_step_groups(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n,
+                                    const float* lr, const float* weight_decay, int n_groups, float beta1, float beta2,
+                                    float eps, int step, int decoupled, const float* inv_scale, const float* found_inf,
+                                    const uint8_t* group_chunks, void* tick_state, void* stream) {
+  AVS_REQUIRE(p && g && m && v && lr && weight_decay, "avs_adam_step: null pointer");
+  AVS_REQUIRE(n % 4 == 0, "avs_adam_step: n must be a multiple of 4 (pad the arena)");
+  AVS_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "avs_adam_step: 16-byte alignment");
+  AVS_REQUIRE(n_groups >= 1 && n_groups <= AVS_ADAM_MAX_GROUPS, "avs_adam_step: 1..%d parameter groups", AVS_ADAM_MAX_GROUPS);
+  AVS_REQUIRE(n_groups == 1 || group_chunks, "avs_adam_step: several groups need the per-chunk group map");
+  AVS_REQUIRE(tick_state != nullptr || step >= 1, "avs_adam_step: step must be >= 1");
+  if (n == 0) return 0;
+  AdamGroups groups;
+  for (int i = 0; i < AVS_ADAM_MAX_GROUPS; ++i) {
+    groups.lr[i] = lr[min(i, n_groups - 1)];
+    groups.wd[i] = weight_decay[min(i, n_groups - 1)];
+  }
+  float bc1 = 1.f, bc2s = 1.f;
+  if (tick_state != nullptr) {
+    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((AdamTick*)tick_state, found_inf, beta1, beta2);
+    if (int rc = avs_check_launch("adam_tick_kernel")) return rc;
+  } else {
+    bc1 = (float)(1.0 - pow((double)beta1, step));
+    bc2s = (float)sqrt(1.0 - pow((double)beta2, step));
+  }
+  const int blocks = (int)min((long long)avs_num_sms() * 16, ceil_div_ll(n / 4, 256));
+  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)shadow_bf16, n, groups, beta1, beta2, eps, bc1,
+                                                        bc2s, decoupled, inv_scale, found_inf, group_chunks,
+                                                        (const AdamTick*)tick_state);
+  return avs_check_launch("adam_kernel");
+}
+
 extern "C" int avs_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr,
                              float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
                              const float* inv_scale, const float* found_inf, const uint8_t* active_chunks,
                              void* stream) {
-  AVS_REQUIRE(p && g && m && v, "avs_adam_step: null pointer");
-  AVS_REQUIRE(n % 4 == 0, "avs_adam_step: n must be a multiple of 4 (pad the arena)");
-  AVS_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "avs_adam_step: 16-byte alignment");
-  AVS_REQUIRE(step >= 1, "avs_adam_step: step must be >= 1");
-  if (n == 0) return 0;
-  const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
-  const int blocks = (int)min((long long)avs_num_sms() * 16, ceil_div_ll(n / 4, 256));
-  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)shadow_bf16, n, lr, beta1, beta2, eps,
-                                                        weight_decay, (float)bc1, (float)sqrt(bc2), decoupled,
-                                                        inv_scale, found_inf, active_chunks);
-  return avs_check_launch("adam_kernel");
+  return avs_adam_step_groups(p, g, m, v, shadow_bf16, n, &lr, &weight_decay, 1, beta1, beta2, eps, step, decoupled,
+                              inv_scale, found_inf, active_chunks, nullptr, stream);
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {

@@ -102,6 +102,22 @@ def mask_argsort(noise: torch.Tensor, len_keep: int):
     return ids_shuffle, ids_restore, mask
 
 
+def mask_force_noise(noise: torch.Tensor, f: int, t: int, cols: Optional[torch.Tensor], rows: Optional[torch.Tensor],
+                     value: float = 1.1) -> None:
+    """In place: noise[n].view(f, t)[:, cols[n]] = value; noise[n].view(f, t)[rows[n], :] = value  (cav_mae_base.py:404-423)."""
+    _chk(noise, F32, "mask_force_noise.noise")
+    N, L = noise.shape
+    if L != f * t:
+        raise RuntimeError(f"mask_force_noise: L={L} != f*t={f}*{t}")
+    kt = kf = 0
+    if cols is not None and cols.numel():
+        _chk(cols, I32, "mask_force_noise.cols"); kt = cols.shape[1]
+    if rows is not None and rows.numel():
+        _chk(rows, I32, "mask_force_noise.rows"); kf = rows.shape[1]
+    _lib.check(_lib.lib().avs_mask_force_noise(noise.data_ptr(), N, f, t, _p(cols) if kt else None, kt,
+                                               _p(rows) if kf else None, kf, value, _stream()), "avs_mask_force_noise")
+
+
 def mask_from_ids(ids_shuffle: torch.Tensor, len_keep: int):
     """ids_restore / mask for SUPPLIED ids_shuffle (int32 [N,L]): sorting the ranks 0..L-1 placed at their
     source index reproduces ids_shuffle exactly, so the same kernel serves both entry points."""
@@ -318,7 +334,10 @@ def infonce_bwd(N, D, temperature, bidirect, weight, upstream, workspace, row0, 
 
 # --------------------------------------------------------------------------------------------- optimizer plumbing
 def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, decoupled=False, inv_scale=None,
-              found_inf=None, active=None):
+              found_inf=None, active=None, tick=None):
+    """One fused Adam launch over a flat fp32 buffer. `lr` / `weight_decay`: floats, or equally long sequences — one
+    entry per param_group, in which case `active` is the per-chunk group map (0 = skip, k = group k-1). `tick`: 16-byte
+    device buffer holding the step counter and bias corrections (advances only when `found_inf` is clear)."""
     for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
         _chk(t, F32, "adam." + n)
     if shadow is not None:
@@ -327,9 +346,17 @@ def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, dec
         _chk(active, torch.uint8, "adam.active")
         if active.numel() * 64 < p.numel():
             raise RuntimeError("adam.active: one byte per 64 parameters required")
-    _lib.check(_lib.lib().avs_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(shadow), p.numel(),
-                                        lr, beta1, beta2, eps, weight_decay, step, int(decoupled), _p(inv_scale),
-                                        _p(found_inf), _p(active), _stream()), "avs_adam_step")
+    lrs = [float(x) for x in lr] if isinstance(lr, (list, tuple)) else [float(lr)]
+    wds = [float(x) for x in weight_decay] if isinstance(weight_decay, (list, tuple)) else [float(weight_decay)] * len(lrs)
+    if len(wds) != len(lrs):
+        raise RuntimeError("adam: lr and weight_decay need one entry per group")
+    if tick is not None and (tick.numel() * tick.element_size() < 16 or not tick.is_cuda):
+        raise RuntimeError("adam.tick: 16 device bytes required")
+    arr = ctypes.c_float * len(lrs)
+    _lib.check(_lib.lib().avs_adam_step_groups(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(shadow),
+                                               p.numel(), arr(*lrs), arr(*wds), len(lrs), beta1, beta2, eps, int(step),
+                                               int(decoupled), _p(inv_scale), _p(found_inf), _p(active), _p(tick),
+                                               _stream()), "avs_adam_step_groups")
 
 
 def cast_f32_to_bf16(src, dst):
@@ -449,7 +476,23 @@ layernorm_bwd = _instrument("layernorm_bwd", layernorm_bwd,
                             lambda dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, **k:
                             (8.0 if k.get("resid") is not None else 6.0) * M * D)
 colsum = _instrument("colsum", colsum, lambda dy, out, M, N, alpha=1.0: 2.0 * M * N)
-adam_step = _instrument("adam", adam_step, lambda p, g, m, v, shadow, *a, **k: 28.0 * p.numel() + (2.0 * p.numel() if shadow is not None else 0.0))
+_ACTIVE_ELEMS = {}   # (data_ptr, numel) of an activity bitmap -> parameters it marks active (timing aid only)
+
+
+def _work_adam(p, g, m, v, shadow, *a, **k):
+    """Algorithmic bytes of one Adam launch: 28 B (+2 B bf16 shadow) per ACTIVE parameter — chunks whose bitmap byte is
+    0 are skipped without touching p / g / m / v (the inactive `ast_base` copy in the single-pass arrangement)."""
+    active = k.get("active", a[9] if len(a) > 9 else None)
+    n = p.numel()
+    if active is not None:
+        key = (active.data_ptr(), active.numel())
+        if key not in _ACTIVE_ELEMS:
+            _ACTIVE_ELEMS[key] = int((active != 0).sum()) * 64
+        n = min(n, _ACTIVE_ELEMS[key])
+    return (28.0 + (2.0 if shadow is not None else 0.0)) * n
+
+
+adam_step = _instrument("adam", adam_step, _work_adam)
 cast_f32_to_bf16 = _instrument("cast", cast_f32_to_bf16, lambda src, dst: 6.0 * src.numel())
 patchify_audio = _instrument("patchify", patchify_audio, lambda audio, ids, keep, patch, out, sample_idx=None: 3.0 * out.numel())
 patchify_video = _instrument("patchify", patchify_video, lambda img, ids, keep, patch, out, sample_idx=None: 3.0 * out.numel())

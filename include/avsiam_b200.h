@@ -69,6 +69,11 @@ int avs_gemm_bf16(const void* A, long long lda, int a_major, const void* B, long
  * ---------------------------------------------------------------------------------------------- */
 int avs_mask_argsort(const float* noise, int N, int L, int len_keep, int32_t* ids_shuffle, int32_t* ids_restore,
                      float* mask, void* stream);
+/* Structured-mask pattern (cav_mae_base.py:404-423, modes 'time' / 'freq' / 'tf'): noise[n, :, cols[n,j]] = value and
+ * noise[n, rows[n,j], :] = value on the [f, t] patch grid; cols int32 [N,kt], rows int32 [N,kf] are the host's
+ * random.sample draws (NULL when the count is 0). Followed by avs_mask_argsort. */
+int avs_mask_force_noise(float* noise, int N, int f, int t, const int32_t* cols, int kt, const int32_t* rows, int kf,
+                         float value, void* stream);
 /* out[n,i,:] = x[n, ids[n,i], :], i < keep; byte-exact (replaces torch.gather at cav_mae_base.py:382,431). */
 int avs_gather_rows(const void* x, const int32_t* ids, void* out, int N, int L, int keep, int ids_ld, int row_bytes,
                     void* stream);
@@ -251,6 +256,17 @@ int avs_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf1
                   const uint8_t* active_chunks /* or NULL: one byte per 64 elements, 0 = parameter had no gradient
                                                   (torch.optim.Adam skips grad-None parameters) */,
                   void* stream);
+/* Same step with torch's param_groups (traintest_ft_base.py:78-83 builds three: base lr, lr*head_lr, lr*mm_lr):
+ * group_chunks[c] = 0 -> chunk skipped, k > 0 -> chunk belongs to group k-1 and is stepped with lr[k-1] /
+ * weight_decay[k-1] (host arrays of n_groups <= 8 entries). tick_state (optional, 16 device bytes
+ * {int step; float bc1; float bc2_sqrt}, zero-initialised by the caller): the step counter is kept on the device and
+ * advances only when found_inf is clear, so a GradScaler-skipped step leaves the bias corrections where torch's
+ * per-parameter counters leave them; `step` is then ignored. */
+int avs_adam_step_groups(float* p, const float* g, float* m, float* v, void* shadow_bf16 /* or NULL */, long long n,
+                         const float* lr, const float* weight_decay, int n_groups, float beta1, float beta2, float eps,
+                         int step, int decoupled, const float* inv_scale /* or NULL */,
+                         const float* found_inf /* or NULL */, const uint8_t* group_chunks /* or NULL */,
+                         void* tick_state /* or NULL */, void* stream);
 int avs_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 int avs_colsum_bf16(const void* dy, long long ld, float* out_accum, int M, int N, float alpha, void* stream);
 int avs_found_inf(const float* g, long long n, float* flag, void* stream);

@@ -220,8 +220,20 @@ def mlp(x, sd: State, pfx: str):
     return F.linear(h, sd[pfx + "fc2.weight"], sd[pfx + "fc2.bias"])
 
 
+CHECKPOINT_BLOCKS = False   # True: recompute each block in backward (same arithmetic; lets the fp32 oracle run the
+#                             benchmark's B = 256 on one GPU as the checker — the S x S attention matrices of the
+#                             decoder alone are 8 GB per block in fp32)
+
+
 def block(x, sd: State, pfx: str, heads: int, modality: Optional[str]):
     """Block.forward, cav_mae_base.py:149-193: pre-LN, LayerNorm set chosen by modality in {None,'a','v'}."""
+    if CHECKPOINT_BLOCKS and torch.is_grad_enabled():
+        from torch.utils.checkpoint import checkpoint
+        return checkpoint(_block, x, sd, pfx, heads, modality, use_reentrant=False)
+    return _block(x, sd, pfx, heads, modality)
+
+
+def _block(x, sd: State, pfx: str, heads: int, modality: Optional[str]):
     sfx = "" if modality is None else "_" + modality
     x = x + attention(layer_norm(x, sd[f"{pfx}norm1{sfx}.weight"], sd[f"{pfx}norm1{sfx}.bias"], LN_EPS_BLOCK), sd,
                       pfx + "attn.", heads)
@@ -243,7 +255,7 @@ def apply_masking(x: torch.Tensor, ids_shuffle: torch.Tensor, len_keep: int):
     ids_restore = torch.argsort(ids_shuffle, dim=1)
     ids_keep = ids_shuffle[:, :len_keep]
     x_masked = torch.gather(x, 1, ids_keep.unsqueeze(-1).expand(-1, -1, D))
-    mask = torch.ones(N, L, dtype=x.dtype)
+    mask = torch.ones(N, L, dtype=x.dtype, device=x.device)
     mask[:, :len_keep] = 0
     mask = torch.gather(mask, 1, ids_restore)
     return x_masked, mask, ids_restore
@@ -282,6 +294,11 @@ class MaskPlan:
     perm_v: Optional[torch.Tensor] = None               # [B] :537
     chunk_ids_a: List[torch.Tensor] = field(default_factory=list)  # 5 x [n_i, Ta]  (:546)
     chunk_ids_v: List[torch.Tensor] = field(default_factory=list)  # 5 x [n_i, Tv]  (:549)
+
+    def to(self, device) -> "MaskPlan":
+        mv = lambda t: None if t is None else t.to(device)
+        return MaskPlan(mv(self.ids_shuffle_a), mv(self.ids_shuffle_v), mv(self.perm_a), mv(self.perm_v),
+                        [t.to(device) for t in self.chunk_ids_a], [t.to(device) for t in self.chunk_ids_v])
 
 
 N_CHUNKS = 5  # cav_mae_base.py:534,538
@@ -366,8 +383,8 @@ def forward_encoder_mmixed(audio, imgs, sd: State, d: Dims, plan: MaskPlan):
                       .mean(dim=1, keepdim=True))
     cv = torch.cat(outs_v, 0)
     ca = torch.cat(outs_a, 0)
-    inv_a = torch.empty_like(plan.perm_a); inv_a[plan.perm_a] = torch.arange(B)   # :584-586
-    inv_v = torch.empty_like(plan.perm_v); inv_v[plan.perm_v] = torch.arange(B)
+    inv_a = torch.empty_like(plan.perm_a); inv_a[plan.perm_a] = torch.arange(B, device=plan.perm_a.device)   # :584-586
+    inv_v = torch.empty_like(plan.perm_v); inv_v[plan.perm_v] = torch.arange(B, device=plan.perm_v.device)
     return ca[inv_a], cv[inv_v]
 
 
@@ -418,7 +435,7 @@ def contrastive(audio_rep, video_rep, bidirect: bool = True):
     v = F.normalize(video_rep, dim=-1)
     total = a @ v.t() / 0.05
     n = total.shape[0]
-    ar = torch.arange(n)
+    ar = torch.arange(n, device=total.device)
     nce_1 = -torch.mean(torch.diag(F.log_softmax(total, dim=0)))
     acc_1 = (torch.argmax(total, dim=0) == ar).sum() / n
     if not bidirect:
@@ -432,7 +449,7 @@ def forward(audio, imgs, sd: State, d: Dims, plan: MaskPlan, mae_loss_weight=1.0
             gather=None):
     """CAVMAE_BASE.forward, cav_mae_base.py:685-741 (two-pass arrangement). `gather(x)->x_global` stands in for
     GatherLayer (gather_layer.py:21-37); None = world size 1."""
-    zero = torch.tensor(0.0)
+    zero = torch.tensor(0.0, device=audio.device)
     mask_a = mask_v = None
     if mae_loss_weight != 0:
         x, mask_a, ira, mask_v, irv, _, _ = forward_encoder(audio, imgs, sd, d, plan, 0.75, 0.75)  # :696 hard-coded
@@ -470,7 +487,7 @@ def forward_single_pass(audio, imgs, sd: State, d: Dims, plan: MaskPlan, mae_los
         a = block(a, sd, f"vit_base.blocks.{i}.", d.heads, "a")
     cv = layer_norm(v, sd["vit_base.norm.weight"], sd["vit_base.norm.bias"], LN_EPS_FINAL)
     ca = layer_norm(a, sd["vit_base.norm_a.weight"], sd["vit_base.norm_a.bias"], LN_EPS_FINAL)
-    zero = torch.tensor(0.0)
+    zero = torch.tensor(0.0, device=audio.device)
     if mae_loss_weight != 0:
         x = torch.cat((ca, cv), 1)
         x = block(x, sd, "mm_layer_1.", d.heads, "a")

@@ -113,6 +113,52 @@ def test_gather_rows_bit_exact_and_golden(golden_dir):
     assert ops.gather_rows(xb, idb, 0).shape == (9, 0, 768)  # empty keep
 
 
+def test_structured_masking_against_reference_golden(golden_dir):
+    """random_masking_structured, modes 'time' / 'freq' / 'tf' (cav_mae_base.py:392-439): same random.seed, same noise
+    as the UNMODIFIED reference method (tests/golden/masking_structured.pt, oracle/make_golden_masking.py).
+    Bit-exact: everything the sort determines. When more tokens are forced to 1.1 than are removed ('order_free'), the
+    reference keeps a few forced tokens picked by torch.argsort's unspecified tie order; there the un-forced part of
+    the result (kept rows, their order, mask, ranks) is still bit-exact and the number of forced survivors equal."""
+    import dataclasses
+    import random
+    from avsiam_b200 import CAVMAE_BASE, Dims
+    cases = torch.load(os.path.join(golden_dir, "masking_structured.pt"), weights_only=False)
+    models = {}
+    for c in cases:
+        t, f, N = c["t"], c["f"], c["N"]
+        L = t * f
+        if (t, f) not in models:
+            d = dataclasses.replace(O.TINY, audio_len=16 * t, mel=16 * f)
+            models[(t, f)] = CAVMAE_BASE(dims=Dims(**dataclasses.asdict(d)))
+        model = models[(t, f)]
+        random.seed(c["seed"])
+        ids, ids_restore, mask, keep = model._structured_ids(N, L, c["ratio"], torch.device(DEV), mode=c["mode"],
+                                                             noise=c["noise"])
+        assert keep == c["x_masked"].shape[1]
+        xm = ops.gather_rows(c["x"].to(DEV), ids, keep).cpu()
+        mask, ids_restore = mask.cpu(), ids_restore.cpu().long()
+        n_forced = c["n_forced"]
+        if not c["order_free"]:
+            assert torch.equal(xm, c["x_masked"]) and torch.equal(mask, c["mask"]), (c["mode"], c["ratio"])
+        for i in range(N):
+            free = L - int(n_forced[i])                      # tokens with their own random noise: ranks 0 .. free-1
+            k_free = min(keep, free)
+            assert torch.equal(xm[i, :k_free], c["x_masked"][i, :k_free])
+            unforced = c["ids_restore"][i] < free
+            assert torch.equal(ids_restore[i] < free, unforced)   # the same columns / rows were forced
+            assert torch.equal(ids_restore[i][unforced], c["ids_restore"][i][unforced])
+            assert torch.equal(mask[i][unforced], c["mask"][i][unforced])
+            assert float(mask[i].sum()) == float(c["mask"][i].sum()) == L - keep
+
+
+def test_structured_masking_rejects_unknown_mode():
+    import dataclasses
+    from avsiam_b200 import CAVMAE_BASE, Dims
+    model = CAVMAE_BASE(dims=Dims(**dataclasses.asdict(O.TINY)))
+    with pytest.raises(ValueError):
+        model._structured_ids(2, O.TINY.Ta, 0.5, torch.device(DEV), mode="diagonal")
+
+
 def test_patchify_matches_patch_embed_order():
     d = O.VIT_B
     B = 3

@@ -1,8 +1,11 @@
 """Whole-path parity (B200): the drop-in CAVMAE_BASE running on libavsiam_b200.so against
   (1) the golden fixtures recorded from the UNMODIFIED reference model file (tests/golden, ViT-B/16), and
   (2) the CPU oracle executed live on identical weights, inputs and supplied mask indices.
-Tolerances are BASELINE.json's: masks bit-exact; losses 2e-2 relative (bf16 mode); per-parameter gradient
-cosine >= 0.999."""
+Tolerances: masks bit-exact; losses 1e-3 relative — BASELINE.json allows 2e-2 in bf16 mode and asks 1e-3 of an fp32
+mode; the bf16-operand / fp32-accumulate path measures 4e-5 ... 2.2e-4 (profiles/r01_loss_parity.log), so the fp32-mode
+bound is what is asserted; per-parameter gradient cosine >= 0.999.
+The benchmarked configuration itself (ViT-B/16, B = 256 per GPU, single_pass; two_pass at B = 64) is checked against
+the same oracle executed in fp32 ON THE GPU (it is plain torch; blocks are recomputed in backward to bound memory)."""
 import dataclasses
 import os
 
@@ -20,7 +23,7 @@ from oracle import avsiam_oracle as O  # noqa: E402
 from oracle.make_golden import synth_inputs  # noqa: E402
 
 DEV = "cuda"
-LOSS_RTOL_BF16 = 2e-2      # BASELINE.json north_star: "within 2e-2 in bf16"
+LOSS_RTOL_BF16 = 1e-3      # BASELINE.json north_star: 2e-2 in bf16 mode, 1e-3 in fp32 mode — the tighter one is asserted
 GRAD_COS_MIN = 0.999       # "per-parameter gradients match at cosine >= 0.999"
 
 
@@ -76,7 +79,7 @@ def test_vitb_against_reference_golden(vitb, golden_cases, idx):
     bad = []
     for k in want:
         n = float(named[k].grad.double().norm())
-        if abs(n - c["grad_norm"][k]) > 0.06 * c["grad_norm"][k] + 1e-6:
+        if abs(n - c["grad_norm"][k]) > 0.03 * c["grad_norm"][k] + 1e-6:
             bad.append((k, n, c["grad_norm"][k]))
     assert not bad, bad[:8]
 
@@ -188,7 +191,20 @@ def test_fused_adam_step_matches_oracle_adam():
     out[0].backward()
     opt.step()
     named = dict(model.named_parameters())
-    # Adam's first step moves every touched weight by ~lr*sign(g): compare the update direction
+    sd = {k: v for k, v in sd.items()}
+    # (1) exact: the fused launch == torch.optim.Adam applied to the SAME gradients (the arena's), parameter by parameter
+    arena = model.arena
+    used = model._used_cache[("single_pass", True, True)][0]
+    for k in used:
+        p0 = sd[k].clone()
+        g = arena.grad(k).detach().cpu().clone()
+        m, v = torch.zeros_like(p0), torch.zeros_like(p0)
+        O.adam_step(p0, g, m, v, 1)
+        assert torch.allclose(named[k].detach().cpu(), p0, rtol=0, atol=2e-7 + 1e-6 * float(p0.abs().max())), k
+    for k, p in named.items():      # parameters without gradient are untouched (no weight decay, no moments)
+        if k not in used:
+            assert torch.equal(p.detach().cpu(), sd[k]), k
+    # (2) against the oracle's own Adam step: the update direction on the well-conditioned entries
     worst = 1.0
     for k, v in state.items():
         if v.grad is None or float(v.grad.abs().max()) < 1e-7:
@@ -241,3 +257,195 @@ def test_wide_geometry_against_oracle():
     low = [(k, cos(named[k].grad, state[k].grad)) for k in want if float(state[k].grad.norm()) > 1e-9]
     low = [(k, c) for k, c in low if c < GRAD_COS_MIN]
     assert not low, low[:8]
+
+
+# ------------------------------------------------------------------------------------------------ benchmarked config
+def run_oracle_gpu(fn, audio, imgs, sd, d, plan, **kw):
+    """The fp32 oracle on the GPU (true fp32: TF32 off), every block recomputed in backward."""
+    assert not torch.backends.cuda.matmul.allow_tf32
+    state = {k: v.to(DEV).requires_grad_(True) for k, v in sd.items() if not k.startswith("my_blocks.")}
+    O.CHECKPOINT_BLOCKS = True
+    try:
+        out = fn(audio.to(DEV), imgs.to(DEV), state, d, plan.to(DEV), **kw)
+        out[0].backward()
+    finally:
+        O.CHECKPOINT_BLOCKS = False
+    return out, state
+
+
+@pytest.mark.parametrize("arrangement,B", [("single_pass", 256), ("two_pass", 64)])
+def test_vitb_benchmark_config_against_fp32_oracle_on_gpu(arrangement, B):
+    """bench.py's workload (BASELINE config 2: ViT-B/16, 256 samples per GPU, 75 % mask, MAE + InfoNCE) — the size at
+    which every GEMM CTA walks many tiles (persistent loop, TMEM double-buffer phases, wave-aware split-K at
+    K = 181 248) — against the fp32 oracle: 5 losses 1e-3, masks bit-exact, EVERY parameter's gradient cosine >= 0.999."""
+    d = O.VIT_B
+    torch.cuda.empty_cache()
+    model, _ = make_model(d, arrangement)
+    sd = O.init_state(d, seed=0, skip_heads=True)
+    audio, imgs = synth_inputs(B, d, 71)
+    plan = O.make_mask_plan(B, d, 72, two_pass=(arrangement == "two_pass"))
+    fn = O.forward if arrangement == "two_pass" else O.forward_single_pass
+    ref, state = run_oracle_gpu(fn, audio, imgs, sd, d, plan, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+    ref_vals = [float(r) for r in ref[:5]]
+    ref_masks = (ref[5].cpu(), ref[6].cpu())
+    ref_acc = float(ref[7])
+    ref_grads = {k: v.grad.detach().cpu() for k, v in state.items() if v.grad is not None}
+    del ref, state
+    torch.cuda.empty_cache()
+    model.mask_plan = plan
+    out = model(audio.to(DEV), imgs.to(DEV), 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+    check_losses(out, ref_vals)
+    assert float(out[7]) == pytest.approx(ref_acc, abs=2.0 / B)     # an argmax can flip only on a near-tie
+    assert torch.equal(out[5].cpu(), ref_masks[0]) and torch.equal(out[6].cpu(), ref_masks[1])
+    out[0].backward()
+    named = dict(model.named_parameters())
+    got = {k for k, p in named.items() if p.grad is not None}
+    assert got == set(ref_grads), (sorted(got - set(ref_grads))[:5], sorted(set(ref_grads) - got)[:5])
+    cosines = {k: cos(named[k].grad, g) for k, g in ref_grads.items() if float(g.norm()) > 1e-12}
+    low = sorted((c, k) for k, c in cosines.items() if c < GRAD_COS_MIN)
+    print(f"[parity B={B} {arrangement}] losses {[float(o) for o in out[:5]]} vs {ref_vals}; "
+          f"worst gradient cosine {min(cosines.values()):.6f} over {len(cosines)} parameters")
+    assert not low, low[:8]
+    del model, out
+    torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------------------------ train-step body
+def _tiny_step_setup(seed=9, B=4, direct=True):
+    d = O.TINY
+    model, sd = make_model(d, "single_pass")
+    model.direct_grads = direct
+    audio, imgs = synth_inputs(B, d, seed)
+    model.mask_plan = O.make_mask_plan(B, d, seed + 1, two_pass=False)
+    return model, sd, audio.to(DEV), imgs.to(DEV)
+
+
+def test_grad_scaler_protocol_matches_unscaled_step_and_skips_on_overflow():
+    """The reference's mixed-precision protocol (traintest_cavmae_base.py:83-84,137-140): scaler.scale(loss).backward()
+    -> scaler.step(optimizer) -> scaler.update(). The loss scale is a power of two, so the scaled route must land on the
+    unscaled route's weights; an overflow must skip the step (weights, moments AND the bias-correction step count
+    untouched) and halve the scale."""
+    adam_kw = dict(lr=2e-4, weight_decay=5e-7, betas=(0.95, 0.999))
+    ref_model, _, audio, imgs = _tiny_step_setup()
+    ref_opt = FusedAdam(ref_model.parameters(), **adam_kw)
+    for _ in range(2):
+        out = ref_model(audio, imgs, 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+        ref_opt.zero_grad()
+        out[0].backward()
+        ref_opt.step()
+    model, sd, audio, imgs = _tiny_step_setup()
+    opt = FusedAdam(model.parameters(), **adam_kw)
+    scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 12)
+    losses = []
+    for it in range(3):
+        with torch.autocast("cuda", dtype=torch.float16):       # `with autocast():` at :131 — a no-op for this module
+            out = model(audio, imgs, 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+        opt.zero_grad()
+        scaler.scale(out[0]).backward()
+        if it == 1:                                             # overflow in the second iteration
+            before = model.arena.flat.clone()
+            m_before = opt._m.clone()
+            model.arena.grads[5] = float("inf")
+        scaler.step(opt)
+        scale_before = scaler.get_scale()
+        scaler.update()
+        if it == 1:
+            assert torch.equal(model.arena.flat, before) and torch.equal(opt._m, m_before)
+            assert scaler.get_scale() == scale_before * 0.5
+            assert opt.steps_taken() == 1
+        losses.append(float(out[0]))
+    assert opt.steps_taken() == 2
+    a, b = model.arena.flat[:model.arena.n_hot], ref_model.arena.flat[:ref_model.arena.n_hot]
+    # identical up to the rounding of bf16 activations' gradients under a power-of-two scale (exact unless a value
+    # crosses the bf16 subnormal range) and the fp32 1/scale multiply
+    assert float((a - b).abs().max()) <= 2e-6 + 1e-5 * float(b.abs().max()), float((a - b).abs().max())
+
+
+def test_two_optimizer_two_pass_body():
+    """traintest_cavmae_base.py:131-152 literally: contrastive pass -> optimizer, MAE pass -> optimizer2, each Adam with its
+    own moments over the same parameter list; compared with the oracle + two torch.optim.Adam on the same draws."""
+    d = O.TINY
+    B = 5
+    model, sd = make_model(d, "two_pass")
+    model.direct_grads = True
+    adam_kw = dict(lr=2e-4, weight_decay=5e-7, betas=(0.95, 0.999))
+    trainables = [p for p in model.parameters() if p.requires_grad]
+    opt1, opt2 = FusedAdam(trainables, **adam_kw), FusedAdam(trainables, **adam_kw)
+    state = {k: v.clone().requires_grad_(True) for k, v in sd.items() if not k.startswith("my_blocks.")}
+    ref1 = torch.optim.Adam(list(state.values()), **adam_kw)
+    ref2 = torch.optim.Adam(list(state.values()), **adam_kw)
+    audio, imgs = synth_inputs(B, d, 77)
+    for it in range(2):
+        plan = O.make_mask_plan(B, d, 400 + it, two_pass=True)
+        model.mask_plan = plan
+        for (mw, cw, opt, ropt) in ((0, 1, opt1, ref1), (1, 0, opt2, ref2)):
+            out = model(audio.to(DEV), imgs.to(DEV), 0.75, 0.75, mae_loss_weight=mw, contrast_loss_weight=cw)
+            opt.zero_grad()
+            out[0].backward()
+            opt.step()
+            ref = O.forward(audio, imgs, state, d, plan, mae_loss_weight=mw, contrast_loss_weight=cw)
+            ropt.zero_grad(set_to_none=True)
+            ref[0].backward()
+            ropt.step()
+            # the losses of the second iteration are taken on weights both optimizers have already moved
+            assert float(out[0]) == pytest.approx(float(ref[0]), rel=2e-3, abs=1e-4), (it, mw, cw)
+    named = dict(model.named_parameters())
+    moved = 0
+    for k, v in state.items():
+        delta_ref = v.detach() - sd[k]
+        delta = named[k].detach().cpu() - sd[k]
+        if float(delta_ref.abs().max()) == 0:
+            assert float(delta.abs().max()) == 0, k
+            continue
+        moved += 1
+        # Adam steps are ~lr * sign-like: after 2 x 2 steps compare where the reference moved decisively
+        big = delta_ref.abs() > 0.5 * delta_ref.abs().max()
+        assert cos(delta[big], delta_ref[big]) > 0.95, (k, cos(delta[big], delta_ref[big]))
+    assert moved > 50
+
+
+def test_fused_adam_param_groups_and_excluded_parameters():
+    """torch semantics of param_groups (traintest_ft_base.py:78-83: three groups with their own lr) and of parameters
+    left out of the optimizer (freeze_base): per-group lr / weight_decay, no update and no decay outside the groups."""
+    model, sd, audio, imgs = _tiny_step_setup(direct=False)
+    named = dict(model.named_parameters())
+    heads = [p for k, p in named.items() if k.startswith("decoder_")]
+    fusion = [p for k, p in named.items() if k.startswith("mm_layer_")]
+    base = [p for k, p in named.items() if k.startswith("vit_base.blocks.")]
+    groups = [{"params": base, "lr": 1e-4}, {"params": heads, "lr": 1e-2, "weight_decay": 1e-3},
+              {"params": fusion, "lr": 3e-3}]
+    opt = FusedAdam(groups, lr=5e-5, weight_decay=5e-7, betas=(0.95, 0.999), model=model)
+    out = model(audio, imgs, 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+    opt.zero_grad()
+    out[0].backward()
+    grads = {k: p.grad.detach().clone() for k, p in named.items() if p.grad is not None}
+    before = {k: p.detach().clone() for k, p in named.items()}
+    ref_params = {k: before[k].clone().requires_grad_(True) for k in named}
+    for k, g in grads.items():
+        ref_params[k].grad = g.clone()
+    pick = lambda ps: [ref_params[k] for k, p in named.items() if any(p is q for q in ps)]
+    ref = torch.optim.Adam([{"params": pick(base), "lr": 1e-4}, {"params": pick(heads), "lr": 1e-2, "weight_decay": 1e-3},
+                            {"params": pick(fusion), "lr": 3e-3}], lr=5e-5, weight_decay=5e-7, betas=(0.95, 0.999))
+    ref.step()
+    opt.step()
+    for k, p in named.items():
+        tol = 2e-7 + 2e-6 * float(before[k].abs().max())
+        assert torch.allclose(p.detach(), ref_params[k].detach(), rtol=0, atol=tol), k
+    untouched = [k for k in named if k.startswith("vit_base.patch_embed") or k.startswith("vit_base.norm")]
+    assert untouched and all(torch.equal(named[k].detach(), before[k]) for k in untouched)   # had grads, not in a group
+    # torch.optim.Adam loads our state_dict and vice versa (best_optim_state.pth interchange)
+    sd_f = opt.state_dict()
+    ref.load_state_dict(sd_f)
+    sd_t = ref.state_dict()
+    opt2 = FusedAdam(groups, lr=5e-5, weight_decay=5e-7, betas=(0.95, 0.999), model=model)
+    opt2.load_state_dict(torch.load(_roundtrip(sd_t), map_location="cpu"))
+    assert torch.equal(opt2._m, opt._m) and torch.equal(opt2._v, opt._v) and opt2.steps_taken() == 1
+    assert opt2._m.is_cuda
+
+
+def _roundtrip(obj):
+    import io
+    buf = io.BytesIO()
+    torch.save(obj, buf)
+    buf.seek(0)
+    return buf
