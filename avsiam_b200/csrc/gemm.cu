@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 #include "../../include/avsiam_b200.h"
 #include "common.cuh"
@@ -10,8 +11,19 @@
 
 using namespace avs;
 
+#ifdef AVS_GEMM_DEBUG   // probe / timing builds only: the release library carries no debug switches in its epilogue
 static int g_desc_variant = getenv("AVS_GEMM_DEBUG") ? atoi(getenv("AVS_GEMM_DEBUG")) : 0;
 extern "C" void avs_debug_set_desc_variant(int v) { g_desc_variant = v; }
+#else
+static const int g_desc_variant = 0;
+#endif
+// tuning knobs (documented in INTEGRATION.md): depth of the epilogue's input-tile ring, TMEM load prefetch
+static int g_in_depth = getenv("AVS_GEMM_IN_DEPTH") ? atoi(getenv("AVS_GEMM_IN_DEPTH")) : 3;
+static int g_tmem_prefetch = getenv("AVS_GEMM_TMEM_PREFETCH") ? atoi(getenv("AVS_GEMM_TMEM_PREFETCH")) : 1;
+extern "C" void avs_gemm_set_tuning(int in_depth, int tmem_prefetch) {
+  if (in_depth > 0) g_in_depth = in_depth;
+  if (tmem_prefetch >= 0) g_tmem_prefetch = tmem_prefetch;
+}
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -26,9 +38,61 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
+// TMA descriptor cache: a training step issues the same ~280 GEMMs on the same buffers every iteration (the caching
+// allocator hands back the same addresses), so each (pointer, shape, pitch, box, swizzle) is encoded once and copied
+// afterwards — 128 bytes instead of a driver call, five times per GEMM. avs_reset() drops the cache (call it after
+// freeing / re-laying-out buffers if the process keeps running with different shapes; entries are keyed by value, so
+// a stale entry can never describe a different tensor than the one asked for).
+struct TmapKey {
+  const void* ptr;
+  long long rows, cols, ld;
+  int box_cols, box_rows, swizzle;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols &&
+           box_rows == o.box_rows && swizzle == o.swizzle;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    h ^= (size_t)k.rows * 0xC2B2AE3D27D4EB4Full + (size_t)k.cols * 0x165667B19E3779F9ull + (size_t)k.ld;
+    h ^= ((size_t)k.box_cols << 40) ^ ((size_t)k.box_rows << 20) ^ (size_t)k.swizzle;
+    return h;
+  }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static std::mutex g_tmap_mutex;
+static const size_t TMAP_CACHE_MAX = 1 << 16;
+
+extern "C" void avs_reset(void) {
+  std::lock_guard<std::mutex> lock(g_tmap_mutex);
+  g_tmap_cache.clear();
+}
+
+static int encode_tmap_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld,
+                          int box_cols, int box_rows, CUtensorMapSwizzle swizzle);
+
 // 2-D bf16 row-major tensor [rows, cols] with pitch ld (elements); box = {box_cols (inner), box_rows}, 128B swizzle.
 static int make_tmap_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld,
                         int box_cols, int box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+  const TmapKey key{ptr, rows, cols, ld, box_cols, box_rows, (int)swizzle};
+  {
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *map = it->second;
+      return 0;
+    }
+  }
+  if (int rc = encode_tmap_2d(map, ptr, rows, cols, ld, box_cols, box_rows, swizzle)) return rc;
+  std::lock_guard<std::mutex> lock(g_tmap_mutex);
+  if (g_tmap_cache.size() >= TMAP_CACHE_MAX) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *map);
+  return 0;
+}
+
+static int encode_tmap_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld,
+                          int box_cols, int box_rows, CUtensorMapSwizzle swizzle) {
   auto fn = get_encode_fn();
   AVS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   AVS_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA: base pointer must be 16-byte aligned");
@@ -68,7 +132,12 @@ static int launch_gemm(const GemmMaps& tm, GemmArgs& args, int grid, cudaStream_
     }
     attr_set = true;
   }
-  const int epw = Cfg::epi_bytes_per_warp(args.tma_epi, args.has_in, args.has_aux_out);
+  // the input-tile ring is as deep as leaves the mainloop at least 3 stages
+  int depth = g_in_depth < 2 ? 2 : (g_in_depth > GEMM_MAX_IN_DEPTH ? GEMM_MAX_IN_DEPTH : g_in_depth);
+  while (depth > 2 && Cfg::pick_stages(Cfg::epi_bytes_per_warp(args.tma_epi, args.has_in, args.has_aux_out, depth)) < 3) --depth;
+  args.in_depth = depth;
+  args.tmem_prefetch = g_tmem_prefetch;
+  const int epw = Cfg::epi_bytes_per_warp(args.tma_epi, args.has_in, args.has_aux_out, depth);
   args.stages = Cfg::pick_stages(epw);
   const int smem = Cfg::smem_bytes(args.stages, epw);
   gemm_bf16_kernel<AM, BM, BN><<<grid, GEMM_THREADS, smem, stream>>>(tm.a, tm.b, tm.c, tm.in, tm.aux, args);

@@ -47,8 +47,11 @@ struct GemmArgs {
   long long ldc;
   int split_k;          // >=1; >1 requires EPI_OUT_ATOMIC
   int kb_per_split;     // k-blocks (of 64) per split
-  int desc_variant;     // debug bits: 1 swaps LBO/SBO of MN-major descriptors (probe only), 2 skips the TMA stores (timing)
+  int desc_variant;     // -DAVS_GEMM_DEBUG builds only: 1 swaps LBO/SBO of MN-major descriptors (probe), 2 skips the TMA
+                        // stores, 4 skips the in-stream loads (timing experiments, wrong results); ignored otherwise
   int stages;           // smem ring depth (runtime: whatever fits beside the epilogue staging buffers)
+  int in_depth;         // tma_epi && has_in: depth of each epilogue warp's ring of [32 x 32] input tiles (2..4)
+  int tmem_prefetch;    // 1: the tcgen05.ld of chunk c+1 is issued before chunk c's math (second register buffer)
   int tma_epi;          // 1: bf16 C (and aux_out) leave through TMA stores, resid/aux_in arrive through TMA loads
   int has_in;           // tma_epi: a [M,N] bf16 input tile stream exists (resid or aux_in — never both)
   int has_aux_out;      // tma_epi: the GELU pre-activation is stored as a second output stream
@@ -59,10 +62,16 @@ constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int GEMM_UMMA_K = 16;
 constexpr int GEMM_EPI_WARPS = 8;  // two warps per TMEM lane quarter, each taking half of the tile's columns
-constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp0 TMA, warp1 MMA, warps2-9 epilogue
+// warps 0-7 epilogue (two warpgroups), warp 8 TMA producer, warp 9 MMA issuer, warps 10-11 idle: the producer
+// warpgroup hands its registers to the epilogue warpgroups (setmaxnreg), which hold two 32-column accumulator
+// chunks, the packed outputs and the input tile of a chunk at once.
+constexpr int GEMM_THREADS = 32 * GEMM_EPI_WARPS + 128;
+constexpr int GEMM_WARP_TMA = GEMM_EPI_WARPS, GEMM_WARP_MMA = GEMM_EPI_WARPS + 1;
+constexpr int GEMM_REGS_EPI = 216, GEMM_REGS_PRODUCER = 80;   // 256 x 216 + 128 x 80 = 65536
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_EPI_CHUNK = 32;                 // columns per epilogue chunk (one tcgen05.ld 32x32b.x32)
 constexpr int GEMM_EPI_BUF = 32 * GEMM_EPI_CHUNK * 2;  // one [32 rows x 32 cols] bf16 input staging tile = 2 KB
+constexpr int GEMM_MAX_IN_DEPTH = 4;
 // Output staging tiles are [32 rows x 64 cols] (128-byte rows, SWIZZLE_128B) and leave every SECOND chunk: the TMA
 // unit turns each box row into one L2 write request, so 64-byte rows (the 32-column tiles of v2) made the stores —
 // 2048 row requests per 128x256 tile — the bound of every bf16-output GEMM (ncu: MMA warp polling tmem_empty).
@@ -79,8 +88,9 @@ struct GemmCfg {
   static constexpr int BAR_BYTES = 512;
   // per epilogue warp: [in x2][out][aux_out] staging tiles (only the ones the launch uses).  (Double-buffering the
   // output tiles was measured and bought nothing: the mainloop, not the store latency, bounds these kernels.)
-  static __host__ __device__ int epi_bytes_per_warp(int tma_epi, int has_in, int has_aux_out) {
-    return tma_epi ? GEMM_EPI_BUF * (has_in ? 2 : 0) + GEMM_OUT_BUF * (1 + (has_aux_out ? 1 : 0)) : 0;
+  static __host__ __device__ int epi_bytes_per_warp(int tma_epi, int has_in, int has_aux_out, int in_depth) {
+    // in tiles first (2 KB each, so the output tiles that follow stay 1024-byte aligned for their 128 B swizzle)
+    return tma_epi ? GEMM_EPI_BUF * (has_in ? in_depth : 0) + GEMM_OUT_BUF * (1 + (has_aux_out ? 1 : 0)) : 0;
   }
   static __host__ int pick_stages(int epi_per_warp) {
     int s = (GEMM_SMEM_LIMIT - 1024 - BAR_BYTES - GEMM_EPI_WARPS * epi_per_warp) / STAGE_BYTES;
@@ -134,15 +144,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  const int epi_per_warp = Cfg::epi_bytes_per_warp(args.tma_epi, args.has_in, args.has_aux_out);
+  const int epi_per_warp = Cfg::epi_bytes_per_warp(args.tma_epi, args.has_in, args.has_aux_out, args.in_depth);
   uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + GEMM_EPI_WARPS * epi_per_warp);
   uint64_t* full_bar = bars;                               // [MAX_STAGES]
   uint64_t* empty_bar = bars + GEMM_MAX_STAGES;            // [MAX_STAGES]
   uint64_t* tfull_bar = bars + 2 * GEMM_MAX_STAGES;        // [2]
   uint64_t* tempty_bar = bars + 2 * GEMM_MAX_STAGES + 2;   // [2]
-  uint64_t* in_bar = bars + 2 * GEMM_MAX_STAGES + 4;       // [EPI_WARPS][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_MAX_STAGES + 4 + 2 * GEMM_EPI_WARPS);
+  uint64_t* in_bar = bars + 2 * GEMM_MAX_STAGES + 4;       // [EPI_WARPS][MAX_IN_DEPTH]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_MAX_STAGES + 4 + GEMM_MAX_IN_DEPTH * GEMM_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -152,7 +162,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int total_kb = (args.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   const int num_tiles = m_tiles * n_tiles * args.split_k;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == GEMM_WARP_TMA && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     if (args.tma_epi) {
@@ -161,7 +171,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (args.has_aux_out) tma_prefetch_desc(&tma_aux);
     }
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == GEMM_WARP_MMA && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -170,10 +180,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], GEMM_EPI_WARPS);
     }
-    for (int i = 0; i < 2 * GEMM_EPI_WARPS; ++i) mbar_init(&in_bar[i], 1);
+    for (int i = 0; i < GEMM_MAX_IN_DEPTH * GEMM_EPI_WARPS; ++i) mbar_init(&in_bar[i], 1);
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 0) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -182,7 +192,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp >= GEMM_EPI_WARPS) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(GEMM_REGS_PRODUCER));
+   if (warp == GEMM_WARP_TMA) {
     // ============================ TMA producer ============================
     // The whole warp runs the loop convergently (loop state stays in uniform registers); one elected lane issues.
     int stage = 0;
@@ -223,7 +235,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
+   } else if (warp == GEMM_WARP_MMA) {
     // ============================ MMA issuer ============================
     // One k-block is only 4 MMAs (~512 tensor cycles at BLOCK_N = 256), so the issuing warp's scalar work must stay
     // well below that: the warp runs convergently, every descriptor is a precomputed 64-bit base plus a 16-byte-unit
@@ -232,8 +244,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // K-major: step 16 elements (32 B) inside the 128 B swizzle row; 8-row groups 1024 B apart.
     // MN-major: step 16 reduction rows (2 swizzle atoms = 2048 B); atoms along MN are BLOCK_K*128 B apart (LBO),
     //           8-row K groups 1024 B apart (SBO).
+#ifdef AVS_GEMM_DEBUG
     const uint32_t mn_lbo = (args.desc_variant & 1) ? 1024 : GEMM_BLOCK_K * 128;
     const uint32_t mn_sbo = (args.desc_variant & 1) ? GEMM_BLOCK_K * 128 : 1024;
+#else
+    constexpr uint32_t mn_lbo = GEMM_BLOCK_K * 128, mn_sbo = 1024;
+#endif
     const uint64_t da0 = (A_MAJOR == MAJOR_K) ? make_smem_desc(smem_u32(smem_a), 0, 1024)
                                               : make_smem_desc(smem_u32(smem_a), mn_lbo, mn_sbo);
     const uint64_t db0 = (B_MAJOR == MAJOR_K) ? make_smem_desc(smem_u32(smem_b), 0, 1024)
@@ -273,10 +289,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+   }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(GEMM_REGS_EPI));
     // ============================ epilogue (8 warps) ============================
     // warp w may only touch TMEM lanes 32*(w%4)..+32; the two warps sharing a quarter split the tile's columns.
-    const int ew = warp - 2;
+    const int ew = warp;
     // column sums of the output (the bias gradient of the upstream Linear), accumulated per CTA and tile in shared
     // memory and flushed with one global atomic per column and tile
     __shared__ float s_colsum[256];
@@ -286,37 +304,46 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     const int quarter = warp & 3;
     const int half = ew >> 2;
-    constexpr int CH = BLOCK_N / (2 * GEMM_EPI_CHUNK);  // chunks per warp per tile
+    constexpr int CH = BLOCK_N / (2 * GEMM_EPI_CHUNK);  // chunks per warp per tile (even)
+    static_assert(CH % 2 == 0, "the epilogue walks chunk pairs");
     const GemmEpilogue& ep = args.epi;
-    uint8_t* my_epi = smem_epi + ew * epi_per_warp;
-    uint8_t* in_buf = my_epi;                                        // [2][2 KB] when has_in
-    uint8_t* out_buf = my_epi + (args.has_in ? 2 * GEMM_EPI_BUF : 0);   // 1024-byte aligned (128 B swizzle pattern)
-    uint8_t* aux_buf = out_buf + GEMM_OUT_BUF;
-    uint64_t* my_in_bar = in_bar + 2 * ew;
     const bool tma_epi = args.tma_epi != 0;
     const bool has_in = tma_epi && args.has_in;
+    const int IN_DEPTH = args.in_depth;
+    uint8_t* my_epi = smem_epi + ew * epi_per_warp;
+    uint8_t* in_buf = my_epi;                                              // [IN_DEPTH][2 KB] when has_in
+    uint8_t* out_buf = my_epi + (args.has_in ? IN_DEPTH * GEMM_EPI_BUF : 0);   // 1024-byte aligned (128 B swizzle)
+    uint8_t* aux_buf = out_buf + GEMM_OUT_BUF;
+    uint64_t* my_in_bar = in_bar + GEMM_MAX_IN_DEPTH * ew;
+#ifdef AVS_GEMM_DEBUG
+    const bool dbg_no_in = (args.desc_variant & 4) != 0, dbg_no_store = (args.desc_variant & 2) != 0;
+#else
+    constexpr bool dbg_no_in = false, dbg_no_store = false;
+#endif
 
-    // flat per-warp chunk sequence q = tile_iteration * CH + chunk; `in` tiles are prefetched two chunks ahead
-    const bool dbg_no_in = (args.desc_variant & 4) != 0;   // timing experiment: no in-stream TMA loads (wrong results)
-    auto issue_in = [&](int q) {
+    // flat per-warp chunk sequence q = tile_iteration * CH + chunk; the `in` tiles (residual / dGELU operand) travel
+    // through a ring of IN_DEPTH slots filled IN_DEPTH chunks ahead: chunk q lives in slot q % IN_DEPTH, and the load
+    // of chunk q + IN_DEPTH is issued into the slot chunk q has just been read from.
+    auto issue_in = [&](int qq, int slot) {
       if (dbg_no_in) return;
-      const int t = blockIdx.x + (q / CH) * (int)gridDim.x;
+      const int t = blockIdx.x + (qq / CH) * (int)gridDim.x;
       if (t >= num_tiles) return;
       const int mn = t / args.split_k;
       const int m0 = (mn / n_tiles) * GEMM_BLOCK_M;
       const int n0 = (mn % n_tiles) * BLOCK_N;
-      const int col = n0 + half * (BLOCK_N / 2) + (q % CH) * GEMM_EPI_CHUNK;
-      mbar_arrive_expect_tx(&my_in_bar[q & 1], GEMM_EPI_BUF);
-      tma_load_2d(in_buf + (q & 1) * GEMM_EPI_BUF, &tma_in, &my_in_bar[q & 1], col, m0 + quarter * 32);
+      const int col = n0 + half * (BLOCK_N / 2) + (qq % CH) * GEMM_EPI_CHUNK;
+      mbar_arrive_expect_tx(&my_in_bar[slot], GEMM_EPI_BUF);
+      tma_load_2d(in_buf + slot * GEMM_EPI_BUF, &tma_in, &my_in_bar[slot], col, m0 + quarter * 32);
     };
     if (has_in && lane == 0) {
-      issue_in(0);
-      issue_in(1);
+      for (int i = 0; i < IN_DEPTH; ++i) issue_in(i, i);
     }
 
     int acc = 0;
     uint32_t acc_phase = 0;
     int q = 0;
+    int in_slot = 0;
+    uint32_t in_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int ks = t % args.split_k;
       const int mn = t / args.split_k;
@@ -332,18 +359,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         rowadd_ptr = ep.rowadd + (long long)ri * args.N;
       }
       const bool lead_split = (ks == 0);
-#pragma unroll 1
-      for (int c = 0; c < CH; ++c, ++q) {
+      const uint32_t tile_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * (BLOCK_N / 2));
+
+      // one 32-column chunk: registers r (raw accumulator bits) -> bias / activation / residual -> staging / global
+      auto process = [&](uint32_t (&r)[32], const int c) {
         const int ccol = half * (BLOCK_N / 2) + c * GEMM_EPI_CHUNK;  // column offset inside the tile
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + ccol);
-        tmem_ld_32x32b_x32(taddr, r);
-        tmem_ld_wait();
-        if (c == CH - 1) {  // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
         const int nc = n0 + ccol;
         const bool col_ok = nc < args.N;
         const bool full = (nc + 32 <= args.N);
@@ -394,12 +414,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
           uint4 in4[4];
           if (has_in) {
-            if (!dbg_no_in) mbar_wait(&my_in_bar[q & 1], (uint32_t)((q >> 1) & 1));
+            if (!dbg_no_in) mbar_wait(&my_in_bar[in_slot], in_phase);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              in4[j] = *reinterpret_cast<const uint4*>(in_buf + (q & 1) * GEMM_EPI_BUF + epi_tile_off(lane, j));
-            __syncwarp();                     // every lane has read its row: the tile may be refilled
-            if (lane == 0) issue_in(q + 2);
+              in4[j] = *reinterpret_cast<const uint4*>(in_buf + in_slot * GEMM_EPI_BUF + epi_tile_off(lane, j));
+            __syncwarp();                     // every lane has read its row: the slot may be refilled
+            if (lane == 0) issue_in(q + IN_DEPTH, in_slot);
+            if (++in_slot == IN_DEPTH) {
+              in_slot = 0;
+              in_phase ^= 1;
+            }
           }
           if (ep.flags & EPI_DGELU) {
 #pragma unroll
@@ -454,7 +478,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             __syncwarp();
             if (lane == 0) {
               const int nc0 = nc - GEMM_EPI_CHUNK;   // first column of the pair
-              if (nc0 < args.N && m0 + quarter * 32 < args.M && !(args.desc_variant & 2)) {  // TMA clips the M / N tails (bit 1: timing experiment, no stores)
+              if (nc0 < args.N && m0 + quarter * 32 < args.M && !dbg_no_store) {  // TMA clips the M / N tails
                 tma_store_2d(&tma_c, out_buf, nc0, m0 + quarter * 32);
                 if (args.has_aux_out) tma_store_2d(&tma_aux, aux_buf, nc0, m0 + quarter * 32);
               }
@@ -479,6 +503,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
         }
+        ++q;
+      };
+
+      // The accumulator is read in chunk pairs through two register buffers: with tmem_prefetch the tcgen05.ld of the
+      // next chunk is in flight while the current chunk's math runs (the ld latency, ~130+ cycles alone and more under
+      // the MMA's TMEM traffic, leaves the dependency chain of a warp that shares its scheduler with one other warp).
+      uint32_t ra[32], rb[32];
+      const bool pf = args.tmem_prefetch != 0;
+      tmem_ld_32x32b_x32(tile_taddr, ra);
+#pragma unroll 1
+      for (int c = 0; c < CH; c += 2) {
+        tmem_ld_wait();
+        if (pf) tmem_ld_32x32b_x32(tile_taddr + (uint32_t)((c + 1) * GEMM_EPI_CHUNK), rb);
+        process(ra, c);
+        if (!pf) tmem_ld_32x32b_x32(tile_taddr + (uint32_t)((c + 1) * GEMM_EPI_CHUNK), rb);
+        tmem_ld_wait();
+        const bool more = (c + 2 < CH);
+        if (!more) {  // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        } else if (pf) {
+          tmem_ld_32x32b_x32(tile_taddr + (uint32_t)((c + 2) * GEMM_EPI_CHUNK), ra);
+        }
+        process(rb, c + 1);
+        if (more && !pf) tmem_ld_32x32b_x32(tile_taddr + (uint32_t)((c + 2) * GEMM_EPI_CHUNK), ra);
       }
       if (ep.colsum != nullptr) {
         asm volatile("bar.sync 1, 256;\n" ::: "memory");      // every epilogue warp has added its rows of this tile
@@ -497,7 +547,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }

@@ -77,7 +77,8 @@ def run_case(name, d, arrangement, B, dev, rank, world, seed):
     sl = slice(rank * B, (rank + 1) * B)
     out = net(audio[sl].to(dev), imgs[sl].to(dev), 0.75, 0.75, mae_loss_weight=mae_w, contrast_loss_weight=c_w)
     loss = float(out[0])
-    assert abs(loss - ref_rank_loss) <= 1e-3 * abs(ref_rank_loss) + 1e-4, (name, "rank loss", loss, ref_rank_loss)
+    rtol = 1e-3 if d is O.VIT_B else 2e-2      # same bounds as tests/test_model_gpu.py (reference geometry / TINY)
+    assert abs(loss - ref_rank_loss) <= rtol * abs(ref_rank_loss) + 1e-4, (name, "rank loss", loss, ref_rank_loss)
     opt.zero_grad()
     out[0].backward()
     torch.cuda.synchronize()
