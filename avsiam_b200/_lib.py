@@ -52,6 +52,8 @@ SIGNATURES = {
     "avs_decoder_restore_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "avs_layernorm_fwd": [_P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "avs_layernorm_bwd": [_P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "avs_layernorm_fwd2": [_P, _P, _P, _I, _P, _P, _F, _P, _P, _P, _I, _I, _P],
+    "avs_layernorm_bwd2": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "avs_seq_mean_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
     "avs_seq_mean_bwd": [_P, _P, _I, _I, _I, _I, _I, _P],
     "avs_eval_stats": [_P, _P, _I, _I, _P, _P, _P, _P, _P],

@@ -467,6 +467,10 @@ extern "C" int avs_attention_fwd(const void* qkv, long long ld_qkv, void* out, l
   if (check_common(qkv, ld_qkv, ld_o, n_seq, S, H, head_dim, "avs_attention_fwd")) return -1;
   AVS_REQUIRE(out && lse2, "avs_attention_fwd: null pointer");
   if (n_seq == 0) return 0;
+  if (avs_attention_tc_enabled()) {   // encoder shapes (head_dim 64, S <= 128): persistent single-tile tcgen05 kernel
+    const int rc = avs_attention_small_fwd(qkv, ld_qkv, out, ld_o, lse2, n_seq, S, H, head_dim, stream);
+    if (rc != -2) return rc;
+  }
   static const bool fwd_tc = avs_attention_tc_enabled() && !(getenv("AVS_ATTN_FWD_TC") && atoi(getenv("AVS_ATTN_FWD_TC")) == 0);
   if (fwd_tc) {   // long head_dim-32 sequences (MAE decoder): tcgen05 kernel, exponential-bound instead of issue-bound
     const int rc = avs_attention_fwd_tc(qkv, ld_qkv, out, ld_o, lse2, n_seq, S, H, head_dim, stream);
@@ -503,6 +507,10 @@ extern "C" int avs_attention_bwd(const void* qkv, long long ld_qkv, const void* 
   if (check_common(qkv, ld_qkv, ld_o, n_seq, S, H, head_dim, "avs_attention_bwd")) return -1;
   AVS_REQUIRE(out && dout && lse2 && delta && dqkv, "avs_attention_bwd: null pointer");
   if (n_seq == 0) return 0;
+  if (avs_attention_tc_enabled()) {   // encoder shapes: one kernel, delta taken inside it (no pre-pass over O / dO)
+    const int rc = avs_attention_small_bwd(qkv, ld_qkv, dout, ld_o, lse2, dqkv, dbias, n_seq, S, H, head_dim, stream_);
+    if (rc != -2) return rc;
+  }
   AttnArgs a = {};
   a.qkv = (const bf16*)qkv; a.dout = (const bf16*)dout; a.lse2 = const_cast<float*>(lse2); a.delta = delta;
   a.dqkv = (bf16*)dqkv;

@@ -36,6 +36,11 @@ int avs_attention_bwd_tc(const void* qkv, long long ld_qkv, const void* dout, lo
                          void* stream);
 int avs_attention_fwd_tc(const void* qkv, long long ld_qkv, void* out, long long ld_o, float* lse2, int n_seq, int S,
                          int H, int head_dim, void* stream);
+// short sequences of the shared encoder (head_dim 64, S <= 128): persistent tcgen05 kernels, attention_small.cu
+int avs_attention_small_fwd(const void* qkv, long long ld_qkv, void* out, long long ld_o, float* lse2, int n_seq, int S,
+                            int H, int head_dim, void* stream);
+int avs_attention_small_bwd(const void* qkv, long long ld_qkv, const void* dout, long long ld_o, const float* lse2,
+                            void* dqkv, float* dbias, int n_seq, int S, int H, int head_dim, void* stream);
 bool avs_attention_tc_enabled();  // AVS_ATTN_TC=0 in the environment selects the mma.sync kernels (A/B timing)
 
 // ---------------------------------------------------------------------------------------------

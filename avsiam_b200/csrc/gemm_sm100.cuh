@@ -67,7 +67,7 @@ constexpr int GEMM_EPI_WARPS = 8;  // two warps per TMEM lane quarter, each taki
 // chunks, the packed outputs and the input tile of a chunk at once.
 constexpr int GEMM_THREADS = 32 * GEMM_EPI_WARPS + 128;
 constexpr int GEMM_WARP_TMA = GEMM_EPI_WARPS, GEMM_WARP_MMA = GEMM_EPI_WARPS + 1;
-constexpr int GEMM_REGS_EPI = 216, GEMM_REGS_PRODUCER = 80;   // 256 x 216 + 128 x 80 = 65536
+constexpr int GEMM_REGS_EPI = 208, GEMM_REGS_PRODUCER = 88;   // 256 x 208 + 128 x 88 = 64512 = the 384 x 168 registers the launch allocates (never more: an inc that does not fit blocks forever)
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_EPI_CHUNK = 32;                 // columns per epilogue chunk (one tcgen05.ld 32x32b.x32)
 constexpr int GEMM_EPI_BUF = 32 * GEMM_EPI_CHUNK * 2;  // one [32 rows x 32 cols] bf16 input staging tile = 2 KB

@@ -10,6 +10,31 @@
 #include "common.cuh"
 #include <stdlib.h>
 
+// Two affine sets in one launch: rows [0, split) use set 0, rows [split, M) set 1 (audio | video tokens of the shared
+// encoder, Block.forward's modality switch at cav_mae_base.py:151-152,169-170,190-191). CTAs [0, cta_split) work on the
+// first range, the rest on the second, so every thread still keeps ITS affine chunk in registers for the whole kernel.
+struct LnSeg {
+  int lo, hi;        // row range of this CTA
+  int bi, nb;        // index of this CTA among the nb CTAs of the range
+  int which;         // 0 / 1
+};
+__device__ __forceinline__ LnSeg ln_segment(int M, int split, int cta_split) {
+  LnSeg s;
+  s.which = ((int)blockIdx.x >= cta_split) ? 1 : 0;
+  s.lo = s.which ? split : 0;
+  s.hi = s.which ? M : split;
+  s.bi = s.which ? (int)blockIdx.x - cta_split : (int)blockIdx.x;
+  s.nb = s.which ? (int)gridDim.x - cta_split : cta_split;
+  return s;
+}
+static int ln_cta_split(int blocks, int M, int split) {
+  if (split >= M) return blocks;
+  if (split <= 0) return 0;
+  if (blocks < 2) return -1;   // caller must provide >= 2 CTAs for two non-empty ranges
+  int c = (int)(((long long)blocks * split + M / 2) / M);
+  return c < 1 ? 1 : (c > blocks - 1 ? blocks - 1 : c);
+}
+
 // rows are counted in int (M < 2^31): the division runs in 32 bits (a 64-bit division costs ~80 instructions, and
 // these kernels are issue-bound)
 __device__ __forceinline__ long long map_row(long long r, int S, int stride, int off) {
@@ -48,12 +73,17 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps,
                                                             bf16* __restrict__ y, float* __restrict__ mean_out,
-                                                            float* __restrict__ rstd_out, int M, int D, int S,
-                                                            int x_stride, int x_off, int y_stride, int y_off) {
+                                                            float* __restrict__ rstd_out, int M_all, int D, int S,
+                                                            int x_stride, int x_off, int y_stride, int y_off,
+                                                            const float* __restrict__ gamma1,
+                                                            const float* __restrict__ beta1, int split, int cta_split) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = D / 8;
-  const long long stride = (long long)gridDim.x * 8;
-  long long r = (long long)blockIdx.x * 8 + warp;
+  const LnSeg sg = ln_segment(M_all, split, cta_split);
+  if (sg.which) { gamma = gamma1; beta = beta1; }
+  const int M = sg.hi;
+  const long long stride = (long long)sg.nb * 8;
+  long long r = (long long)sg.lo + (long long)sg.bi * 8 + warp;
   uint4 cur[NCH], nxt[NCH];
   auto issue = [&](long long row, uint4 (&dst)[NCH]) {
     const long long xr = map_row(row, S, x_stride, x_off);
@@ -142,8 +172,13 @@ __global__ void __launch_bounds__(TPR * RG, 2) layernorm_bwd_kernel(
     const bf16* __restrict__ dy, const float* __restrict__ dpool, float pool_scale, const bf16* __restrict__ x,
     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
     const bf16* __restrict__ resid, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-    float* __restrict__ dbias, int M, int S, int x_stride, int x_off, int y_stride, int y_off) {
+    float* __restrict__ dbias, int M_all, int S, int x_stride, int x_off, int y_stride, int y_off,
+    const float* __restrict__ gamma1, float* __restrict__ dgamma1, float* __restrict__ dbeta1, int split,
+    int cta_split) {
   constexpr int NT = TPR * RG, NW = (NT + 31) / 32, D = TPR * 8;
+  const LnSeg sg = ln_segment(M_all, split, cta_split);
+  if (sg.which) { gamma = gamma1; dgamma = dgamma1; dbeta = dbeta1; }
+  const int M = sg.hi;
   constexpr int WPG = (TPR >= 32) ? TPR / 32 : 1;   // warps per row group
   __shared__ float red[2][LNB_R][2][NW];
   __shared__ float sacc[3][D];
@@ -166,7 +201,7 @@ __global__ void __launch_bounds__(TPR * RG, 2) layernorm_bwd_kernel(
   // on its own cp.async groups — and the loads of the next iterations stay in flight during the reductions of this
   // one (with plain loads the kernel alternated between a burst of loads and a compute phase: ~3 TB/s).
   extern __shared__ uint4 ln_ring[];    // [LNB_STAGES][LNB_R][3][NT]
-  const long long step = (long long)gridDim.x * (RG * LNB_R);
+  const long long step = (long long)sg.nb * (RG * LNB_R);
   auto issue = [&](long long base, int stage) {
 #pragma unroll
     for (int k = 0; k < LNB_R; ++k) {
@@ -181,7 +216,7 @@ __global__ void __launch_bounds__(TPR * RG, 2) layernorm_bwd_kernel(
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   };
-  const long long base0 = (long long)blockIdx.x * (RG * LNB_R);
+  const long long base0 = (long long)sg.lo + (long long)sg.bi * (RG * LNB_R);
 #pragma unroll
   for (int st = 0; st < LNB_STAGES - 1; ++st) issue(base0 + st * step, st);   // (groups past M are empty)
 
@@ -315,9 +350,13 @@ constexpr int LNF_R = 2, LNF_STAGES = 4;
 template <int TPR, int RG>
 __global__ void __launch_bounds__(TPR * RG, 2) layernorm_fwd_rg_kernel(
     const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-    bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int S, int x_stride,
-    int x_off, int y_stride, int y_off) {
+    bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M_all, int S, int x_stride,
+    int x_off, int y_stride, int y_off, const float* __restrict__ gamma1, const float* __restrict__ beta1, int split,
+    int cta_split) {
   constexpr int NT = TPR * RG, NW = NT / 32, D = TPR * 8, WPG = TPR / 32;
+  const LnSeg sg = ln_segment(M_all, split, cta_split);
+  if (sg.which) { gamma = gamma1; beta = beta1; }
+  const int M = sg.hi;
   static_assert(TPR % 32 == 0 && WPG >= 2, "row groups must be whole warps");
   extern __shared__ uint4 lnf_ring[];   // [LNF_STAGES][LNF_R][NT]
   __shared__ float red[2][LNF_R][NW];
@@ -329,7 +368,7 @@ __global__ void __launch_bounds__(TPR * RG, 2) layernorm_fwd_rg_kernel(
     g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
     b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
   }
-  const long long step = (long long)gridDim.x * (RG * LNF_R);
+  const long long step = (long long)sg.nb * (RG * LNF_R);
   auto issue = [&](long long base, int stage) {
 #pragma unroll
     for (int k = 0; k < LNF_R; ++k) {
@@ -338,7 +377,7 @@ __global__ void __launch_bounds__(TPR * RG, 2) layernorm_fwd_rg_kernel(
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   };
-  const long long base0 = (long long)blockIdx.x * (RG * LNF_R);
+  const long long base0 = (long long)sg.lo + (long long)sg.bi * (RG * LNF_R);
 #pragma unroll
   for (int st = 0; st < LNF_STAGES - 1; ++st) issue(base0 + st * step, st);
   const float inv_d = 1.0f / D;
@@ -406,39 +445,41 @@ __global__ void __launch_bounds__(TPR * RG, 2) layernorm_fwd_rg_kernel(
 template <int TPR, int RG>
 static void launch_ln_fwd_rg(const void* x, const float* gamma, const float* beta, float eps, void* y, float* mean,
                              float* rstd, int M, int S, int x_stride, int x_off, int y_stride, int y_off,
-                             cudaStream_t stream) {
+                             const float* gamma1, const float* beta1, int split, cudaStream_t stream) {
   const int ring = LNF_STAGES * LNF_R * TPR * RG * 16;
   static bool ring_set = false;
   if (!ring_set) {
     cudaFuncSetAttribute(layernorm_fwd_rg_kernel<TPR, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring);
     ring_set = true;
   }
-  const int blocks = min(avs_num_sms() * 2, ceil_div(M, RG * LNF_R));
+  const int blocks = max(split < M && split > 0 ? 2 : 1, min(avs_num_sms() * 2, ceil_div(M, RG * LNF_R)));
   layernorm_fwd_rg_kernel<TPR, RG><<<blocks, TPR * RG, ring, stream>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, mean,
-                                                                      rstd, M, S, x_stride, x_off, y_stride, y_off);
+                                                                      rstd, M, S, x_stride, x_off, y_stride, y_off,
+                                                                      gamma1, beta1, split, ln_cta_split(blocks, M, split));
 }
 
 static int ln_nch(int D) { return (D + 255) / 256; }
 
-extern "C" int avs_layernorm_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y,
-                                 float* mean, float* rstd, int M, int D, int seq_len, int x_seq_stride, int x_off,
-                                 int y_seq_stride, int y_off, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int ln_fwd_impl(const void* x, const float* gamma, const float* beta, float eps, void* y, float* mean,
+                       float* rstd, int M, int D, int seq_len, int x_seq_stride, int x_off, int y_seq_stride, int y_off,
+                       const float* gamma1, const float* beta1, int split, cudaStream_t stream) {
   AVS_REQUIRE(x && gamma && beta && y && mean && rstd, "avs_layernorm_fwd: null pointer");
   AVS_REQUIRE(D % 8 == 0 && D <= 2048, "avs_layernorm_fwd: D must be a multiple of 8 and <= 2048 (got %d)", D);
   AVS_REQUIRE(((uintptr_t)gamma & 15) == 0 && ((uintptr_t)beta & 15) == 0, "avs_layernorm_fwd: gamma/beta 16-byte alignment");
   if (M == 0) return 0;
   static const bool rg_path = !(getenv("AVS_LN_FWD_RG") && atoi(getenv("AVS_LN_FWD_RG")) == 0);
   if (rg_path && (D == 512 || D == 768 || D == 1024)) {
-    if (D == 512) launch_ln_fwd_rg<64, 4>(x, gamma, beta, eps, y, mean, rstd, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off, stream);
-    else if (D == 768) launch_ln_fwd_rg<96, 2>(x, gamma, beta, eps, y, mean, rstd, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off, stream);
-    else launch_ln_fwd_rg<128, 2>(x, gamma, beta, eps, y, mean, rstd, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off, stream);
+    if (D == 512) launch_ln_fwd_rg<64, 4>(x, gamma, beta, eps, y, mean, rstd, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off, gamma1, beta1, split, stream);
+    else if (D == 768) launch_ln_fwd_rg<96, 2>(x, gamma, beta, eps, y, mean, rstd, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off, gamma1, beta1, split, stream);
+    else launch_ln_fwd_rg<128, 2>(x, gamma, beta, eps, y, mean, rstd, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off, gamma1, beta1, split, stream);
     return avs_check_launch("layernorm_fwd_rg_kernel");
   }
-  const int blocks = min(avs_num_sms() * 8, ceil_div(M, 8));
+  const int blocks = max(split < M && split > 0 ? 2 : 1, min(avs_num_sms() * 8, ceil_div(M, 8)));
+  const int cta_split = ln_cta_split(blocks, M, split);
 #define LN_FWD(N)                                                                                              \
   layernorm_fwd_kernel<N><<<blocks, 256, 0, stream>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, mean, rstd, M, D, \
-                                                      seq_len, x_seq_stride, x_off, y_seq_stride, y_off)
+                                                      seq_len, x_seq_stride, x_off, y_seq_stride, y_off, gamma1, beta1, \
+                                                      split, cta_split)
   switch (ln_nch(D)) {
     case 1: LN_FWD(1); break;
     case 2: LN_FWD(2); break;
@@ -451,14 +492,32 @@ extern "C" int avs_layernorm_fwd(const void* x, const float* gamma, const float*
   return avs_check_launch("layernorm_fwd_kernel");
 }
 
+extern "C" int avs_layernorm_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y,
+                                 float* mean, float* rstd, int M, int D, int seq_len, int x_seq_stride, int x_off,
+                                 int y_seq_stride, int y_off, void* stream_) {
+  return ln_fwd_impl(x, gamma, beta, eps, y, mean, rstd, M, D, seq_len, x_seq_stride, x_off, y_seq_stride, y_off,
+                     nullptr, nullptr, M, (cudaStream_t)stream_);
+}
+
+extern "C" int avs_layernorm_fwd2(const void* x, const float* gamma0, const float* beta0, int split_row,
+                                  const float* gamma1, const float* beta1, float eps, void* y, float* mean,
+                                  float* rstd, int M, int D, void* stream_) {
+  AVS_REQUIRE(split_row >= 0 && split_row <= M, "avs_layernorm_fwd2: split_row out of range");
+  AVS_REQUIRE(split_row == M || (gamma1 && beta1 && ((uintptr_t)gamma1 & 15) == 0 && ((uintptr_t)beta1 & 15) == 0),
+              "avs_layernorm_fwd2: second affine set missing / misaligned");
+  return ln_fwd_impl(x, gamma0, beta0, eps, y, mean, rstd, M, D, 0, 0, 0, 0, 0, gamma1, beta1, split_row,
+                     (cudaStream_t)stream_);
+}
+
 template <int TPR, int RG>
 static void launch_ln_bwd(const void* dy, const float* dpool, float pool_scale, const void* x, const float* mean,
                           const float* rstd, const float* gamma, const void* resid, void* dx, float* dgamma,
                           float* dbeta, float* dbias, int M, int seq_len, int x_seq_stride, int x_off,
-                          int y_seq_stride, int y_off, cudaStream_t stream) {
+                          int y_seq_stride, int y_off, const float* gamma1, float* dgamma1, float* dbeta1, int split,
+                          cudaStream_t stream) {
   const int rows_per_cta = RG * LNB_R;
   const int ctas_per_sm = 2;
-  const int blocks = min(avs_num_sms() * ctas_per_sm, ceil_div(M, rows_per_cta));
+  const int blocks = max(split < M && split > 0 ? 2 : 1, min(avs_num_sms() * ctas_per_sm, ceil_div(M, rows_per_cta)));
   const int ring = LNB_STAGES * LNB_R * 3 * TPR * RG * 16;
   static bool ring_set = false;   // per instantiation (static + dynamic shared memory can exceed the 48 KB default)
   if (!ring_set) {
@@ -467,14 +526,14 @@ static void launch_ln_bwd(const void* dy, const float* dpool, float pool_scale, 
   }
   layernorm_bwd_kernel<TPR, RG><<<blocks, TPR * RG, ring, stream>>>(
       (const bf16*)dy, dpool, pool_scale, (const bf16*)x, mean, rstd, gamma, (const bf16*)resid, (bf16*)dx, dgamma,
-      dbeta, dbias, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off);
+      dbeta, dbias, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off, gamma1, dgamma1, dbeta1, split,
+      ln_cta_split(blocks, M, split));
 }
 
-extern "C" int avs_layernorm_bwd(const void* dy, const float* dpool, float pool_scale, const void* x,
-                                 const float* mean, const float* rstd, const float* gamma, const void* resid,
-                                 void* dx, float* dgamma, float* dbeta, float* dbias, int M, int D, int seq_len,
-                                 int x_seq_stride, int x_off, int y_seq_stride, int y_off, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int ln_bwd_impl(const void* dy, const float* dpool, float pool_scale, const void* x, const float* mean,
+                       const float* rstd, const float* gamma, const void* resid, void* dx, float* dgamma, float* dbeta,
+                       float* dbias, int M, int D, int seq_len, int x_seq_stride, int x_off, int y_seq_stride, int y_off,
+                       const float* gamma1, float* dgamma1, float* dbeta1, int split, cudaStream_t stream) {
   AVS_REQUIRE(x && mean && rstd && gamma && dx && dgamma && dbeta, "avs_layernorm_bwd: null pointer");
   AVS_REQUIRE(dy != nullptr || dpool != nullptr, "avs_layernorm_bwd: need dy and/or dpool");
   AVS_REQUIRE(dpool == nullptr || seq_len > 0, "avs_layernorm_bwd: dpool needs seq_len");
@@ -483,7 +542,7 @@ extern "C" int avs_layernorm_bwd(const void* dy, const float* dpool, float pool_
   if (M == 0) return 0;
 #define LN_BWD(TPR, RG)                                                                                          \
   launch_ln_bwd<TPR, RG>(dy, dpool, pool_scale, x, mean, rstd, gamma, resid, dx, dgamma, dbeta, dbias, M, seq_len, \
-                         x_seq_stride, x_off, y_seq_stride, y_off, stream)
+                         x_seq_stride, x_off, y_seq_stride, y_off, gamma1, dgamma1, dbeta1, split, stream)
   switch (D) {
     case 64: LN_BWD(8, 32); break;
     case 128: LN_BWD(16, 16); break;
@@ -498,6 +557,26 @@ extern "C" int avs_layernorm_bwd(const void* dy, const float* dpool, float pool_
   }
 #undef LN_BWD
   return avs_check_launch("layernorm_bwd_kernel");
+}
+
+extern "C" int avs_layernorm_bwd(const void* dy, const float* dpool, float pool_scale, const void* x,
+                                 const float* mean, const float* rstd, const float* gamma, const void* resid,
+                                 void* dx, float* dgamma, float* dbeta, float* dbias, int M, int D, int seq_len,
+                                 int x_seq_stride, int x_off, int y_seq_stride, int y_off, void* stream_) {
+  return ln_bwd_impl(dy, dpool, pool_scale, x, mean, rstd, gamma, resid, dx, dgamma, dbeta, dbias, M, D, seq_len,
+                     x_seq_stride, x_off, y_seq_stride, y_off, nullptr, nullptr, nullptr, M, (cudaStream_t)stream_);
+}
+
+extern "C" int avs_layernorm_bwd2(const void* dy, const void* x, const float* mean, const float* rstd,
+                                  const float* gamma0, float* dgamma0, float* dbeta0, int split_row,
+                                  const float* gamma1, float* dgamma1, float* dbeta1, const void* resid, void* dx,
+                                  float* dbias, int M, int D, void* stream_) {
+  AVS_REQUIRE(split_row >= 0 && split_row <= M, "avs_layernorm_bwd2: split_row out of range");
+  AVS_REQUIRE(split_row == M || (gamma1 && dgamma1 && dbeta1 && ((uintptr_t)gamma1 & 15) == 0),
+              "avs_layernorm_bwd2: second affine set missing / misaligned");
+  AVS_REQUIRE(dy != nullptr, "avs_layernorm_bwd2: dy required");
+  return ln_bwd_impl(dy, nullptr, 0.f, x, mean, rstd, gamma0, resid, dx, dgamma0, dbeta0, dbias, M, D, 0, 0, 0, 0, 0,
+                     gamma1, dgamma1, dbeta1, split_row, (cudaStream_t)stream_);
 }
 
 // out[s, :] = (1/S) * sum_t y[y_row(s*S + t), :]   (fp32 output)

@@ -237,20 +237,46 @@ class Engine:
         return x, groups
 
     # -------------------------------------------------------------------------------------------- transformer block
-    def _ln_fwd_groups(self, x, y, mean, rstd, groups, pfx, which, D):
+    @staticmethod
+    def _ln_segments(groups):
+        """Contiguous row ranges that share one affine set: consecutive groups of the same modality merge (the five
+        audio chunks and the five video chunks of the mixed-ratio pass are two ranges)."""
+        segs = []
         for g in groups:
             sfx = "" if g.mod is None else "_" + g.mod
-            r0, r1 = g.row0, g.row0 + g.rows
-            ops.layernorm_fwd(x[r0:r1], self.P.f32(f"{pfx}{which}{sfx}.weight"), self.P.f32(f"{pfx}{which}{sfx}.bias"),
-                              LN_EPS_BLOCK, y[r0:r1], mean[r0:r1], rstd[r0:r1], g.rows, D)
+            if segs and segs[-1][2] == sfx and segs[-1][1] == g.row0:
+                segs[-1][1] = g.row0 + g.rows
+            else:
+                segs.append([g.row0, g.row0 + g.rows, sfx])
+        return segs
+
+    def _ln_fwd_groups(self, x, y, mean, rstd, groups, pfx, which, D):
+        segs = self._ln_segments(groups)
+        P = self.P
+        if len(segs) == 2 and segs[0][0] == 0 and segs[0][1] == segs[1][0]:   # audio | video: ONE launch, two affine sets
+            (_, split, s0), (_, end, s1) = segs
+            ops.layernorm_fwd2(x[:end], P.f32(f"{pfx}{which}{s0}.weight"), P.f32(f"{pfx}{which}{s0}.bias"), split,
+                               P.f32(f"{pfx}{which}{s1}.weight"), P.f32(f"{pfx}{which}{s1}.bias"), LN_EPS_BLOCK, y[:end],
+                               mean[:end], rstd[:end], end, D)
+            return
+        for r0, r1, sfx in segs:
+            ops.layernorm_fwd(x[r0:r1], P.f32(f"{pfx}{which}{sfx}.weight"), P.f32(f"{pfx}{which}{sfx}.bias"),
+                              LN_EPS_BLOCK, y[r0:r1], mean[r0:r1], rstd[r0:r1], r1 - r0, D)
 
     def _ln_bwd_groups(self, dy, x, mean, rstd, dx, resid, groups, pfx, which, D, dbias=None):
-        for g in groups:
-            sfx = "" if g.mod is None else "_" + g.mod
-            r0, r1 = g.row0, g.row0 + g.rows
-            ops.layernorm_bwd(dy[r0:r1], x[r0:r1], mean[r0:r1], rstd[r0:r1], self.P.f32(f"{pfx}{which}{sfx}.weight"),
-                              dx[r0:r1], self.P.grad(f"{pfx}{which}{sfx}.weight"),
-                              self.P.grad(f"{pfx}{which}{sfx}.bias"), g.rows, D, resid=resid[r0:r1], dbias=dbias)
+        segs = self._ln_segments(groups)
+        P = self.P
+        if len(segs) == 2 and segs[0][0] == 0 and segs[0][1] == segs[1][0]:
+            (_, split, s0), (_, end, s1) = segs
+            ops.layernorm_bwd2(dy[:end], x[:end], mean[:end], rstd[:end], P.f32(f"{pfx}{which}{s0}.weight"),
+                               P.grad(f"{pfx}{which}{s0}.weight"), P.grad(f"{pfx}{which}{s0}.bias"), split,
+                               P.f32(f"{pfx}{which}{s1}.weight"), P.grad(f"{pfx}{which}{s1}.weight"),
+                               P.grad(f"{pfx}{which}{s1}.bias"), dx[:end], end, D, resid=resid[:end], dbias=dbias)
+            return
+        for r0, r1, sfx in segs:
+            ops.layernorm_bwd(dy[r0:r1], x[r0:r1], mean[r0:r1], rstd[r0:r1], P.f32(f"{pfx}{which}{sfx}.weight"),
+                              dx[r0:r1], P.grad(f"{pfx}{which}{sfx}.weight"), P.grad(f"{pfx}{which}{sfx}.bias"),
+                              r1 - r0, D, resid=resid[r0:r1], dbias=dbias)
 
     def block(self, tape: Optional[list], xin: Act, groups: Sequence[Group], pfx: str, heads: int) -> Act:
         """Block.forward (cav_mae_base.py:149-193): x += proj(attn(LN1_m x)); x += fc2(gelu(fc1(LN2_m x)))."""

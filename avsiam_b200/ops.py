@@ -232,6 +232,31 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, *, resid=No
                                             y_seq_stride, y_off, _stream()), "avs_layernorm_bwd")
 
 
+def layernorm_fwd2(x, gamma0, beta0, split_row, gamma1, beta1, eps, y, mean, rstd, M, D):
+    """Rows [0, split_row) normalised with (gamma0, beta0), rows [split_row, M) with (gamma1, beta1), one launch."""
+    _chk(x, BF16, "ln.x"); _chk(y, BF16, "ln.y"); _chk(mean, F32, "ln.mean"); _chk(rstd, F32, "ln.rstd")
+    for t in (gamma0, beta0, gamma1, beta1):
+        _chk(t, F32, "ln.affine")
+    _lib.check(_lib.lib().avs_layernorm_fwd2(x.data_ptr(), gamma0.data_ptr(), beta0.data_ptr(), split_row,
+                                             gamma1.data_ptr(), beta1.data_ptr(), eps, y.data_ptr(), mean.data_ptr(),
+                                             rstd.data_ptr(), M, D, _stream()), "avs_layernorm_fwd2")
+
+
+def layernorm_bwd2(dy, x, mean, rstd, gamma0, dgamma0, dbeta0, split_row, gamma1, dgamma1, dbeta1, dx, M, D, *,
+                   resid=None, dbias=None):
+    _chk(dy, BF16, "ln_bwd.dy"); _chk(x, BF16, "ln_bwd.x"); _chk(dx, BF16, "ln_bwd.dx")
+    for t in (gamma0, dgamma0, dbeta0, gamma1, dgamma1, dbeta1):
+        _chk(t, F32, "ln_bwd.affine")
+    if resid is not None:
+        _chk(resid, BF16, "ln_bwd.resid")
+    if dbias is not None:
+        _chk(dbias, F32, "ln_bwd.dbias")
+    _lib.check(_lib.lib().avs_layernorm_bwd2(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                             gamma0.data_ptr(), dgamma0.data_ptr(), dbeta0.data_ptr(), split_row,
+                                             gamma1.data_ptr(), dgamma1.data_ptr(), dbeta1.data_ptr(), _p(resid),
+                                             dx.data_ptr(), _p(dbias), M, D, _stream()), "avs_layernorm_bwd2")
+
+
 def seq_mean_fwd(y, out, n_seq, seq_len, D, y_seq_stride=None, y_off=0):
     _chk(y, BF16, "seq_mean.y"); _chk(out, F32, "seq_mean.out")
     _lib.check(_lib.lib().avs_seq_mean_fwd(y.data_ptr(), out.data_ptr(), n_seq, seq_len, D,
@@ -472,6 +497,11 @@ attention_fwd = _instrument("attention_fwd", attention_fwd, _work_attn_fwd, _det
 attention_bwd = _instrument("attention_bwd", attention_bwd, _work_attn_bwd, _detail_attn("attention_bwd"))
 layernorm_fwd = _instrument("layernorm_fwd", layernorm_fwd,
                             lambda x, gamma, beta, eps, y, mean, rstd, M, D, **k: 4.0 * M * D)
+layernorm_fwd2 = _instrument("layernorm_fwd", layernorm_fwd2,
+                             lambda x, g0, b0, split, g1, b1, eps, y, mean, rstd, M, D: 4.0 * M * D)
+layernorm_bwd2 = _instrument("layernorm_bwd", layernorm_bwd2,
+                             lambda dy, x, mean, rstd, g0, dg0, db0, split, g1, dg1, db1, dx, M, D, **k:
+                             (8.0 if k.get("resid") is not None else 6.0) * M * D)
 layernorm_bwd = _instrument("layernorm_bwd", layernorm_bwd,
                             lambda dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, **k:
                             (8.0 if k.get("resid") is not None else 6.0) * M * D)

@@ -135,6 +135,16 @@ int avs_layernorm_bwd(const void* dy, const float* dpool, float pool_scale, cons
                                       writes this residual stream) */,
                       int M, int D, int seq_len, int x_seq_stride, int x_off, int y_seq_stride, int y_off,
                       void* stream);
+/* Two affine sets in ONE launch: rows [0, split_row) use set 0, rows [split_row, M) set 1 — the audio | video token
+ * ranges of the shared encoder, whose Block picks norm{1,2}_a / norm{1,2}_v per modality (cav_mae_base.py:151-152,
+ * 169-170,190-191). Identity row maps. bwd2 accumulates each range's dgamma / dbeta into its own set; dbias (the
+ * column sums of dx) is common to both ranges. */
+int avs_layernorm_fwd2(const void* x, const float* gamma0, const float* beta0, int split_row, const float* gamma1,
+                       const float* beta1, float eps, void* y, float* mean, float* rstd, int M, int D, void* stream);
+int avs_layernorm_bwd2(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma0,
+                       float* dgamma0, float* dbeta0, int split_row, const float* gamma1, float* dgamma1,
+                       float* dbeta1, const void* resid /* or NULL */, void* dx, float* dbias /* or NULL */, int M,
+                       int D, void* stream);
 /* out fp32 [n_seq, D] = mean over the seq_len tokens of each sequence (.mean(dim=1), cav_mae_base.py:563-566,729) */
 int avs_seq_mean_fwd(const void* y, float* out, int n_seq, int seq_len, int D, int y_seq_stride, int y_off,
                      void* stream);

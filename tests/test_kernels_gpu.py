@@ -233,6 +233,35 @@ def test_layernorm_fwd_bwd(M, D, eps):
     assert torch.allclose(dbias, 1.0 + (xr.grad + res.float()).sum(0), rtol=2e-3, atol=2e-2 * math.sqrt(M))
 
 
+@pytest.mark.parametrize("M,D,split", [(45312, 768, 32768), (1000, 768, 600), (777, 512, 1), (300, 1024, 299),
+                                       (500, 128, 200), (64, 768, 0), (64, 768, 64), (3, 512, 2)])
+def test_layernorm_two_affine_sets_one_launch(M, D, split):
+    """Rows [0, split) with the audio LayerNorm set, rows [split, M) with the video set, in ONE launch
+    (Block.forward's norm{1,2}_a / norm{1,2}_v switch, cav_mae_base.py:151-152,169-170,190-191)."""
+    x = rnd(M, D, scale=2.0, dtype=torch.bfloat16)
+    g0, b0, g1, b1 = 1 + 0.1 * rnd(D, seed=1), 0.1 * rnd(D, seed=2), 1 + 0.2 * rnd(D, seed=3), 0.3 * rnd(D, seed=4)
+    y = torch.empty_like(x)
+    mean, rstd = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    ops.layernorm_fwd2(x, g0, b0, split, g1, b1, 1e-5, y, mean, rstd, M, D)
+    xr = x.float().requires_grad_(True)
+    gs = [t.clone().requires_grad_(True) for t in (g0, b0, g1, b1)]
+    ref = torch.cat([F.layer_norm(xr[:split], (D,), gs[0], gs[1], 1e-5), F.layer_norm(xr[split:], (D,), gs[2], gs[3], 1e-5)])
+    assert rel_err(y, ref) < 4e-3
+    dy, res = rnd(M, D, dtype=torch.bfloat16), rnd(M, D, dtype=torch.bfloat16)
+    ref.backward(dy.float())
+    dx = torch.empty_like(x)
+    dg0, db0, dg1, db1, dbias = (torch.zeros(D, device=DEV) for _ in range(5))
+    ops.layernorm_bwd2(dy, x, mean, rstd, g0, dg0, db0, split, g1, dg1, db1, dx, M, D, resid=res, dbias=dbias)
+    assert rel_err(dx, xr.grad + res.float()) < 5e-3
+    for got, want, rows in ((dg0, gs[0].grad, split), (db0, gs[1].grad, split), (dg1, gs[2].grad, M - split),
+                            (db1, gs[3].grad, M - split)):
+        if rows == 0:
+            assert float(got.abs().max()) == 0.0
+        else:
+            assert rel_err(got, want) < 1e-3
+    assert torch.allclose(dbias, (xr.grad + res.float()).sum(0), rtol=2e-3, atol=2e-2 * math.sqrt(M))
+
+
 def test_layernorm_rowmap_and_pool_grad():
     n_seq, S, D, stride, off = 4, 5, 128, 12, 7
     M = n_seq * S
@@ -262,6 +291,10 @@ def test_layernorm_rowmap_and_pool_grad():
 # ------------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("n_seq,S,H,hd", [(3, 49, 12, 64), (2, 128, 12, 64), (2, 177, 12, 64), (2, 708, 16, 32),
                                           (1, 64, 2, 32), (2, 1, 2, 64),
+                                          # persistent single-tile tcgen05 kernels (head_dim 64, S <= 128): pair packing
+                                          # with an odd sequence count, slot edges, more tiles than CTAs
+                                          (1, 49, 2, 64), (5, 64, 2, 64), (3, 65, 2, 64), (2, 100, 4, 64), (3, 127, 2, 64),
+                                          (7, 17, 2, 64), (64, 128, 12, 64), (101, 49, 12, 64),
                                           # tcgen05 forward range (head_dim 32, 256 <= S <= 768): unit / block edges
                                           (1, 256, 4, 32), (3, 257, 2, 32), (2, 300, 2, 32), (1, 511, 2, 32),
                                           (1, 640, 2, 32), (2, 768, 2, 32)])
@@ -295,6 +328,33 @@ def test_attention_fwd_bwd(n_seq, S, H, hd):
             continue
         e = rel_err(got, want)
         assert e < 2e-2, (name, e)   # bf16 P / dS operands in the tensor-core products
+
+
+@pytest.mark.parametrize("n_seq,S", [(3, 49), (2, 128), (5, 80)])
+def test_attention_small_writes_only_its_rows(n_seq, S):
+    """The encoder groups are row slices of shared [tokens, 3D] / [tokens, D] buffers (audio rows, then video rows): the
+    persistent kernels load 64-row boxes that reach into the neighbouring group and must never WRITE outside their own
+    rows. Guard rows before and after the slice must keep their contents, and the result must not depend on them."""
+    H, hd = 2, 64
+    D, G = H * hd, 70
+    rows = n_seq * S
+    big_qkv = rnd(rows + 2 * G, 3 * D, dtype=torch.bfloat16, seed=5)
+    big_out = torch.full((rows + 2 * G, D), 7.0, dtype=torch.bfloat16, device=DEV)
+    big_dqkv = torch.full((rows + 2 * G, 3 * D), 9.0, dtype=torch.bfloat16, device=DEV)
+    big_dout = rnd(rows + 2 * G, D, dtype=torch.bfloat16, seed=6)
+    qkv, out, dqkv, dout = big_qkv[G:G + rows], big_out[G:G + rows], big_dqkv[G:G + rows], big_dout[G:G + rows]
+    lse2 = torch.empty(n_seq, H, S, device=DEV)
+    delta = torch.empty(n_seq, H, S, device=DEV)
+    ops.attention_fwd(qkv, out, lse2, n_seq, S, H, hd)
+    ops.attention_bwd(qkv, out, dout, lse2, delta, dqkv, n_seq, S, H, hd)
+    for big, fill in ((big_out, 7.0), (big_dqkv, 9.0)):
+        assert bool((big[:G] == fill).all()) and bool((big[G + rows:] == fill).all())
+    # same inputs in a stand-alone buffer (different neighbours: zero fill) give the same result
+    out2, dqkv2 = torch.empty(rows, D, dtype=torch.bfloat16, device=DEV), torch.empty(rows, 3 * D, dtype=torch.bfloat16, device=DEV)
+    lse2b = torch.empty_like(lse2)
+    ops.attention_fwd(qkv.contiguous(), out2, lse2b, n_seq, S, H, hd)
+    ops.attention_bwd(qkv.contiguous(), out2, dout.contiguous(), lse2b, delta, dqkv2, n_seq, S, H, hd)
+    assert torch.equal(out2, out) and torch.equal(dqkv2, dqkv) and torch.equal(lse2, lse2b)
 
 
 @pytest.mark.parametrize("S", [708, 400])
