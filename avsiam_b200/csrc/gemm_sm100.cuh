@@ -305,7 +305,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int quarter = warp & 3;
     const int half = ew >> 2;
     constexpr int CH = BLOCK_N / (2 * GEMM_EPI_CHUNK);  // chunks per warp per tile (even)
-    static_assert(CH % 2 == 0, "the epilogue walks chunk pairs");
+    static_assert(CH % 2 == 0, "output staging tiles hold chunk pairs");
     const GemmEpilogue& ep = args.epi;
     const bool tma_epi = args.tma_epi != 0;
     const bool has_in = tma_epi && args.has_in;
@@ -506,29 +506,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         ++q;
       };
 
-      // The accumulator is read in chunk pairs through two register buffers: with tmem_prefetch the tcgen05.ld of the
-      // next chunk is in flight while the current chunk's math runs (the ld latency, ~130+ cycles alone and more under
-      // the MMA's TMEM traffic, leaves the dependency chain of a warp that shares its scheduler with one other warp).
-      uint32_t ra[32], rb[32];
+      // The tcgen05.ld of chunk c+1 is issued before chunk c's math (tmem_prefetch): its latency (~130+ cycles alone,
+      // more under the MMA's TMEM traffic) leaves the dependency chain of a warp that shares its scheduler with one other
+      // warp. The chunk body exists ONCE (the prefetched registers are moved into the working set, 32 MOVs per chunk):
+      // two copies of it made the kernel 170 KB of SASS and every epilogue variant slower — instruction-cache misses.
+      uint32_t rcur[32], rnext[32];
       const bool pf = args.tmem_prefetch != 0;
-      tmem_ld_32x32b_x32(tile_taddr, ra);
+      tmem_ld_32x32b_x32(tile_taddr, rnext);
 #pragma unroll 1
-      for (int c = 0; c < CH; c += 2) {
+      for (int c = 0; c < CH; ++c) {
         tmem_ld_wait();
-        if (pf) tmem_ld_32x32b_x32(tile_taddr + (uint32_t)((c + 1) * GEMM_EPI_CHUNK), rb);
-        process(ra, c);
-        if (!pf) tmem_ld_32x32b_x32(tile_taddr + (uint32_t)((c + 1) * GEMM_EPI_CHUNK), rb);
-        tmem_ld_wait();
-        const bool more = (c + 2 < CH);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rcur[j] = rnext[j];
+        const bool more = (c + 1 < CH);
         if (!more) {  // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         } else if (pf) {
-          tmem_ld_32x32b_x32(tile_taddr + (uint32_t)((c + 2) * GEMM_EPI_CHUNK), ra);
+          tmem_ld_32x32b_x32(tile_taddr + (uint32_t)((c + 1) * GEMM_EPI_CHUNK), rnext);
         }
-        process(rb, c + 1);
-        if (more && !pf) tmem_ld_32x32b_x32(tile_taddr + (uint32_t)((c + 2) * GEMM_EPI_CHUNK), ra);
+        process(rcur, c);
+        if (more && !pf) tmem_ld_32x32b_x32(tile_taddr + (uint32_t)((c + 1) * GEMM_EPI_CHUNK), rnext);
       }
       if (ep.colsum != nullptr) {
         asm volatile("bar.sync 1, 256;\n" ::: "memory");      // every epilogue warp has added its rows of this tile
