@@ -213,6 +213,8 @@ class CAVMAE_BASE(nn.Module):
         self._used_cache = {}            # (arrangement, do_mae, do_c) -> (names, active-chunk bitmap)
         self._last_active = None         # bitmap of the parameters the last backward wrote (FusedAdam skips the rest)
         self.register_load_state_dict_post_hook(CAVMAE_BASE._after_load_state_dict)
+        from .optim import register_model
+        register_model(self)   # FusedAdam(model.parameters(), ...) finds the arena owner from a bare parameter list
 
     @staticmethod
     def _after_load_state_dict(module, incompatible_keys):

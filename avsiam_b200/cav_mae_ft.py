@@ -116,6 +116,8 @@ class CAVMAEFT_BASE(nn.Module):
         self._used_cache = {}
         self._last_active = None
         self.register_load_state_dict_post_hook(CAVMAEFT_BASE._after_load_state_dict)
+        from .optim import register_model
+        register_model(self)   # FusedAdam(model.parameters(), ...) finds the arena owner from a bare parameter list
 
     def __create_fusion__(self):
         """Run after loading pretraining weights (:823-825): the fusion blocks restart from blocks 10 / 11."""
