@@ -68,8 +68,13 @@ constexpr int GEMM_EPI_WARPS = 8;  // two warps per TMEM lane quarter, each taki
 // the LOWEST warp ids: with the roles the other way round (epilogue warps 0-7, issuers 8-9) every shape ran 8-40 %
 // slower — the issuers then lose the scheduler's arbitration against the two epilogue warps of their sub-partition
 // and the tensor pipe waits for its next instruction.
+#ifdef AVS_GEMM_LEGACY_ROLES   // A/B build: 10 warps, no register hand-over (warps 2-9 epilogue, compiler cap 168 registers)
+constexpr int GEMM_THREADS = 32 * GEMM_EPI_WARPS + 64;
+constexpr int GEMM_WARP_TMA = 0, GEMM_WARP_MMA = 1, GEMM_FIRST_EPI_WARP = 2;
+#else
 constexpr int GEMM_THREADS = 32 * GEMM_EPI_WARPS + 128;
 constexpr int GEMM_WARP_TMA = 0, GEMM_WARP_MMA = 1, GEMM_FIRST_EPI_WARP = 4;
+#endif
 constexpr int GEMM_REGS_EPI = 208, GEMM_REGS_PRODUCER = 88;   // 256 x 208 + 128 x 88 = 64512 = the 384 x 168 registers the launch allocates (never more: an inc that does not fit blocks forever)
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_EPI_CHUNK = 32;                 // columns per epilogue chunk (one tcgen05.ld 32x32b.x32)
@@ -196,7 +201,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < GEMM_FIRST_EPI_WARP) {
+#ifndef AVS_GEMM_LEGACY_ROLES
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(GEMM_REGS_PRODUCER));
+#endif
    if (warp == GEMM_WARP_TMA) {
     // ============================ TMA producer ============================
     // The whole warp runs the loop convergently (loop state stays in uniform registers); one elected lane issues.
@@ -294,7 +301,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
    }
   } else {
+#ifndef AVS_GEMM_LEGACY_ROLES
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(GEMM_REGS_EPI));
+#endif
     // ============================ epilogue (8 warps) ============================
     // warp w may only touch TMEM lanes 32*(w%4)..+32; the two warps sharing a quarter split the tile's columns.
     const int ew = warp - GEMM_FIRST_EPI_WARP;
