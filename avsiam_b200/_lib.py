@@ -40,7 +40,6 @@ SIGNATURES = {
     "avs_launch_count": [],
     "avs_reset_launch_count": [],
     "avs_reset": [],
-    "avs_gemm_set_tuning": [_I, _I],
     "avs_gemm_bf16": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, POINTER(GemmEpilogue), _I, _P],
     "avs_mask_argsort": [_P, _I, _I, _I, _P, _P, _P, _P],
     "avs_mask_force_noise": [_P, _I, _I, _I, _P, _I, _P, _I, _F, _P],
@@ -86,7 +85,6 @@ _RESTYPES = {
     "avs_launch_count": c_longlong,
     "avs_reset_launch_count": None,
     "avs_reset": None,
-    "avs_gemm_set_tuning": None,
     "avs_infonce_workspace_bytes": c_size_t,
 }
 

@@ -17,13 +17,6 @@ extern "C" void avs_debug_set_desc_variant(int v) { g_desc_variant = v; }
 #else
 static const int g_desc_variant = 0;
 #endif
-// tuning knobs (documented in INTEGRATION.md): depth of the epilogue's input-tile ring, TMEM load prefetch
-static int g_in_depth = getenv("AVS_GEMM_IN_DEPTH") ? atoi(getenv("AVS_GEMM_IN_DEPTH")) : 3;
-static int g_tmem_prefetch = getenv("AVS_GEMM_TMEM_PREFETCH") ? atoi(getenv("AVS_GEMM_TMEM_PREFETCH")) : 1;
-extern "C" void avs_gemm_set_tuning(int in_depth, int tmem_prefetch) {
-  if (in_depth > 0) g_in_depth = in_depth;
-  if (tmem_prefetch >= 0) g_tmem_prefetch = tmem_prefetch;
-}
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -132,12 +125,7 @@ static int launch_gemm(const GemmMaps& tm, GemmArgs& args, int grid, cudaStream_
     }
     attr_set = true;
   }
-  // the input-tile ring is as deep as leaves the mainloop at least 3 stages
-  int depth = g_in_depth < 2 ? 2 : (g_in_depth > GEMM_MAX_IN_DEPTH ? GEMM_MAX_IN_DEPTH : g_in_depth);
-  while (depth > 2 && Cfg::pick_stages(Cfg::epi_bytes_per_warp(args.tma_epi, args.has_in, args.has_aux_out, depth)) < 3) --depth;
-  args.in_depth = depth;
-  args.tmem_prefetch = g_tmem_prefetch;
-  const int epw = Cfg::epi_bytes_per_warp(args.tma_epi, args.has_in, args.has_aux_out, depth);
+  const int epw = Cfg::epi_bytes_per_warp(args.tma_epi, args.has_in, args.has_aux_out);
   args.stages = Cfg::pick_stages(epw);
   const int smem = Cfg::smem_bytes(args.stages, epw);
   gemm_bf16_kernel<AM, BM, BN><<<grid, GEMM_THREADS, smem, stream>>>(tm.a, tm.b, tm.c, tm.in, tm.aux, args);

@@ -50,8 +50,6 @@ struct GemmArgs {
   int desc_variant;     // -DAVS_GEMM_DEBUG builds only: 1 swaps LBO/SBO of MN-major descriptors (probe), 2 skips the TMA
                         // stores, 4 skips the in-stream loads (timing experiments, wrong results); ignored otherwise
   int stages;           // smem ring depth (runtime: whatever fits beside the epilogue staging buffers)
-  int in_depth;         // tma_epi && has_in: depth of each epilogue warp's ring of [32 x 32] input tiles (2..4)
-  int tmem_prefetch;    // 1: the tcgen05.ld of chunk c+1 is issued before chunk c's math (second register buffer)
   int tma_epi;          // 1: bf16 C (and aux_out) leave through TMA stores, resid/aux_in arrive through TMA loads
   int has_in;           // tma_epi: a [M,N] bf16 input tile stream exists (resid or aux_in — never both)
   int has_aux_out;      // tma_epi: the GELU pre-activation is stored as a second output stream
@@ -62,24 +60,10 @@ constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int GEMM_UMMA_K = 16;
 constexpr int GEMM_EPI_WARPS = 8;  // two warps per TMEM lane quarter, each taking half of the tile's columns
-// warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 idle (together the producer warpgroup), warps 4-11 epilogue (two
-// warpgroups): the producer warpgroup hands its registers to the epilogue warpgroups (setmaxnreg), which hold two
-// 32-column accumulator chunks, the packed outputs and the input tile of a chunk at once. The two issuing warps keep
-// the LOWEST warp ids: with the roles the other way round (epilogue warps 0-7, issuers 8-9) every shape ran 8-40 %
-// slower — the issuers then lose the scheduler's arbitration against the two epilogue warps of their sub-partition
-// and the tensor pipe waits for its next instruction.
-#ifdef AVS_GEMM_LEGACY_ROLES   // A/B build: 10 warps, no register hand-over (warps 2-9 epilogue, compiler cap 168 registers)
-constexpr int GEMM_THREADS = 32 * GEMM_EPI_WARPS + 64;
-constexpr int GEMM_WARP_TMA = 0, GEMM_WARP_MMA = 1, GEMM_FIRST_EPI_WARP = 2;
-#else
-constexpr int GEMM_THREADS = 32 * GEMM_EPI_WARPS + 128;
-constexpr int GEMM_WARP_TMA = 0, GEMM_WARP_MMA = 1, GEMM_FIRST_EPI_WARP = 4;
-#endif
-constexpr int GEMM_REGS_EPI = 208, GEMM_REGS_PRODUCER = 88;   // 256 x 208 + 128 x 88 = 64512 = the 384 x 168 registers the launch allocates (never more: an inc that does not fit blocks forever)
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp0 TMA, warp1 MMA, warps2-9 epilogue
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_EPI_CHUNK = 32;                 // columns per epilogue chunk (one tcgen05.ld 32x32b.x32)
 constexpr int GEMM_EPI_BUF = 32 * GEMM_EPI_CHUNK * 2;  // one [32 rows x 32 cols] bf16 input staging tile = 2 KB
-constexpr int GEMM_MAX_IN_DEPTH = 4;
 // Output staging tiles are [32 rows x 64 cols] (128-byte rows, SWIZZLE_128B) and leave every SECOND chunk: the TMA
 // unit turns each box row into one L2 write request, so 64-byte rows (the 32-column tiles of v2) made the stores —
 // 2048 row requests per 128x256 tile — the bound of every bf16-output GEMM (ncu: MMA warp polling tmem_empty).
@@ -96,9 +80,8 @@ struct GemmCfg {
   static constexpr int BAR_BYTES = 512;
   // per epilogue warp: [in x2][out][aux_out] staging tiles (only the ones the launch uses).  (Double-buffering the
   // output tiles was measured and bought nothing: the mainloop, not the store latency, bounds these kernels.)
-  static __host__ __device__ int epi_bytes_per_warp(int tma_epi, int has_in, int has_aux_out, int in_depth) {
-    // in tiles first (2 KB each, so the output tiles that follow stay 1024-byte aligned for their 128 B swizzle)
-    return tma_epi ? GEMM_EPI_BUF * (has_in ? in_depth : 0) + GEMM_OUT_BUF * (1 + (has_aux_out ? 1 : 0)) : 0;
+  static __host__ __device__ int epi_bytes_per_warp(int tma_epi, int has_in, int has_aux_out) {
+    return tma_epi ? GEMM_EPI_BUF * (has_in ? 2 : 0) + GEMM_OUT_BUF * (1 + (has_aux_out ? 1 : 0)) : 0;
   }
   static __host__ int pick_stages(int epi_per_warp) {
     int s = (GEMM_SMEM_LIMIT - 1024 - BAR_BYTES - GEMM_EPI_WARPS * epi_per_warp) / STAGE_BYTES;
@@ -152,15 +135,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  const int epi_per_warp = Cfg::epi_bytes_per_warp(args.tma_epi, args.has_in, args.has_aux_out, args.in_depth);
+  const int epi_per_warp = Cfg::epi_bytes_per_warp(args.tma_epi, args.has_in, args.has_aux_out);
   uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + GEMM_EPI_WARPS * epi_per_warp);
   uint64_t* full_bar = bars;                               // [MAX_STAGES]
   uint64_t* empty_bar = bars + GEMM_MAX_STAGES;            // [MAX_STAGES]
   uint64_t* tfull_bar = bars + 2 * GEMM_MAX_STAGES;        // [2]
   uint64_t* tempty_bar = bars + 2 * GEMM_MAX_STAGES + 2;   // [2]
-  uint64_t* in_bar = bars + 2 * GEMM_MAX_STAGES + 4;       // [EPI_WARPS][MAX_IN_DEPTH]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_MAX_STAGES + 4 + GEMM_MAX_IN_DEPTH * GEMM_EPI_WARPS);
+  uint64_t* in_bar = bars + 2 * GEMM_MAX_STAGES + 4;       // [EPI_WARPS][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_MAX_STAGES + 4 + 2 * GEMM_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -170,7 +153,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int total_kb = (args.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   const int num_tiles = m_tiles * n_tiles * args.split_k;
 
-  if (warp == GEMM_WARP_TMA && lane == 0) {
+  if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     if (args.tma_epi) {
@@ -179,7 +162,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (args.has_aux_out) tma_prefetch_desc(&tma_aux);
     }
   }
-  if (warp == GEMM_WARP_MMA && lane == 0) {
+  if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -188,10 +171,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], GEMM_EPI_WARPS);
     }
-    for (int i = 0; i < GEMM_MAX_IN_DEPTH * GEMM_EPI_WARPS; ++i) mbar_init(&in_bar[i], 1);
+    for (int i = 0; i < 2 * GEMM_EPI_WARPS; ++i) mbar_init(&in_bar[i], 1);
     fence_mbar_init();
   }
-  if (warp == GEMM_FIRST_EPI_WARP) {
+  if (warp == 2) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -200,11 +183,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < GEMM_FIRST_EPI_WARP) {
-#ifndef AVS_GEMM_LEGACY_ROLES
-   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(GEMM_REGS_PRODUCER));
-#endif
-   if (warp == GEMM_WARP_TMA) {
+  if (warp == 0) {
     // ============================ TMA producer ============================
     // The whole warp runs the loop convergently (loop state stays in uniform registers); one elected lane issues.
     int stage = 0;
@@ -245,7 +224,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
       }
     }
-   } else if (warp == GEMM_WARP_MMA) {
+  } else if (warp == 1) {
     // ============================ MMA issuer ============================
     // One k-block is only 4 MMAs (~512 tensor cycles at BLOCK_N = 256), so the issuing warp's scalar work must stay
     // well below that: the warp runs convergently, every descriptor is a precomputed 64-bit base plus a 16-byte-unit
@@ -299,14 +278,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-   }
   } else {
-#ifndef AVS_GEMM_LEGACY_ROLES
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(GEMM_REGS_EPI));
-#endif
     // ============================ epilogue (8 warps) ============================
     // warp w may only touch TMEM lanes 32*(w%4)..+32; the two warps sharing a quarter split the tile's columns.
-    const int ew = warp - GEMM_FIRST_EPI_WARP;
+    const int ew = warp - 2;
     // column sums of the output (the bias gradient of the upstream Linear), accumulated per CTA and tile in shared
     // memory and flushed with one global atomic per column and tile
     __shared__ float s_colsum[256];
@@ -316,46 +291,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     const int quarter = warp & 3;
     const int half = ew >> 2;
-    constexpr int CH = BLOCK_N / (2 * GEMM_EPI_CHUNK);  // chunks per warp per tile (even)
-    static_assert(CH % 2 == 0, "output staging tiles hold chunk pairs");
+    constexpr int CH = BLOCK_N / (2 * GEMM_EPI_CHUNK);  // chunks per warp per tile
     const GemmEpilogue& ep = args.epi;
+    uint8_t* my_epi = smem_epi + ew * epi_per_warp;
+    uint8_t* in_buf = my_epi;                                        // [2][2 KB] when has_in
+    uint8_t* out_buf = my_epi + (args.has_in ? 2 * GEMM_EPI_BUF : 0);   // 1024-byte aligned (128 B swizzle pattern)
+    uint8_t* aux_buf = out_buf + GEMM_OUT_BUF;
+    uint64_t* my_in_bar = in_bar + 2 * ew;
     const bool tma_epi = args.tma_epi != 0;
     const bool has_in = tma_epi && args.has_in;
-    const int IN_DEPTH = args.in_depth;
-    uint8_t* my_epi = smem_epi + ew * epi_per_warp;
-    uint8_t* in_buf = my_epi;                                              // [IN_DEPTH][2 KB] when has_in
-    uint8_t* out_buf = my_epi + (args.has_in ? IN_DEPTH * GEMM_EPI_BUF : 0);   // 1024-byte aligned (128 B swizzle)
-    uint8_t* aux_buf = out_buf + GEMM_OUT_BUF;
-    uint64_t* my_in_bar = in_bar + GEMM_MAX_IN_DEPTH * ew;
+
+    // flat per-warp chunk sequence q = tile_iteration * CH + chunk; `in` tiles are prefetched two chunks ahead
 #ifdef AVS_GEMM_DEBUG
-    const bool dbg_no_in = (args.desc_variant & 4) != 0, dbg_no_store = (args.desc_variant & 2) != 0;
+    const bool dbg_no_in = (args.desc_variant & 4) != 0;   // timing experiment: no in-stream TMA loads (wrong results)
+    const bool dbg_no_store = (args.desc_variant & 2) != 0;
 #else
     constexpr bool dbg_no_in = false, dbg_no_store = false;
 #endif
-
-    // flat per-warp chunk sequence q = tile_iteration * CH + chunk; the `in` tiles (residual / dGELU operand) travel
-    // through a ring of IN_DEPTH slots filled IN_DEPTH chunks ahead: chunk q lives in slot q % IN_DEPTH, and the load
-    // of chunk q + IN_DEPTH is issued into the slot chunk q has just been read from.
-    auto issue_in = [&](int qq, int slot) {
+    auto issue_in = [&](int q) {
       if (dbg_no_in) return;
-      const int t = blockIdx.x + (qq / CH) * (int)gridDim.x;
+      const int t = blockIdx.x + (q / CH) * (int)gridDim.x;
       if (t >= num_tiles) return;
       const int mn = t / args.split_k;
       const int m0 = (mn / n_tiles) * GEMM_BLOCK_M;
       const int n0 = (mn % n_tiles) * BLOCK_N;
-      const int col = n0 + half * (BLOCK_N / 2) + (qq % CH) * GEMM_EPI_CHUNK;
-      mbar_arrive_expect_tx(&my_in_bar[slot], GEMM_EPI_BUF);
-      tma_load_2d(in_buf + slot * GEMM_EPI_BUF, &tma_in, &my_in_bar[slot], col, m0 + quarter * 32);
+      const int col = n0 + half * (BLOCK_N / 2) + (q % CH) * GEMM_EPI_CHUNK;
+      mbar_arrive_expect_tx(&my_in_bar[q & 1], GEMM_EPI_BUF);
+      tma_load_2d(in_buf + (q & 1) * GEMM_EPI_BUF, &tma_in, &my_in_bar[q & 1], col, m0 + quarter * 32);
     };
     if (has_in && lane == 0) {
-      for (int i = 0; i < IN_DEPTH; ++i) issue_in(i, i);
+      issue_in(0);
+      issue_in(1);
     }
 
     int acc = 0;
     uint32_t acc_phase = 0;
     int q = 0;
-    int in_slot = 0;
-    uint32_t in_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int ks = t % args.split_k;
       const int mn = t / args.split_k;
@@ -371,11 +342,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         rowadd_ptr = ep.rowadd + (long long)ri * args.N;
       }
       const bool lead_split = (ks == 0);
-      const uint32_t tile_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * (BLOCK_N / 2));
-
-      // one 32-column chunk: registers r (raw accumulator bits) -> bias / activation / residual -> staging / global
-      auto process = [&](uint32_t (&r)[32], const int c) {
+#pragma unroll 1
+      for (int c = 0; c < CH; ++c, ++q) {
         const int ccol = half * (BLOCK_N / 2) + c * GEMM_EPI_CHUNK;  // column offset inside the tile
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + ccol);
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_wait();
+        if (c == CH - 1) {  // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
         const int nc = n0 + ccol;
         const bool col_ok = nc < args.N;
         const bool full = (nc + 32 <= args.N);
@@ -426,16 +404,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
           uint4 in4[4];
           if (has_in) {
-            if (!dbg_no_in) mbar_wait(&my_in_bar[in_slot], in_phase);
+            if (!dbg_no_in) mbar_wait(&my_in_bar[q & 1], (uint32_t)((q >> 1) & 1));
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              in4[j] = *reinterpret_cast<const uint4*>(in_buf + in_slot * GEMM_EPI_BUF + epi_tile_off(lane, j));
-            __syncwarp();                     // every lane has read its row: the slot may be refilled
-            if (lane == 0) issue_in(q + IN_DEPTH, in_slot);
-            if (++in_slot == IN_DEPTH) {
-              in_slot = 0;
-              in_phase ^= 1;
-            }
+              in4[j] = *reinterpret_cast<const uint4*>(in_buf + (q & 1) * GEMM_EPI_BUF + epi_tile_off(lane, j));
+            __syncwarp();                     // every lane has read its row: the tile may be refilled
+            if (lane == 0) issue_in(q + 2);
           }
           if (ep.flags & EPI_DGELU) {
 #pragma unroll
@@ -515,31 +489,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
         }
-        ++q;
-      };
-
-      // The tcgen05.ld of chunk c+1 is issued before chunk c's math (tmem_prefetch): its latency (~130+ cycles alone,
-      // more under the MMA's TMEM traffic) leaves the dependency chain of a warp that shares its scheduler with one other
-      // warp. The chunk body exists ONCE (the prefetched registers are moved into the working set, 32 MOVs per chunk):
-      // two copies of it made the kernel 170 KB of SASS and every epilogue variant slower — instruction-cache misses.
-      uint32_t rcur[32], rnext[32];
-      const bool pf = args.tmem_prefetch != 0;
-      tmem_ld_32x32b_x32(tile_taddr, rnext);
-#pragma unroll 1
-      for (int c = 0; c < CH; ++c) {
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) rcur[j] = rnext[j];
-        const bool more = (c + 1 < CH);
-        if (!more) {  // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        } else if (pf) {
-          tmem_ld_32x32b_x32(tile_taddr + (uint32_t)((c + 1) * GEMM_EPI_CHUNK), rnext);
-        }
-        process(rcur, c);
-        if (more && !pf) tmem_ld_32x32b_x32(tile_taddr + (uint32_t)((c + 1) * GEMM_EPI_CHUNK), rnext);
       }
       if (ep.colsum != nullptr) {
         asm volatile("bar.sync 1, 256;\n" ::: "memory");      // every epilogue warp has added its rows of this tile
@@ -558,7 +507,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == GEMM_FIRST_EPI_WARP) {
+  if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }

@@ -33,11 +33,6 @@ void avs_reset_launch_count(void);
  * Never required for correctness — entries are matched by value — it only bounds the cache of a long-lived process
  * that keeps changing shapes. */
 void avs_reset(void);
-/* Tuning knobs of the GEMM epilogue (defaults are the measured best): depth (2..4) of each
- * epilogue warp's ring of residual / dGELU input tiles, and whether the next accumulator chunk is prefetched from
- * tensor memory. Arguments <= 0 / < 0 leave the value unchanged. Also read from AVS_GEMM_IN_DEPTH /
- * AVS_GEMM_TMEM_PREFETCH at load time. */
-void avs_gemm_set_tuning(int in_depth, int tmem_prefetch);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM (tcgen05 / TMEM / TMA).  D[M,N] = epi( sum_k A(m,k) * B(n,k) ), bf16 operands, fp32 accumulate.
