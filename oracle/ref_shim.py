@@ -161,3 +161,69 @@ def build_reference_model(norm_pix_loss=False):
     with contextlib.redirect_stdout(io.StringIO()):
         m = ref.CAVMAE_BASE(audio_length=1024, norm_pix_loss=norm_pix_loss, modality_specific_depth=23, tr_pos=False)
     return m
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The reference's training loop (src/traintest_cavmae_base.py), loaded UNMODIFIED by file path.
+# ---------------------------------------------------------------------------------------------------------
+class SyntheticAVDataset(torch.utils.data.Dataset):
+    """Stands in for dataloader.AudiosetDataset (the loop builds its own DataLoader from it at
+    traintest_cavmae_base.py:95-97): seeded (fbank [1024,128], frame [3,224,224], label) samples."""
+
+    n_samples = 4
+    seed = 4242
+
+    def __init__(self, dataset_json_file=None, audio_conf=None, label_csv=None, **_):
+        g = torch.Generator().manual_seed(self.seed)
+        self.a = torch.randn(self.n_samples, 1024, 128, generator=g)
+        self.v = torch.randn(self.n_samples, 3, 224, 224, generator=g)
+
+    def __len__(self):
+        return self.n_samples
+
+    def __getitem__(self, i):
+        return self.a[i], self.v[i], torch.zeros(1)
+
+
+_TRAINTEST = None
+
+
+def load_traintest():
+    """Returns the reference's own `traintest_cavmae_base` module object. Its imports that cannot be satisfied here
+    are stubbed from the OUTSIDE: `utilities` (the shipped utilities/__init__.py is not Python source; the package is
+    rebuilt from utilities/util.py and utilities/stats.py, which are), `dataloader` (AudiosetDataset -> synthetic
+    samples), `wandb`, `ipdb`, `deepspeed` (imported, never used on the path)."""
+    global _TRAINTEST
+    if _TRAINTEST is not None:
+        return _TRAINTEST
+    load_reference()                       # installs timm / tome / ipdb / models stubs
+    import importlib.util as iu
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    util_spec = iu.spec_from_file_location("_ref_utilities_util", os.path.join(REF_SRC, "utilities", "util.py"))
+    util = iu.module_from_spec(util_spec)
+    util_spec.loader.exec_module(util)
+    public = {k: v for k, v in util.__dict__.items() if not k.startswith("_")}
+    utilities = mod("utilities", **public)
+    utilities.__path__ = []
+    mod("dataloader", AudiosetDataset=SyntheticAVDataset)
+    mod("wandb", log=lambda *a, **k: None, init=lambda *a, **k: None)
+    ds = mod("deepspeed")
+    ds.profiling = mod("deepspeed.profiling")
+    ds.profiling.flops_profiler = mod("deepspeed.profiling.flops_profiler")
+    ds.profiling.flops_profiler.profiler = mod("deepspeed.profiling.flops_profiler.profiler", FlopsProfiler=object)
+    spec = iu.spec_from_file_location("traintest_cavmae_base", os.path.join(REF_SRC, "traintest_cavmae_base.py"))
+    m = iu.module_from_spec(spec)
+    argv = sys.argv
+    try:
+        sys.argv = [os.path.join(REF_SRC, "traintest_cavmae_base.py")]   # the file appends to sys.path from sys.path[0]
+        spec.loader.exec_module(m)
+    finally:
+        sys.argv = argv
+    _TRAINTEST = m
+    return m

@@ -256,3 +256,36 @@ def test_checkpoint_roundtrip_pt_to_ft_and_weight_average(tmp_path):
     assert torch.allclose(avg[k], want, atol=1e-7)
     m3 = CAVMAE_BASE(dims=d)
     assert ck.load_model(m3, avg) == ([], [])
+
+
+def test_patch_rebinds_the_names_the_reference_train_loop_resolves():
+    """avsiam_b200.patch() on the UNMODIFIED reference modules (build container only): `DDP`, `torch.optim.Adam` and
+    `models.CAVMAE_BASE` / `CAVMAEFT_BASE` are what train() / run_cavmae_*.py resolve at run time, everything else
+    passes through, and undo() restores the originals."""
+    import os
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("reference tree not present (GPU box)")
+    import sys
+    import torch
+    import avsiam_b200
+    from oracle import ref_shim
+    tt = ref_shim.load_traintest()
+    models_pkg = sys.modules["models"]
+    names = tt.train.__code__.co_names
+    assert "DDP" in names and "torch" in names and "GradScaler" in names      # globals looked up by name at call time
+    assert tt.train.__globals__ is tt.__dict__
+    orig_ddp, orig_torch = tt.DDP, tt.torch
+    undo = avsiam_b200.patch(tt, models_pkg)
+    try:
+        assert tt.DDP is avsiam_b200.B200DDP
+        assert tt.torch.optim.Adam is avsiam_b200.FusedAdam
+        assert tt.torch.optim.lr_scheduler.MultiStepLR is torch.optim.lr_scheduler.MultiStepLR
+        assert tt.torch.device is torch.device and tt.torch.nn.SyncBatchNorm is torch.nn.SyncBatchNorm
+        assert tt.torch.utils.data.DataLoader is torch.utils.data.DataLoader and tt.torch.save is torch.save
+        assert models_pkg.CAVMAE_BASE is avsiam_b200.CAVMAE_BASE and models_pkg.CAVMAEFT_BASE is avsiam_b200.CAVMAEFT_BASE
+        # the constructor call of run_cavmae_pretrain_base.py:175 is accepted as written
+        m = models_pkg.CAVMAE_BASE(audio_length=1024, norm_pix_loss=False, modality_specific_depth=23, tr_pos=False, opt=None)
+        assert len(m.state_dict()) == 963
+    finally:
+        undo()
+    assert tt.DDP is orig_ddp and tt.torch is orig_torch
