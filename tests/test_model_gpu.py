@@ -401,6 +401,9 @@ def test_two_optimizer_two_pass_body():
             assert float(delta.abs().max()) == 0, k
             continue
         moved += 1
+        if k.endswith("attn.qkv.bias"):     # the key-bias gradient is identically zero in exact arithmetic (softmax is
+            n3 = delta.numel() // 3        # shift-invariant): Adam turns its rounding noise into full-size steps
+            delta, delta_ref = torch.cat([delta[:n3], delta[2 * n3:]]), torch.cat([delta_ref[:n3], delta_ref[2 * n3:]])
         # Adam steps are ~lr * sign-like: after 2 x 2 steps compare where the reference moved decisively
         big = delta_ref.abs() > 0.5 * delta_ref.abs().max()
         assert cos(delta[big], delta_ref[big]) > 0.95, (k, cos(delta[big], delta_ref[big]))
