@@ -153,6 +153,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     B = args.cpu_batch
+    # all host cores, whatever the launcher exported (torch.distributed.run sets OMP_NUM_THREADS=1 for N > 1)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     cores = torch.get_num_threads()
     sps, s_per_step = time_cpu(args.arrangement, B, args.steps, args.warmup)
     sample = (f"{args.steps} steps x batch {B} of the ViT-B/16 {args.arrangement} step (fp32, torch CPU kernels, "
@@ -174,6 +176,108 @@ def workload_config(args, per_gpu_batch: int, world: int):
                         f"mask 0.75, MAE + global-batch InfoNCE, Adam",
             "arrangement": args.arrangement, "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * world,
             "parallelism": f"dp{world}", "l2": "inputs (288 MB/step) and activations (>40 GB/step) exceed the 126 MB L2"}
+
+
+# ----------------------------------------------------------------------------------------------------- checkers
+def oracle_state_from_model(model, dev, dtype=torch.float32):
+    """The model's current weights as the oracle's flat {key: tensor} state (test infrastructure: the oracle is used
+    here only as the CHECKER of the step-0 loss and as the library-call comparator, never in the timed product path)."""
+    return {k: v.detach().to(dev, dtype).clone() for k, v in model.state_dict().items()
+            if not k.startswith("my_blocks.") and ".head." not in k}
+
+
+def check_step0_loss(model, net, args, dev, rank, world, dist):
+    """One untimed forward with supplied mask indices, compared with the fp32 oracle evaluated by the same rank on its
+    own batch (InfoNCE over the all-gathered oracle embeddings when world > 1): the N-GPU bench refuses to report a
+    number for a path whose loss is wrong. Returns (loss, oracle_loss)."""
+    from oracle import avsiam_oracle as O
+    d = O.VIT_B
+    B = min(args.batch, 16)          # bounded: the checker runs the fp32 oracle
+    g = torch.Generator().manual_seed(4321 + rank)
+    audio = torch.randn(B, d.audio_len, d.mel, generator=g).to(dev)
+    imgs = torch.randn(B, d.in_chans, d.img, d.img, generator=g).to(dev)
+    plan = O.make_mask_plan(B, d, 99 + rank, two_pass=(args.arrangement == "two_pass"))
+    model.mask_plan = plan
+    with torch.no_grad():
+        out = net(audio, imgs, 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+    model.mask_plan = None
+    state = oracle_state_from_model(model, dev)
+
+    def gather(x):
+        if world == 1:
+            return x
+        parts = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(parts, x.contiguous())
+        return torch.cat(parts, 0)
+
+    with torch.no_grad():
+        if args.arrangement == "single_pass":
+            ref = O.forward_single_pass(audio, imgs, state, d, plan.to(dev), mae_loss_weight=1.0,
+                                        contrast_loss_weight=0.01, gather=gather)
+        else:
+            ref = O.forward(audio, imgs, state, d, plan.to(dev), mae_loss_weight=1.0, contrast_loss_weight=0.01,
+                            gather=lambda x: gather(x))
+    got, want = float(out[0]), float(ref[0])
+    if not abs(got - want) <= 1e-3 * abs(want) + 1e-4:
+        raise SystemExit(f"bench.py: rank {rank}: step-0 loss {got} differs from the fp32 oracle {want}")
+    return got, want
+
+
+def time_library_baseline(args, dev, model, steps=3, warmup=2):
+    """The comparator SURVEY.md 8(d) asks for: the same step written as plain torch library calls (the oracle module's
+    F.linear / F.layer_norm / F.gelu -> cuBLAS and torch kernels, attention through F.scaled_dot_product_attention as in the
+    reference, cav_mae_base.py:65-68) under torch.autocast(bfloat16) with torch autograd and torch.optim.Adam(fused=True),
+    on THIS B200, same batch, nothing recomputed. A reported comparator, never part of the product path."""
+    from oracle import avsiam_oracle as O
+    import torch.nn.functional as F
+    d = O.VIT_B
+    B = args.batch
+    torch.cuda.empty_cache()
+    state = {k: v.requires_grad_(True) for k, v in oracle_state_from_model(model, dev).items()}
+    params = list(state.values())
+    opt = torch.optim.Adam(params, 2e-4, weight_decay=5e-7, betas=(0.95, 0.999), fused=True)
+    audio = torch.randn(B, d.audio_len, d.mel, device=dev)
+    imgs = torch.randn(B, d.in_chans, d.img, d.img, device=dev)
+    plan = O.make_mask_plan(B, d, 7, two_pass=False).to(dev)
+    # the library's own fused attention instead of the oracle's explicit softmax(QK^T)V (memory, and a fair comparator)
+    orig_attention = O.attention
+
+    def sdpa_attention(x, sd, pfx, heads):
+        Bq, N, C = x.shape
+        hd = C // heads
+        qkv = F.linear(x, sd[pfx + "qkv.weight"], sd[pfx + "qkv.bias"]).reshape(Bq, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+        o = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2]).transpose(1, 2).reshape(Bq, N, C)
+        return F.linear(o, sd[pfx + "proj.weight"], sd[pfx + "proj.bias"])
+
+    O.attention = sdpa_attention
+    try:
+        def step():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = O.forward_single_pass(audio, imgs, state, d, plan, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+            opt.zero_grad(set_to_none=True)
+            out[0].backward()
+            opt.step()
+            return out[0]
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        assert bool(torch.isfinite(loss)), "library baseline: non-finite loss"
+    finally:
+        O.attention = orig_attention
+        del state, params, opt
+        torch.cuda.empty_cache()
+    return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "what": "torch 2.11 eager, autocast(bfloat16), cuBLAS GEMMs + F.scaled_dot_product_attention + torch autograd + "
+                    "torch.optim.Adam(fused=True); same ViT-B/16 single_pass step, same batch, same GPU; activations kept "
+                    "by autograd (no recomputation)"}
 
 
 # ----------------------------------------------------------------------------------------------------- GPU arm
@@ -242,6 +346,11 @@ def run_gpu_arm(args):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
+
+    # ---- (0) untimed correctness gate: step-0 loss against the fp32 oracle (every rank; global InfoNCE at N > 1)
+    step0 = None
+    if not args.no_loss_check:
+        step0 = check_step0_loss(model, net, args, dev, rank, world, dist)
 
     # ---- (1) device-resident inputs: `value`
     for i in range(args.warmup):
@@ -327,11 +436,17 @@ def run_gpu_arm(args):
     fam_total = sum(f["ms"] for f in fam.values())
     gemm = fam.get("gemm", {"ms": 0.0, "work": 0.0, "calls": 0})
     gemm_tflops = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+    if os.path.exists(tpath) and args.arrangement == "single_pass" and B == 256:
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     roofline = {
         "kernel": "avs::gemm_bf16_kernel (tcgen05.mma + TMEM + TMA, all Linear / patch-embed fwd, dgrad, wgrad)",
         "bound": "tensor", "achieved": gemm_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
         "frac": gemm_tflops / peaks["bf16_tflops_sustained"], "peak_source": f"{peaks_src} (sustained cuBLAS bf16)",
-        "traffic": None, "launches_per_step": gemm["calls"], "ms_per_step": gemm["ms"],
+        "traffic": traffic, "traffic_unit": "bytes of DRAM read + write per launch (average over the launches of one step)",
+        "traffic_source": traffic_src, "launches_per_step": gemm["calls"], "ms_per_step": gemm["ms"],
         "share_of_kernel_time": gemm["ms"] / fam_total if fam_total else None,
     }
     families = {k: {"ms": round(v["ms"], 3), "calls": v["calls"],
@@ -348,6 +463,14 @@ def run_gpu_arm(args):
                         "sample": f"3 steps x batch {args.cpu_batch} (1 warm-up) of the same ViT-B/16 "
                                   f"{args.arrangement} step, fp32 torch CPU, oracle/avsiam_oracle.py"}
 
+    # ---- (5) library-call comparator on the same GPU (rank 0, N=1 only): torch eager bf16
+    library_baseline = None
+    if rank == 0 and world == 1 and args.library_baseline and args.arrangement == "single_pass":
+        try:
+            library_baseline = time_library_baseline(args, dev, model)
+        except torch.cuda.OutOfMemoryError as e:    # reported, not hidden: the comparator keeps every activation
+            library_baseline = {"unavailable": f"out of memory at batch {B}: {str(e)[:120]}"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -360,6 +483,8 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "library_baseline": library_baseline,
+            "step0_loss_check": None if step0 is None else {"loss": step0[0], "oracle_fp32": step0[1], "rtol": 1e-3},
             "tensor_pipe_util_vs_burst_peak": step_util,
             "train_gflop_per_sample": TRAIN_GFLOP_PER_SAMPLE[args.arrangement],
             "kernel_families_ms": families,
@@ -380,6 +505,9 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the CPU reference sample (config 1: 2)")
     ap.add_argument("--arrangement", default="single_pass", choices=["single_pass", "two_pass"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-loss-check", action="store_true", help="skip the untimed step-0 loss check against the fp32 oracle")
+    ap.add_argument("--no-library-baseline", dest="library_baseline", action="store_false",
+                    help="skip the torch-eager bf16 comparator (N=1 only)")
     ap.add_argument("--detail", action="store_true", help="print a per-shape kernel time table to stderr")
     ap.add_argument("--kernel-only", action="store_true", help="stop after the device-resident timed region (ncu aid)")
     args = ap.parse_args()

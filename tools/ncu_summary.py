@@ -17,10 +17,11 @@ WANT = [
     ("launch__shared_mem_per_block_dynamic", "dyn smem/block"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
-    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe active % (legacy mma.sync path)"),
-    ("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "  hmma subpipe %"),
-    ("sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
-     "tensor bf16->fp32 ops % of peak (tcgen05 + mma.sync)"),
+    # sm__pipe_tensor_cycles_active counts the tensor pipe for BOTH tcgen05.mma (UTCHMMA) and mma.sync (HMMA) issue
+    # paths on sm_100 — it is the utilisation figure to quote for the tcgen05 kernels (the per-op
+    # sm__ops_path_tensor_op_hmma_* counters stay 0 for UTCHMMA and are left out)
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe active % (tcgen05.mma and mma.sync)"),
+    ("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "  half-precision sub-pipe active %"),
     ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU (MUFU) pipe %"),
     ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe %"),
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe %"),
