@@ -26,7 +26,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .engine import Act, EmbedSpec, Engine, Group, ParamArena
-from .gather_layer import all_gather_embeddings
+from .gather_layer import PendingGather, all_gather_embeddings
 
 I32, F32 = torch.int32, torch.float32
 
@@ -323,6 +323,10 @@ class CAVMAE_BASE(nn.Module):
                 x = eng.block(tape, x, groups, f"vit_base.blocks.{i}.", d.heads)
             xcat, pooled = eng.final_norm(tape, x, groups, {"a": "vit_base.norm_a", "v": "vit_base.norm"}, cat=True,
                                           pool=do_c)
+            if do_c and world > 1:
+                # GatherLayer's all-gather (cav_mae_base.py:724-725) starts here, under the whole MAE branch
+                pending = PendingGather(pooled[0].t, pooled[1].t, self.process_group)
+                gather = lambda a, v: pending.wait()
             if do_mae:
                 run_mae(xcat, ira, irv, mask_a, mask_v, ka, kv)
             if do_c:

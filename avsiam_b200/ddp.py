@@ -138,12 +138,32 @@ class B200DDP(nn.Module):
         if not hasattr(module, "arena"):
             raise TypeError("B200DDP wraps avsiam_b200.CAVMAE_BASE (it synchronises the model's gradient arena)")
         module.process_group = process_group
-        module.grad_sync = GradSync(process_group, int(bucket_cap_mb * 1024 * 1024 // 4))
+        module.grad_sync = GradSync(self._gradient_group(process_group), int(bucket_cap_mb * 1024 * 1024 // 4))
         arena = module.arena                        # builds + binds the arena on the module's device
         if dist.is_initialized() and dist.get_world_size(process_group) > 1:
             dist.broadcast(arena.flat, src=dist.get_global_rank(process_group, 0) if process_group else 0,
                            group=process_group)
             arena.shadow_fresh = False
+
+    @staticmethod
+    def _gradient_group(process_group):
+        """A communicator of its own for the gradient buckets, limited to a few CTAs per all-reduce: the buckets overlap
+        the persistent 148-CTA GEMMs of the reverse pass, every SM an NCCL kernel holds is taken from them, and over
+        NVLink 5 / NVSwitch a handful of channels already carries the bandwidth the overlap needs
+        (AVS_DDP_MAX_CTAS, default 8; 0 = share the caller's group as it is)."""
+        import os
+        max_ctas = int(os.environ.get("AVS_DDP_MAX_CTAS", "8"))
+        if (not dist.is_initialized() or dist.get_world_size(process_group) == 1 or max_ctas <= 0
+                or dist.get_backend(process_group) != "nccl"):
+            return process_group
+        try:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = max_ctas
+            opts.config.min_ctas = min(max_ctas, 4)
+            ranks = dist.get_process_group_ranks(process_group) if process_group is not None else None
+            return dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+        except (AttributeError, RuntimeError):     # older NCCL / torch without communicator config: keep the group
+            return process_group
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)

@@ -29,6 +29,27 @@ class GatherLayer(torch.autograd.Function):
         return all_gradients[dist.get_rank()]
 
 
+class PendingGather:
+    """An all-gather of the pooled embeddings in flight: issued as soon as the encoder's final norm has produced them
+    (before the fusion blocks and the 8-block decoder run), joined just before the InfoNCE kernels need the global
+    batch — the exchange and, more importantly, the wait for the slowest rank's encoder hide under the MAE branch."""
+
+    def __init__(self, ea: torch.Tensor, ev: torch.Tensor, group=None):
+        B, D = ea.shape
+        self.D = D
+        world = dist.get_world_size(group)
+        self.packed = torch.cat([ea, ev], dim=1).contiguous()              # [B, 2D]: one message for both modalities
+        self.out = torch.empty(world * B, 2 * D, dtype=ea.dtype, device=ea.device)
+        self.work = dist.all_gather_into_tensor(self.out, self.packed, group=group, async_op=True)
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()          # stream-level join on NCCL (no host sync)
+            self.work = None
+        D = self.D
+        return self.out[:, :D].contiguous(), self.out[:, D:].contiguous()
+
+
 def all_gather_embeddings(ea: torch.Tensor, ev: torch.Tensor, group=None):
     """ea, ev fp32 [B, D] -> global [W*B, D] each (rank-major, like torch.cat(GatherLayer.apply(x), dim=0))."""
     B, D = ea.shape
