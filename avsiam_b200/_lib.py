@@ -29,7 +29,7 @@ class GemmEpilogue(Structure):
     ]
 
 
-EPI_GELU, EPI_DGELU, EPI_OUT_F32, EPI_OUT_ATOMIC = 1, 2, 4, 8
+EPI_GELU, EPI_DGELU, EPI_OUT_F32, EPI_OUT_ATOMIC, EPI_AUX_GRAD, EPI_MUL_AUX = 1, 2, 4, 8, 16, 32
 
 _P, _I, _L, _F = c_void_p, c_int, c_longlong, c_float
 

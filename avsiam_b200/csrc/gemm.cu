@@ -144,7 +144,11 @@ extern "C" int avs_gemm_bf16(const void* A, long long lda, int a_major, const vo
   const bool out_f32 = (epi->flags & (AVS_EPI_OUT_F32 | AVS_EPI_OUT_ATOMIC)) != 0;
   AVS_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc * (out_f32 ? 4 : 2)) % 16 == 0,
               "avs_gemm_bf16: C must be 16-byte aligned with a 16-byte-multiple pitch");
-  if (epi->flags & AVS_EPI_DGELU) AVS_REQUIRE(epi->aux_in != nullptr, "avs_gemm_bf16: DGELU needs aux_in");
+  if (epi->flags & (AVS_EPI_DGELU | AVS_EPI_MUL_AUX))
+    AVS_REQUIRE(epi->aux_in != nullptr, "avs_gemm_bf16: DGELU / MUL_AUX need aux_in");
+  AVS_REQUIRE(!((epi->flags & AVS_EPI_DGELU) && (epi->flags & AVS_EPI_MUL_AUX)), "avs_gemm_bf16: DGELU and MUL_AUX exclude each other");
+  if (epi->flags & AVS_EPI_AUX_GRAD)
+    AVS_REQUIRE((epi->flags & AVS_EPI_GELU) && epi->aux_out, "avs_gemm_bf16: AUX_GRAD needs GELU and aux_out");
   if (epi->bias) AVS_REQUIRE((reinterpret_cast<uintptr_t>(epi->bias) & 15) == 0, "avs_gemm_bf16: bias alignment");
   if (epi->rowadd) AVS_REQUIRE(epi->rowadd_rows > 0, "avs_gemm_bf16: rowadd_rows must be > 0");
   AVS_REQUIRE(!epi->colsum || !out_f32, "avs_gemm_bf16: colsum needs a bf16 output");
@@ -192,9 +196,10 @@ extern "C" int avs_gemm_bf16(const void* A, long long lda, int a_major, const vo
   const void* in_ptr = nullptr;
   long long in_ld = 0;
   if (tma_epi) {
-    AVS_REQUIRE(!(epi->resid && (epi->flags & AVS_EPI_DGELU)), "avs_gemm_bf16: resid and DGELU cannot be combined");
+    AVS_REQUIRE(!(epi->resid && (epi->flags & (AVS_EPI_DGELU | AVS_EPI_MUL_AUX))),
+                "avs_gemm_bf16: resid and DGELU / MUL_AUX cannot be combined");
     if ((rc = make_tmap_2d(&tm.c, C, M, N, ldc, 2 * GEMM_EPI_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if (epi->flags & AVS_EPI_DGELU) { in_ptr = epi->aux_in; in_ld = epi->ld_aux; }
+    if (epi->flags & (AVS_EPI_DGELU | AVS_EPI_MUL_AUX)) { in_ptr = epi->aux_in; in_ld = epi->ld_aux; }
     else if (epi->resid) { in_ptr = epi->resid; in_ld = epi->ld_resid; }
     if (in_ptr && (rc = make_tmap_2d(&tm.in, in_ptr, M, N, in_ld, GEMM_EPI_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B)))
       return rc;
@@ -202,7 +207,7 @@ extern "C" int avs_gemm_bf16(const void* A, long long lda, int a_major, const vo
         (rc = make_tmap_2d(&tm.aux, epi->aux_out, M, N, epi->ld_aux, 2 * GEMM_EPI_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_128B)))
       return rc;
   } else {
-    AVS_REQUIRE(!epi->resid && !(epi->flags & (AVS_EPI_GELU | AVS_EPI_DGELU)),
+    AVS_REQUIRE(!epi->resid && !(epi->flags & (AVS_EPI_GELU | AVS_EPI_DGELU | AVS_EPI_MUL_AUX)),
                 "avs_gemm_bf16: fp32 outputs support bias / rowadd / alpha only");
   }
 

@@ -24,6 +24,8 @@ enum {
   EPI_DGELU = 2,       // v = v * gelu'(aux_in)
   EPI_OUT_F32 = 4,     // C is fp32 (else bf16)
   EPI_OUT_ATOMIC = 8,  // C is fp32 and accumulated with red.global.add (split-K / grad accumulation)
+  EPI_AUX_GRAD = 16,   // with EPI_GELU: aux_out receives gelu'(pre) instead of pre
+  EPI_MUL_AUX = 32,    // v = v * aux_in  (aux_in holds the stored gelu'; the dGELU epilogue without the derivative math)
 };
 
 struct GemmEpilogue {
@@ -392,15 +394,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           // staging tiles) comes as late as possible so that it overlaps this chunk's math.
           uint4 ax[4];
           if (ep.flags & EPI_GELU) {
-            if (args.has_aux_out) {
+            if (args.has_aux_out && (ep.flags & EPI_AUX_GRAD)) {
+              // the derivative is evaluated here, where the tanh is already paid for, and stored instead of the
+              // pre-activation: the dgrad GEMM of fc2 then only multiplies
+              float dg[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) gelu_and_grad(v[j], v[j], dg[j]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                ax[j].x = pack_bf16x2(v[8 * j], v[8 * j + 1]); ax[j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                ax[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); ax[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                ax[j].x = pack_bf16x2(dg[8 * j], dg[8 * j + 1]); ax[j].y = pack_bf16x2(dg[8 * j + 2], dg[8 * j + 3]);
+                ax[j].z = pack_bf16x2(dg[8 * j + 4], dg[8 * j + 5]); ax[j].w = pack_bf16x2(dg[8 * j + 6], dg[8 * j + 7]);
               }
-            }
+            } else {
+              if (args.has_aux_out) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                for (int j = 0; j < 4; ++j) {
+                  ax[j].x = pack_bf16x2(v[8 * j], v[8 * j + 1]); ax[j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                  ax[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); ax[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            }
           }
           uint4 in4[4];
           if (has_in) {
@@ -411,7 +426,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             __syncwarp();                     // every lane has read its row: the tile may be refilled
             if (lane == 0) issue_in(q + 2);
           }
-          if (ep.flags & EPI_DGELU) {
+          if (ep.flags & EPI_MUL_AUX) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 f;
+              f = unpack_bf16x2(in4[j].x); v[8 * j] *= f.x; v[8 * j + 1] *= f.y;
+              f = unpack_bf16x2(in4[j].y); v[8 * j + 2] *= f.x; v[8 * j + 3] *= f.y;
+              f = unpack_bf16x2(in4[j].z); v[8 * j + 4] *= f.x; v[8 * j + 5] *= f.y;
+              f = unpack_bf16x2(in4[j].w); v[8 * j + 6] *= f.x; v[8 * j + 7] *= f.y;
+            }
+          } else if (ep.flags & EPI_DGELU) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float2 f;
@@ -425,7 +449,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
           }
-          if (has_in && !(ep.flags & EPI_DGELU)) {  // residual add
+          if (has_in && !(ep.flags & (EPI_DGELU | EPI_MUL_AUX))) {  // residual add
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float2 f;

@@ -169,6 +169,8 @@ class Engine:
         self.d = dims
         self.dev = arena.device
         self.fuse_fc1_bias = os.environ.get("AVS_FUSE_FC1_BIAS", "1") != "0"   # A/B switch
+        # fc1's epilogue stores gelu'(pre) instead of pre, fc2's dgrad epilogue multiplies by it (A/B switch)
+        self.store_gelu_grad = os.environ.get("AVS_STORE_GELU_GRAD", "1") != "0"
 
     # -------------------------------------------------------------------------------------------- helpers
     def _empty(self, *shape, dtype=BF16) -> torch.Tensor:
@@ -184,13 +186,14 @@ class Engine:
 
     def _linear_bwd(self, dy: torch.Tensor, x_in: torch.Tensor, wname: str, bname: str, M: int, n_out: int, k_in: int,
                     dx_out: Optional[torch.Tensor], dgelu_aux: Optional[torch.Tensor] = None, alpha: float = 1.0,
-                    skip_bias: bool = False, dx_colsum: Optional[torch.Tensor] = None):
+                    skip_bias: bool = False, dx_colsum: Optional[torch.Tensor] = None,
+                    mul_aux: Optional[torch.Tensor] = None):
         """dgrad (optional), wgrad and bias-grad of y = x W^T + b. No transposes: see gemm_sm100.cuh.
         `dx_colsum` (fp32 [k_in]): += column sums of dx, accumulated in the dgrad GEMM's epilogue — the bias gradient of
         the Linear whose output gradient dx is (fc1, when this is fc2's dgrad with the dGELU epilogue)."""
         if dx_out is not None:
             ops.gemm(dy, self._w2d(wname), dx_out, M, k_in, n_out, b_major=MAJOR_MN, dgelu_aux=dgelu_aux,
-                     colsum=dx_colsum)
+                     colsum=dx_colsum, mul_aux=mul_aux)
         ops.gemm(dy, x_in, self._g2d(wname), n_out, k_in, M, a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
                  split_k=0, alpha=alpha)
         if not skip_bias:
@@ -299,8 +302,9 @@ class Engine:
         ln2, mean2, rstd2 = self._empty(M, D), self._empty(M, dtype=F32), self._empty(M, dtype=F32)
         self._ln_fwd_groups(x1, ln2, mean2, rstd2, groups, pfx, "norm2", D)
         hpre, hact = self._empty(M, Hid), self._empty(M, Hid)
+        sg = self.store_gelu_grad    # hpre then holds gelu'(fc1 output), not the fc1 output itself
         ops.gemm(ln2, self._w2d(pfx + "mlp.fc1.weight"), hact, M, Hid, D, bias=self.P.f32(pfx + "mlp.fc1.bias"),
-                 gelu=True, aux_out=hpre)
+                 gelu=True, aux_out=hpre, aux_grad=sg)
         out = Act(self._empty(M, D))
         out.bias_sink = self.P.grad(pfx + "mlp.fc2.bias")
         ops.gemm(hact, self._w2d(pfx + "mlp.fc2.weight"), out.t, M, D, Hid, bias=self.P.f32(pfx + "mlp.fc2.bias"),
@@ -310,7 +314,8 @@ class Engine:
                 dx2 = out.g
                 dh = self._empty(M, Hid)
                 fuse = self.fuse_fc1_bias
-                self._linear_bwd(dx2, hact, pfx + "mlp.fc2.weight", pfx + "mlp.fc2.bias", M, D, Hid, dh, dgelu_aux=hpre,
+                self._linear_bwd(dx2, hact, pfx + "mlp.fc2.weight", pfx + "mlp.fc2.bias", M, D, Hid, dh,
+                                 dgelu_aux=None if sg else hpre, mul_aux=hpre if sg else None,
                                  skip_bias=out.sink_done,
                                  dx_colsum=self.P.grad(pfx + "mlp.fc1.bias") if fuse else None)
                 dln2 = self._empty(M, D)

@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import EPI_DGELU, EPI_GELU, EPI_OUT_ATOMIC, EPI_OUT_F32, GemmEpilogue
+from ._lib import EPI_AUX_GRAD, EPI_DGELU, EPI_GELU, EPI_MUL_AUX, EPI_OUT_ATOMIC, EPI_OUT_F32, GemmEpilogue
 
 MAJOR_K, MAJOR_MN = 0, 1
 BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
@@ -48,8 +48,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, M: int, N: int, K:
          aux_out: Optional[torch.Tensor] = None, dgelu_aux: Optional[torch.Tensor] = None,
          resid: Optional[torch.Tensor] = None, rowadd: Optional[torch.Tensor] = None,
          rowidx: Optional[torch.Tensor] = None, alpha: float = 1.0, accumulate: bool = False, split_k: int = 1,
-         colsum: Optional[torch.Tensor] = None):
-    """out[M,N] = epi(sum_k A(m,k) B(n,k)); see avs_gemm_bf16. `a`/`b` are 2-D bf16 views (row pitch = stride(0))."""
+         colsum: Optional[torch.Tensor] = None, aux_grad: bool = False, mul_aux: Optional[torch.Tensor] = None):
+    """out[M,N] = epi(sum_k A(m,k) B(n,k)); see avs_gemm_bf16. `a`/`b` are 2-D bf16 views (row pitch = stride(0)).
+    gelu + aux_out: aux_out receives the pre-activation, or gelu'(pre) with aux_grad=True; mul_aux: out = acc * mul_aux
+    (the stored derivative) — the pair replaces aux_out=pre / dgelu_aux=pre with one multiply in the backward epilogue."""
     _chk(a, BF16, "gemm.a", contiguous=False)
     _chk(b, BF16, "gemm.b", contiguous=False)
     lda, ldb = _row_major_2d(a, "gemm.a"), _row_major_2d(b, "gemm.b")
@@ -71,6 +73,16 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, M: int, N: int, K:
         if aux_out is not None:
             _chk(aux_out, BF16, "gemm.aux_out", contiguous=False)
             ep.aux_out, ep.ld_aux = aux_out.data_ptr(), _row_major_2d(aux_out, "gemm.aux_out")
+    if aux_grad:
+        if not (gelu and aux_out is not None):
+            raise RuntimeError("gemm: aux_grad needs gelu=True and aux_out")
+        flags |= EPI_AUX_GRAD
+    if mul_aux is not None:
+        if dgelu_aux is not None:
+            raise RuntimeError("gemm: mul_aux and dgelu_aux exclude each other")
+        flags |= EPI_MUL_AUX
+        _chk(mul_aux, BF16, "gemm.mul_aux", contiguous=False)
+        ep.aux_in, ep.ld_aux = mul_aux.data_ptr(), _row_major_2d(mul_aux, "gemm.mul_aux")
     if dgelu_aux is not None:
         flags |= EPI_DGELU
         _chk(dgelu_aux, BF16, "gemm.dgelu_aux", contiguous=False)
@@ -463,7 +475,7 @@ def _work_attn_bwd(qkv, out, dout, lse2, delta, dqkv, n_seq, S, H, hd, dbias=Non
 
 def _detail_gemm(a, b, out, M, N, K, **kw):
     tag = "".join(c for c, f in (("b", kw.get("bias") is not None), ("g", kw.get("gelu")), ("r", kw.get("resid") is not None),
-                                  ("d", kw.get("dgelu_aux") is not None), ("p", kw.get("rowadd") is not None),
+                                  ("d", kw.get("dgelu_aux") is not None or kw.get("mul_aux") is not None), ("p", kw.get("rowadd") is not None),
                                   ("A", kw.get("accumulate"))) if f)
     return f"gemm M={M} N={N} K={K} maj={kw.get('a_major', 0)}{kw.get('b_major', 0)} {tag}"
 

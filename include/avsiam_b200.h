@@ -45,7 +45,9 @@ enum {
   AVS_EPI_GELU = 1,       /* v = gelu_erf(v); aux_out (optional) receives the pre-activation (bf16) */
   AVS_EPI_DGELU = 2,      /* v = v * gelu'(aux_in) */
   AVS_EPI_OUT_F32 = 4,    /* C is fp32 */
-  AVS_EPI_OUT_ATOMIC = 8  /* C is fp32, accumulated in place (split-K, gradient accumulation) */
+  AVS_EPI_OUT_ATOMIC = 8, /* C is fp32, accumulated in place (split-K, gradient accumulation) */
+  AVS_EPI_AUX_GRAD = 16,  /* with AVS_EPI_GELU: aux_out receives gelu'(pre) (bf16) instead of the pre-activation */
+  AVS_EPI_MUL_AUX = 32    /* v = v * aux_in: the dGELU epilogue when aux_in already holds gelu'(pre) */
 };
 typedef struct {
   int flags;

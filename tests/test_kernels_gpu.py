@@ -72,6 +72,31 @@ def test_gemm_dgrad_dgelu_and_wgrad_accumulate():
     assert rel_err(dw, ref) < 1e-4           # fp32 accumulate of exact bf16 products
 
 
+def test_gemm_stored_gelu_derivative_pair():
+    """fc1's epilogue stores gelu'(pre) instead of pre (aux_grad), fc2's dgrad epilogue multiplies by it (mul_aux): the
+    pair must reproduce gelu / dgelu of the exact-erf GELU (timm Mlp at cav_mae_base.py:138-143)."""
+    M, N, K = 708, 2048, 512
+    x, w = rnd(M, K, dtype=torch.bfloat16), rnd(N, K, scale=K ** -0.5, dtype=torch.bfloat16)
+    bias = rnd(N)
+    act = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    dact = torch.empty_like(act)
+    ops.gemm(x, w, act, M, N, K, bias=bias, gelu=True, aux_out=dact, aux_grad=True)
+    pre = (x.float() @ w.float().t() + bias).requires_grad_(True)
+    ref = F.gelu(pre)
+    ref.sum().backward()
+    assert rel_err(act, ref) < 6e-3
+    assert rel_err(dact, pre.grad) < 6e-3                       # gelu'(pre), bf16 rounding dominates
+    dy, w2 = rnd(M, K, dtype=torch.bfloat16), rnd(K, N, scale=K ** -0.5, dtype=torch.bfloat16)
+    dh = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    cs = torch.zeros(N, device=DEV)
+    ops.gemm(dy, w2, dh, M, N, K, b_major=ops.MAJOR_MN, mul_aux=dact, colsum=cs)
+    want = (dy.float() @ w2.float()) * dact.float()
+    assert rel_err(dh, want) < 6e-3
+    assert torch.allclose(cs, want.sum(0), rtol=2e-3, atol=2e-2 * math.sqrt(M))
+    with pytest.raises(RuntimeError):
+        ops.gemm(dy, w2, dh, M, N, K, b_major=ops.MAJOR_MN, mul_aux=dact, dgelu_aux=dact)
+
+
 def test_gemm_rejects_bad_input():
     a = rnd(8, 60, dtype=torch.bfloat16)  # pitch 60 not a multiple of 8
     w = rnd(16, 60, dtype=torch.bfloat16)

@@ -18,9 +18,13 @@ def load(path):
     return l
 
 
-def gemm(l, a, b, c, M, N, K, b_major=0, bias=None, gelu=False, aux_out=None, resid=None, dgelu_aux=None, colsum=None):
+def gemm(l, a, b, c, M, N, K, b_major=0, bias=None, gelu=False, aux_out=None, resid=None, dgelu_aux=None, colsum=None,
+         aux_grad=False, mul_aux=None):
     e = GemmEpilogue()
-    e.flags = (EPI_GELU if gelu else 0) | (EPI_DGELU if dgelu_aux is not None else 0)
+    e.flags = (EPI_GELU if gelu else 0) | (EPI_DGELU if dgelu_aux is not None else 0) | (16 if aux_grad else 0) | \
+              (32 if mul_aux is not None else 0)
+    if mul_aux is not None:
+        dgelu_aux = mul_aux
     e.alpha = 1.0
     e.bias = bias.data_ptr() if bias is not None else None
     e.resid = resid.data_ptr() if resid is not None else None
@@ -32,7 +36,8 @@ def gemm(l, a, b, c, M, N, K, b_major=0, bias=None, gelu=False, aux_out=None, re
     e.colsum = colsum.data_ptr() if colsum is not None else None
     rc = l.avs_gemm_bf16(a.data_ptr(), a.stride(0), 0, b.data_ptr(), b.stride(0), b_major, c.data_ptr(), c.stride(0), M, N,
                          K, ctypes.byref(e), 1, torch.cuda.current_stream().cuda_stream)
-    assert rc == 0, l.avs_last_error()
+    if rc != 0:
+        raise RuntimeError(l.avs_last_error())
 
 
 def t(fn, n=12):
@@ -70,6 +75,9 @@ for (M, N, K, name) in [(181248, 2048, 512, "dec"), (45312, 3072, 768, "enc")]:
         "fc1 resid": lambda l: gemm(l, x, w, out, M, N, K, bias=bias, resid=pre),
         "fc2 dgrad dgelu": lambda l: gemm(l, dy, w2, dh, M, N, K, b_major=1, dgelu_aux=pre),
         "fc2 dgrad dgelu+colsum": lambda l: gemm(l, dy, w2, dh, M, N, K, b_major=1, dgelu_aux=pre, colsum=cs),
+        "fc1 gelu+GRADaux (new)": lambda l: gemm(l, x, w, out, M, N, K, bias=bias, gelu=True, aux_out=dh, aux_grad=True),
+        "fc2 dgrad MULaux (new)": lambda l: gemm(l, dy, w2, dh, M, N, K, b_major=1, mul_aux=pre),
+        "fc2 dgrad MULaux+colsum": lambda l: gemm(l, dy, w2, dh, M, N, K, b_major=1, mul_aux=pre, colsum=cs),
         "fc2 fwd bias+resid": lambda l: gemm(l, pre, wf2, o2, M, K, N, bias=b2, resid=res),
         "fc2 fwd bias": lambda l: gemm(l, pre, wf2, o2, M, K, N, bias=b2),
     }
@@ -77,6 +85,9 @@ for (M, N, K, name) in [(181248, 2048, 512, "dec"), (45312, 3072, 768, "enc")]:
         cells = []
         for rep in range(2):
             for p, l in libs:
-                ms = t(lambda: fn(l))
-                cells.append(f"{ms:.3f}")
+                try:
+                    ms = t(lambda: fn(l))
+                    cells.append(f"{ms:.3f}")
+                except RuntimeError:
+                    cells.append("  n/a")
         print(f"{name} M={M} N={N} K={K} {k:24s}: " + " | ".join(cells) + "   (lib order repeated twice)", flush=True)
