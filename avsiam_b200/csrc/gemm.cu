@@ -112,12 +112,12 @@ int avs_make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, long long rows, lon
                       swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int AM, int BM, int BN>
+template <int AM, int BM, int BN, int EPI>
 static int launch_gemm(const GemmMaps& tm, GemmArgs& args, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;  // idempotent; benign race
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<AM, BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<AM, BM, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GEMM_SMEM_LIMIT);
     if (e != cudaSuccess) {
       avs_set_error("cudaFuncSetAttribute(gemm smem=%d): %s", GEMM_SMEM_LIMIT, cudaGetErrorString(e));
@@ -126,10 +126,22 @@ static int launch_gemm(const GemmMaps& tm, GemmArgs& args, int grid, cudaStream_
     attr_set = true;
   }
   const int epw = Cfg::epi_bytes_per_warp(args.tma_epi, args.has_in, args.has_aux_out);
-  args.stages = Cfg::pick_stages(epw);
-  const int smem = Cfg::smem_bytes(args.stages, epw);
-  gemm_bf16_kernel<AM, BM, BN><<<grid, GEMM_THREADS, smem, stream>>>(tm.a, tm.b, tm.c, tm.in, tm.aux, args);
+  const int extra = (EPI == GEMM_E_MUL) ? GEMM_COLSUM_BYTES : 0;
+  args.stages = Cfg::pick_stages(epw, extra);
+  const int smem = Cfg::smem_bytes(args.stages, epw, extra);
+  gemm_bf16_kernel<AM, BM, BN, EPI><<<grid, GEMM_THREADS, smem, stream>>>(tm.a, tm.b, tm.c, tm.in, tm.aux, args);
   return avs_check_launch("gemm_bf16_kernel");
+}
+
+template <int AM, int BM, int BN>
+static int launch_gemm_class(int cls, const GemmMaps& tm, GemmArgs& args, int grid, cudaStream_t stream) {
+  switch (cls) {
+    case GEMM_E_PLAIN: return launch_gemm<AM, BM, BN, GEMM_E_PLAIN>(tm, args, grid, stream);
+    case GEMM_E_GELU: return launch_gemm<AM, BM, BN, GEMM_E_GELU>(tm, args, grid, stream);
+    case GEMM_E_RESID: return launch_gemm<AM, BM, BN, GEMM_E_RESID>(tm, args, grid, stream);
+    case GEMM_E_MUL: return launch_gemm<AM, BM, BN, GEMM_E_MUL>(tm, args, grid, stream);
+    default: return launch_gemm<AM, BM, BN, GEMM_E_F32>(tm, args, grid, stream);
+  }
 }
 
 extern "C" int avs_gemm_bf16(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major,
@@ -151,7 +163,15 @@ extern "C" int avs_gemm_bf16(const void* A, long long lda, int a_major, const vo
     AVS_REQUIRE((epi->flags & AVS_EPI_GELU) && epi->aux_out, "avs_gemm_bf16: AUX_GRAD needs GELU and aux_out");
   if (epi->bias) AVS_REQUIRE((reinterpret_cast<uintptr_t>(epi->bias) & 15) == 0, "avs_gemm_bf16: bias alignment");
   if (epi->rowadd) AVS_REQUIRE(epi->rowadd_rows > 0, "avs_gemm_bf16: rowadd_rows must be > 0");
-  AVS_REQUIRE(!epi->colsum || !out_f32, "avs_gemm_bf16: colsum needs a bf16 output");
+  // epilogue class (one kernel instantiation each; gemm_sm100.cuh)
+  const int cls = out_f32 ? GEMM_E_F32
+                  : (epi->flags & AVS_EPI_GELU) ? GEMM_E_GELU
+                  : (epi->flags & (AVS_EPI_DGELU | AVS_EPI_MUL_AUX)) ? GEMM_E_MUL
+                  : epi->resid ? GEMM_E_RESID : GEMM_E_PLAIN;
+  AVS_REQUIRE(!epi->colsum || cls == GEMM_E_MUL, "avs_gemm_bf16: colsum is fused into the DGELU / MUL_AUX epilogues only");
+  AVS_REQUIRE(!epi->rowadd || cls == GEMM_E_PLAIN || cls == GEMM_E_F32,
+              "avs_gemm_bf16: rowadd combines with bias / alpha only (patch-embed epilogue)");
+  AVS_REQUIRE(!(epi->resid && cls == GEMM_E_GELU), "avs_gemm_bf16: GELU and resid cannot be combined");
 
   const int BN = (N > 128) ? 256 : 128;
   const int m_tiles = ceil_div(M, GEMM_BLOCK_M), n_tiles = ceil_div(N, BN);
@@ -237,12 +257,12 @@ extern "C" int avs_gemm_bf16(const void* A, long long lda, int a_major, const vo
   const int grid = num_tiles < sms ? num_tiles : sms;
   const int key = a_major * 2 + b_major;
   if (BN == 256) {
-    if (key == 0) return launch_gemm<MAJOR_K, MAJOR_K, 256>(tm, args, grid, stream);
-    if (key == 1) return launch_gemm<MAJOR_K, MAJOR_MN, 256>(tm, args, grid, stream);
-    return launch_gemm<MAJOR_MN, MAJOR_MN, 256>(tm, args, grid, stream);
+    if (key == 0) return launch_gemm_class<MAJOR_K, MAJOR_K, 256>(cls, tm, args, grid, stream);
+    if (key == 1) return launch_gemm_class<MAJOR_K, MAJOR_MN, 256>(cls, tm, args, grid, stream);
+    return launch_gemm_class<MAJOR_MN, MAJOR_MN, 256>(cls, tm, args, grid, stream);
   } else {
-    if (key == 0) return launch_gemm<MAJOR_K, MAJOR_K, 128>(tm, args, grid, stream);
-    if (key == 1) return launch_gemm<MAJOR_K, MAJOR_MN, 128>(tm, args, grid, stream);
-    return launch_gemm<MAJOR_MN, MAJOR_MN, 128>(tm, args, grid, stream);
+    if (key == 0) return launch_gemm_class<MAJOR_K, MAJOR_K, 128>(cls, tm, args, grid, stream);
+    if (key == 1) return launch_gemm_class<MAJOR_K, MAJOR_MN, 128>(cls, tm, args, grid, stream);
+    return launch_gemm_class<MAJOR_MN, MAJOR_MN, 128>(cls, tm, args, grid, stream);
   }
 }

@@ -28,6 +28,18 @@ enum {
   EPI_MUL_AUX = 32,    // v = v * aux_in  (aux_in holds the stored gelu'; the dGELU epilogue without the derivative math)
 };
 
+// Epilogue class = template parameter of the kernel: every instantiation carries only the code of its own epilogue.
+// With all variants behind run-time flags in one kernel (6.7 k SASS instructions, 107 KB) the shapes whose epilogue is the
+// bound ran 8 % slower than with the 5.7 k-instruction kernel that lacked two of the variants — the epilogue loop no
+// longer fitted the instruction cache next to the producer / issuer code.
+enum {
+  GEMM_E_PLAIN = 0,   // bf16 out: bias, row table, alpha
+  GEMM_E_GELU = 1,    // bf16 out: bias + GELU, optional second output (pre-activation or gelu')
+  GEMM_E_RESID = 2,   // bf16 out: bias + residual input stream
+  GEMM_E_MUL = 3,     // bf16 out: product with an input stream (stored gelu', or gelu'(pre) evaluated here), column sums
+  GEMM_E_F32 = 4,     // fp32 out (overwrite or red.global.add): wgrad / split-K
+};
+
 struct GemmEpilogue {
   int flags;
   float alpha;          // final scale (before the residual add)
@@ -70,7 +82,8 @@ constexpr int GEMM_EPI_BUF = 32 * GEMM_EPI_CHUNK * 2;  // one [32 rows x 32 cols
 // unit turns each box row into one L2 write request, so 64-byte rows (the 32-column tiles of v2) made the stores —
 // 2048 row requests per 128x256 tile — the bound of every bf16-output GEMM (ncu: MMA warp polling tmem_empty).
 constexpr int GEMM_OUT_BUF = 32 * 64 * 2;
-constexpr int GEMM_SMEM_LIMIT = 226 * 1024;   // dynamic part; 1 KB of static shared memory holds the column-sum accumulators
+constexpr int GEMM_SMEM_LIMIT = 226 * 1024;   // dynamic shared memory per CTA
+constexpr int GEMM_COLSUM_BYTES = 2 * 4 * 256 * 4;   // [tile parity][lane quarter][column] fp32, behind the barriers
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -85,12 +98,12 @@ struct GemmCfg {
   static __host__ __device__ int epi_bytes_per_warp(int tma_epi, int has_in, int has_aux_out) {
     return tma_epi ? GEMM_EPI_BUF * (has_in ? 2 : 0) + GEMM_OUT_BUF * (1 + (has_aux_out ? 1 : 0)) : 0;
   }
-  static __host__ int pick_stages(int epi_per_warp) {
-    int s = (GEMM_SMEM_LIMIT - 1024 - BAR_BYTES - GEMM_EPI_WARPS * epi_per_warp) / STAGE_BYTES;
+  static __host__ int pick_stages(int epi_per_warp, int extra = 0) {
+    int s = (GEMM_SMEM_LIMIT - 1024 - BAR_BYTES - extra - GEMM_EPI_WARPS * epi_per_warp) / STAGE_BYTES;
     return s > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : s;
   }
-  static __host__ int smem_bytes(int stages, int epi_per_warp) {
-    return stages * STAGE_BYTES + GEMM_EPI_WARPS * epi_per_warp + 1024 + BAR_BYTES;
+  static __host__ int smem_bytes(int stages, int epi_per_warp, int extra = 0) {
+    return stages * STAGE_BYTES + GEMM_EPI_WARPS * epi_per_warp + 1024 + BAR_BYTES + extra;
   }
 };
 
@@ -126,12 +139,14 @@ __device__ __forceinline__ uint32_t epi_tile_off(int r, int j) { return (uint32_
 // byte offset of 16-byte chunk `j` (0..7) of row `r` inside a [32 x 64] bf16 output staging tile, SWIZZLE_128B
 __device__ __forceinline__ uint32_t out_tile_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
-template <int A_MAJOR, int B_MAJOR, int BLOCK_N>
+template <int A_MAJOR, int B_MAJOR, int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_in,
                  const __grid_constant__ CUtensorMap tma_aux, const GemmArgs args) {
   using Cfg = GemmCfg<BLOCK_N>;
+  constexpr bool TMA_EPI = EPI != GEMM_E_F32;                        // bf16 outputs leave through TMA stores
+  constexpr bool HAS_IN = EPI == GEMM_E_RESID || EPI == GEMM_E_MUL;  // a bf16 [M, N] input tile stream exists
   const int STAGES = args.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -158,10 +173,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
-    if (args.tma_epi) {
+    if (TMA_EPI) {
       tma_prefetch_desc(&tma_c);
-      if (args.has_in) tma_prefetch_desc(&tma_in);
-      if (args.has_aux_out) tma_prefetch_desc(&tma_aux);
+      if (HAS_IN) tma_prefetch_desc(&tma_in);
+      if (EPI == GEMM_E_GELU && args.has_aux_out) tma_prefetch_desc(&tma_aux);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -284,24 +299,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // ============================ epilogue (8 warps) ============================
     // warp w may only touch TMEM lanes 32*(w%4)..+32; the two warps sharing a quarter split the tile's columns.
     const int ew = warp - 2;
-    // column sums of the output (the bias gradient of the upstream Linear), accumulated per CTA and tile in shared
-    // memory and flushed with one global atomic per column and tile
-    __shared__ float s_colsum[256];
-    if (args.epi.colsum != nullptr) {
-      s_colsum[ew * 32 + lane] = 0.f;
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");
-    }
+    // column sums of the output (the bias gradient of the upstream Linear): every epilogue warp writes the sums over
+    // its 32 rows into its lane quarter's slot [tile parity][quarter][column] (plain stores — shared-memory float
+    // atomics are compare-and-swap loops), one barrier per tile, then one global atomic per column and tile
+    float* s_colsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);   // [2][4][256]
     const int quarter = warp & 3;
     const int half = ew >> 2;
     constexpr int CH = BLOCK_N / (2 * GEMM_EPI_CHUNK);  // chunks per warp per tile
     const GemmEpilogue& ep = args.epi;
     uint8_t* my_epi = smem_epi + ew * epi_per_warp;
     uint8_t* in_buf = my_epi;                                        // [2][2 KB] when has_in
-    uint8_t* out_buf = my_epi + (args.has_in ? 2 * GEMM_EPI_BUF : 0);   // 1024-byte aligned (128 B swizzle pattern)
+    uint8_t* out_buf = my_epi + (HAS_IN ? 2 * GEMM_EPI_BUF : 0);   // 1024-byte aligned (128 B swizzle pattern)
     uint8_t* aux_buf = out_buf + GEMM_OUT_BUF;
     uint64_t* my_in_bar = in_bar + 2 * ew;
-    const bool tma_epi = args.tma_epi != 0;
-    const bool has_in = tma_epi && args.has_in;
+    constexpr bool tma_epi = TMA_EPI;
+    constexpr bool has_in = HAS_IN;
 
     // flat per-warp chunk sequence q = tile_iteration * CH + chunk; `in` tiles are prefetched two chunks ahead
 #ifdef AVS_GEMM_DEBUG
@@ -329,6 +341,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     int q = 0;
+    int tile_par = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int ks = t % args.split_k;
       const int mn = t / args.split_k;
@@ -339,7 +352,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < args.M;
       const float* rowadd_ptr = nullptr;
-      if (ep.rowadd != nullptr && row_ok) {
+      if ((EPI == GEMM_E_PLAIN || EPI == GEMM_E_F32) && ep.rowadd != nullptr && row_ok) {
         const int ri = ep.rowidx ? ep.rowidx[row] : (row % ep.rowadd_rows);
         rowadd_ptr = ep.rowadd + (long long)ri * args.N;
       }
@@ -379,7 +392,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
           }
         }
-        if (rowadd_ptr != nullptr && lead_split && col_ok) {
+        if ((EPI == GEMM_E_PLAIN || EPI == GEMM_E_F32) && rowadd_ptr != nullptr && lead_split && col_ok) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             if (full || nc + j < args.N) {
@@ -388,12 +401,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
           }
         }
-        if (tma_epi) {
+        if constexpr (tma_epi) {
           // ---------------- bf16 outputs: staged in smem, moved by TMA ----------------
           // Everything is computed in registers first; the wait for the previous chunk's TMA stores (they read the
           // staging tiles) comes as late as possible so that it overlaps this chunk's math.
           uint4 ax[4];
-          if (ep.flags & EPI_GELU) {
+          if constexpr (EPI == GEMM_E_GELU) {
             if (args.has_aux_out && (ep.flags & EPI_AUX_GRAD)) {
               // the derivative is evaluated here, where the tanh is already paid for, and stored instead of the
               // pre-activation: the dgrad GEMM of fc2 then only multiplies
@@ -418,7 +431,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
           }
           uint4 in4[4];
-          if (has_in) {
+          if constexpr (has_in) {
             if (!dbg_no_in) mbar_wait(&my_in_bar[q & 1], (uint32_t)((q >> 1) & 1));
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -426,7 +439,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             __syncwarp();                     // every lane has read its row: the tile may be refilled
             if (lane == 0) issue_in(q + 2);
           }
-          if (ep.flags & EPI_MUL_AUX) {
+          if constexpr (EPI == GEMM_E_MUL) {
+           if (ep.flags & EPI_MUL_AUX) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float2 f;
@@ -435,7 +449,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               f = unpack_bf16x2(in4[j].z); v[8 * j + 4] *= f.x; v[8 * j + 5] *= f.y;
               f = unpack_bf16x2(in4[j].w); v[8 * j + 6] *= f.x; v[8 * j + 7] *= f.y;
             }
-          } else if (ep.flags & EPI_DGELU) {
+           } else {   // EPI_DGELU
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float2 f;
@@ -444,12 +458,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               f = unpack_bf16x2(in4[j].z); v[8 * j + 4] *= dgelu_erf(f.x); v[8 * j + 5] *= dgelu_erf(f.y);
               f = unpack_bf16x2(in4[j].w); v[8 * j + 6] *= dgelu_erf(f.x); v[8 * j + 7] *= dgelu_erf(f.y);
             }
+           }
           }
           if (ep.alpha != 1.0f) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
           }
-          if (has_in && !(ep.flags & (EPI_DGELU | EPI_MUL_AUX))) {  // residual add
+          if constexpr (EPI == GEMM_E_RESID) {  // residual add
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float2 f;
@@ -459,12 +474,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               f = unpack_bf16x2(in4[j].w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
             }
           }
-          if (ep.colsum != nullptr) {
+          if (EPI == GEMM_E_MUL && ep.colsum != nullptr) {
             float cs[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) cs[j] = row_ok ? v[j] : 0.f;
             warp_colsum<32>(cs, lane);                  // lane L now holds the sum of column L over the warp's 32 rows
-            if (nc + lane < args.N) atomicAdd(&s_colsum[ccol + lane], cs[0]);
+            s_colsum[((tile_par * 4 + quarter) << 8) + ccol + lane] = cs[0];
           }
           uint4 o[4];
 #pragma unroll
@@ -477,7 +492,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if (lane == 0) bulk_wait_read0();  // the previous pair's stores have finished reading the staging tiles
             __syncwarp();
           }
-          if ((ep.flags & EPI_GELU) && args.has_aux_out) {
+          if (EPI == GEMM_E_GELU && args.has_aux_out) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(aux_buf + out_tile_off(lane, hsel * 4 + j)) = ax[j];
           }
@@ -490,7 +505,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               const int nc0 = nc - GEMM_EPI_CHUNK;   // first column of the pair
               if (nc0 < args.N && m0 + quarter * 32 < args.M && !dbg_no_store) {  // TMA clips the M / N tails
                 tma_store_2d(&tma_c, out_buf, nc0, m0 + quarter * 32);
-                if (args.has_aux_out) tma_store_2d(&tma_aux, aux_buf, nc0, m0 + quarter * 32);
+                if (EPI == GEMM_E_GELU && args.has_aux_out) tma_store_2d(&tma_aux, aux_buf, nc0, m0 + quarter * 32);
               }
               bulk_commit();
             }
@@ -514,14 +529,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
         }
       }
-      if (ep.colsum != nullptr) {
+      if (EPI == GEMM_E_MUL && ep.colsum != nullptr) {
         asm volatile("bar.sync 1, 256;\n" ::: "memory");      // every epilogue warp has added its rows of this tile
         const int et = ew * 32 + lane;
         if (et < BLOCK_N && n0 + et < args.N) {
-          atomicAdd(ep.colsum + n0 + et, s_colsum[et]);
-          s_colsum[et] = 0.f;
+          const float* sc = s_colsum + (tile_par << 10) + et;
+          atomicAdd(ep.colsum + n0 + et, (sc[0] + sc[256]) + (sc[512] + sc[768]));
         }
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        tile_par ^= 1;   // the next tile writes the other buffer: its barrier orders the one after against these reads
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;

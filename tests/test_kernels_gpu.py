@@ -35,11 +35,18 @@ def test_gemm_fwd_bias_gelu_resid(M, N, K):
     bias, res = rnd(N), rnd(M, N, dtype=torch.bfloat16)
     out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
     pre = torch.empty_like(out)
-    ops.gemm(a, w, out, M, N, K, bias=bias, gelu=True, aux_out=pre, resid=res)
     ref_pre = a.float() @ w.float().t() + bias
-    ref = F.gelu(ref_pre) + res.float()
+    ops.gemm(a, w, out, M, N, K, bias=bias, gelu=True, aux_out=pre)          # fc1: GELU class, second output = pre
     assert rel_err(pre, ref_pre) < 6e-3      # bf16 output rounding (2^-9) dominates
-    assert rel_err(out, ref) < 6e-3
+    assert rel_err(out, F.gelu(ref_pre)) < 6e-3
+    ops.gemm(a, w, out, M, N, K, bias=bias, gelu=True)                       # no second output
+    assert rel_err(out, F.gelu(ref_pre)) < 6e-3
+    ops.gemm(a, w, out, M, N, K, bias=bias, resid=res)                       # proj / fc2: residual class
+    assert rel_err(out, ref_pre + res.float()) < 6e-3
+    ops.gemm(a, w, out, M, N, K, bias=bias, alpha=0.5)                       # plain class
+    assert rel_err(out, 0.5 * ref_pre) < 6e-3
+    with pytest.raises(RuntimeError):                                        # one epilogue class per launch
+        ops.gemm(a, w, out, M, N, K, bias=bias, gelu=True, resid=res)
 
 
 def test_gemm_rowadd_alpha_patch_embed_epilogue():
