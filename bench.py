@@ -31,7 +31,29 @@ import torch  # noqa: E402
 
 METRIC = "AV pretrain samples/sec"
 UNIT = "samples/s"
-TRAIN_GFLOP_PER_SAMPLE = {"single_pass": 242.0, "two_pass": 474.0}   # BASELINE.md §4 (3 x forward)
+TRAIN_GFLOP_PER_SAMPLE = {"single_pass": 242.0, "two_pass": 474.0}   # BASELINE.md §4 (3 x forward), ViT-B/16
+# BASELINE config 5 geometries. ViT-H/14 (head_dim 80, patch 14) is not built: no attention tile
+# shape for head_dim 80 in this library.
+MODEL_DIMS = {"vit_b": {}, "vit_l": dict(embed_dim=1024, depth=24, heads=16, dec_depth=6)}
+
+
+def train_gflop_per_sample(dims, keep_a, keep_v):
+    """3 x forward FLOPs of the single-pass step (2 per multiply-add): encoder over the kept tokens, two fusion blocks,
+    decoder over all tokens, patch embedding and prediction heads; attention 4 S^2 hd per head."""
+    D, Dd, p = dims.embed_dim, dims.dec_dim, dims.patch
+
+    def block(tokens, seqs, width, heads):
+        gemm = 2.0 * tokens * width * width * 12            # qkv 3 + proj 1 + fc1 4 + fc2 4
+        attn = sum(4.0 * S * S * (width // heads) * heads for S in seqs)
+        return gemm + attn
+
+    enc_tokens = keep_a + keep_v
+    f = dims.depth * block(enc_tokens, [keep_a, keep_v], D, dims.heads)
+    f += 2 * block(enc_tokens, [enc_tokens], D, dims.heads)
+    f += dims.dec_depth * block(dims.Ta + dims.Tv, [dims.Ta + dims.Tv], Dd, dims.dec_heads)
+    f += 2.0 * keep_a * D * p * p + 2.0 * keep_v * D * p * p * dims.in_chans + 2.0 * enc_tokens * D * Dd
+    f += 2.0 * dims.Ta * Dd * p * p + 2.0 * dims.Tv * Dd * p * p * dims.in_chans
+    return 3.0 * f / 1e9
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}  # B200_PROFILING.md
 
 
@@ -172,7 +194,8 @@ def run_reference_arm(args):
 
 
 def workload_config(args, per_gpu_batch: int, world: int):
-    return {"workload": f"ViT-B/16 AVSiam pretrain step ({args.arrangement}), 1024x128 fbank + 1x224x224 frame, "
+    name = {"vit_b": "ViT-B/16", "vit_l": "ViT-L/16"}[getattr(args, "model", "vit_b")]
+    return {"workload": f"{name} AVSiam pretrain step ({args.arrangement}), 1024x128 fbank + 1x224x224 frame, "
                         f"mask 0.75, MAE + global-batch InfoNCE, Adam",
             "arrangement": args.arrangement, "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * world,
             "parallelism": f"dp{world}", "l2": "inputs (288 MB/step) and activations (>40 GB/step) exceed the 126 MB L2"}
@@ -191,7 +214,7 @@ def check_step0_loss(model, net, args, dev, rank, world, dist):
     own batch (InfoNCE over the all-gathered oracle embeddings when world > 1): the N-GPU bench refuses to report a
     number for a path whose loss is wrong. Returns (loss, oracle_loss)."""
     from oracle import avsiam_oracle as O
-    d = O.VIT_B
+    d = O.Dims(**MODEL_DIMS[args.model])
     B = min(args.batch, 16)          # bounded: the checker runs the fp32 oracle
     g = torch.Generator().manual_seed(4321 + rank)
     audio = torch.randn(B, d.audio_len, d.mel, generator=g).to(dev)
@@ -230,7 +253,7 @@ def time_library_baseline(args, dev, model, steps=3, warmup=2):
     on THIS B200, same batch, nothing recomputed. A reported comparator, never part of the product path."""
     from oracle import avsiam_oracle as O
     import torch.nn.functional as F
-    d = O.VIT_B
+    d = O.Dims(**MODEL_DIMS[args.model])
     B = args.batch
     torch.cuda.empty_cache()
     state = {k: v.requires_grad_(True) for k, v in oracle_state_from_model(model, dev).items()}
@@ -299,8 +322,9 @@ def run_gpu_arm(args):
     B = args.batch
 
     torch.manual_seed(0)                      # identical random-init weights on every rank
+    dims = avsiam_b200.Dims(**MODEL_DIMS[args.model]) if MODEL_DIMS[args.model] else None
     model = CAVMAE_BASE(audio_length=1024, norm_pix_loss=False, modality_specific_depth=23, tr_pos=False,
-                        arrangement=args.arrangement).to(dev)
+                        arrangement=args.arrangement, dims=dims).to(dev)
     with torch.no_grad():                     # the reference zero-inits these (cav_mae_base.py:312-337); any value works
         for n in ("mask_token", "decoder_pos_embed_a", "decoder_pos_embed_v", "decoder_modality_a", "decoder_modality_v"):
             getattr(model, n).normal_(std=0.02)
@@ -438,7 +462,7 @@ def run_gpu_arm(args):
     gemm_tflops = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
-    if os.path.exists(tpath) and args.arrangement == "single_pass" and B == 256:
+    if os.path.exists(tpath) and args.arrangement == "single_pass" and B == 256 and args.model == "vit_b":
         tj = json.load(open(tpath))
         traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     roofline = {
@@ -452,11 +476,16 @@ def run_gpu_arm(args):
     families = {k: {"ms": round(v["ms"], 3), "calls": v["calls"],
                     "rate": (v["work"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None)}
                 for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
-    step_util = (value / world) * TRAIN_GFLOP_PER_SAMPLE[args.arrangement] * 1e9 / (peaks["bf16_tflops"] * 1e12)
+    if args.model == "vit_b":
+        gflop_sample = TRAIN_GFLOP_PER_SAMPLE[args.arrangement]
+    else:
+        md = model.dims
+        gflop_sample = train_gflop_per_sample(md, int(md.Ta * 0.25), int(md.Tv * 0.25))
+    step_util = (value / world) * gflop_sample * 1e9 / (peaks["bf16_tflops"] * 1e12)
 
     # ---- (4) CPU baseline (rank 0, N=1 only): bounded sample of the same step on the host cores
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "vit_b":
         cores = torch.get_num_threads()
         sps, _ = time_cpu(args.arrangement, args.cpu_batch, 3, 1)
         cpu_baseline = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
@@ -486,7 +515,7 @@ def run_gpu_arm(args):
             "library_baseline": library_baseline,
             "step0_loss_check": None if step0 is None else {"loss": step0[0], "oracle_fp32": step0[1], "rtol": 1e-3},
             "tensor_pipe_util_vs_burst_peak": step_util,
-            "train_gflop_per_sample": TRAIN_GFLOP_PER_SAMPLE[args.arrangement],
+            "train_gflop_per_sample": gflop_sample,
             "kernel_families_ms": families,
             "loss": loss_val,
         }
@@ -504,6 +533,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE.json config 2: 256)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the CPU reference sample (config 1: 2)")
     ap.add_argument("--arrangement", default="single_pass", choices=["single_pass", "two_pass"])
+    ap.add_argument("--model", default="vit_b", choices=sorted(MODEL_DIMS), help="encoder geometry (config 5: vit_l)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-loss-check", action="store_true", help="skip the untimed step-0 loss check against the fp32 oracle")
     ap.add_argument("--no-library-baseline", dest="library_baseline", action="store_false",

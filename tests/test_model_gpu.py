@@ -455,3 +455,38 @@ def _roundtrip(obj):
     torch.save(obj, buf)
     buf.seek(0)
     return buf
+
+
+def test_vit_large_single_pass_against_fp32_oracle_on_gpu():
+    """BASELINE config 5, ViT-L/16 geometry (D 1024, depth 24, 16 heads of 64, decoder 512 x 6 x 16 heads,
+    512 / 196 tokens): the full-depth model in the single-pass arrangement against the fp32 oracle on the GPU — losses
+    1e-3, masks bit-exact, every parameter's gradient cosine >= 0.999."""
+    d = dataclasses.replace(O.VIT_B, embed_dim=1024, depth=24, heads=16, dec_depth=6, head_classes=64)
+    B = 8
+    torch.cuda.empty_cache()
+    model, _ = make_model(d, "single_pass")
+    sd = O.init_state(d, seed=0, skip_heads=True)
+    audio, imgs = synth_inputs(B, d, 91)
+    plan = O.make_mask_plan(B, d, 92, two_pass=False)
+    ref, state = run_oracle_gpu(O.forward_single_pass, audio, imgs, sd, d, plan, mae_loss_weight=1.0,
+                                contrast_loss_weight=0.01)
+    ref_vals = [float(r) for r in ref[:5]]
+    ref_masks = (ref[5].cpu(), ref[6].cpu())
+    ref_grads = {k: v.grad.detach().cpu() for k, v in state.items() if v.grad is not None}
+    del ref, state
+    torch.cuda.empty_cache()
+    model.mask_plan = plan
+    out = model(audio.to(DEV), imgs.to(DEV), 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+    check_losses(out, ref_vals)
+    assert torch.equal(out[5].cpu(), ref_masks[0]) and torch.equal(out[6].cpu(), ref_masks[1])
+    out[0].backward()
+    named = dict(model.named_parameters())
+    got = {k for k, p in named.items() if p.grad is not None}
+    assert got == set(ref_grads), (sorted(got - set(ref_grads))[:5], sorted(set(ref_grads) - got)[:5])
+    cosines = {k: cos(named[k].grad, g) for k, g in ref_grads.items() if float(g.norm()) > 1e-12}
+    low = sorted((c, k) for k, c in cosines.items() if c < GRAD_COS_MIN)
+    print(f"[parity ViT-L B={B}] losses {[float(o) for o in out[:5]]} vs {ref_vals}; worst gradient cosine "
+          f"{min(cosines.values()):.6f} over {len(cosines)} parameters")
+    assert not low, low[:8]
+    del model, out
+    torch.cuda.empty_cache()
