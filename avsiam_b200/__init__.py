@@ -12,8 +12,9 @@ from .stats import calculate_stats, d_prime  # noqa: F401
 from .ddp import B200DDP, GradSync  # noqa: F401
 from .gather_layer import GatherLayer  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
+from .graph import GraphedTrainStep  # noqa: F401
 
-__all__ = ["CAVMAE_BASE", "CAVMAEFT_BASE", "Dims", "GatherLayer", "wav2fbank", "calculate_stats", "d_prime", "FusedAdam", "B200DDP", "GradSync", "patch"]
+__all__ = ["CAVMAE_BASE", "CAVMAEFT_BASE", "Dims", "GatherLayer", "wav2fbank", "calculate_stats", "d_prime", "FusedAdam", "B200DDP", "GradSync", "GraphedTrainStep", "patch"]
 __version__ = "0.1.0"
 
 

@@ -360,7 +360,7 @@ class CAVMAE_BASE(nn.Module):
             holder = {"module": self, "tape": tape, "up": up, "used": used, "active": active, "key": key}
             la, lv, lc_raw = _TapeFn.apply(holder, la, lv, lc_raw, *[arena.params[n] for n in used])
         acc = acc.detach().clone()
-        zero = torch.tensor(0.0, device=dev)
+        zero = torch.zeros((), device=dev)
         if do_mae:
             loss_mae_a, loss_mae_v = la, lv
             loss_mae = loss_mae_a + loss_mae_v

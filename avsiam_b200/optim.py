@@ -46,6 +46,7 @@ class FusedAdam(torch.optim.Optimizer):
         if len(self.param_groups) > self.MAX_GROUPS:
             raise ValueError(f"FusedAdam supports at most {self.MAX_GROUPS} param_groups")
         self.decoupled = decoupled
+        self.capturable = False    # True: the step counter / bias corrections always live on the device (CUDA graphs)
         self._step = 0
         self._m: Optional[torch.Tensor] = None
         self._v: Optional[torch.Tensor] = None
@@ -136,6 +137,11 @@ class FusedAdam(torch.optim.Optimizer):
             found_inf.zero_()
             ops.found_inf(arena.grads[:n], found_inf)
             grad_scaler._per_optimizer_states[id(self)]["found_inf_per_device"] = {arena.device: found_inf}
+            if self._tick is None:
+                self._tick = torch.zeros(4, dtype=torch.int32, device=arena.device)
+                self._tick[0] = self._step
+            tick = self._tick
+        elif self.capturable:
             if self._tick is None:
                 self._tick = torch.zeros(4, dtype=torch.int32, device=arena.device)
                 self._tick[0] = self._step

@@ -342,7 +342,29 @@ def run_gpu_arm(args):
     dev_v = [t.to(dev) for t in host_v]
     h2d_bytes = host_a[0].numel() * 4 + host_v[0].numel() * 4
 
+    graphed = None
+    if args.graph and args.arrangement == "single_pass":
+        # forward + reverse pass + Adam as ONE CUDA graph (avsiam_b200.GraphedTrainStep); falls back to eager launches,
+        # and says so on the JSON line, if this torch / NCCL combination cannot capture the step
+        try:
+            graphed = avsiam_b200.GraphedTrainStep(net, opt1, 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+            graphed(torch.randn(B, 1024, 128, device=dev), torch.randn(B, 3, 224, 224, device=dev))
+            torch.cuda.synchronize()
+        except Exception as e:   # noqa: BLE001
+            print(f"bench.py: CUDA-graph capture unavailable ({type(e).__name__}: {str(e)[:200]}); eager launches", file=sys.stderr)
+            graphed = None
+            opt1.capturable = False
+
+    def eager_step(a, v):
+        out = net(a, v, 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+        opt1.zero_grad()
+        out[0].backward()
+        opt1.step()
+        return out[0]
+
     def train_step(a, v):
+        if graphed is not None:
+            return graphed(a, v)
         if args.arrangement == "single_pass":
             out = net(a, v, 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
             opt1.zero_grad()
@@ -389,7 +411,7 @@ def run_gpu_arm(args):
         loss = train_step(dev_a[i % n_host], dev_v[i % n_host])
     e1.record()
     barrier()
-    launches = ops.launch_count()
+    launches = ops.launch_count() if graphed is None else graphed.launches_per_step * args.steps   # graph kernel nodes
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     loss_val = float(loss)
@@ -400,7 +422,7 @@ def run_gpu_arm(args):
 
     if args.detail:      # developer aid: per-shape device time of one step, printed to stderr
         with ops.KernelTimer(detail=True) as kt:
-            train_step(dev_a[0], dev_v[0])
+            (eager_step if graphed is not None else train_step)(dev_a[0], dev_v[0])
         rows = sorted(kt.summary().items(), key=lambda kv: -kv[1]["ms"])
         for k, v in rows:
             rate = v["work"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0
@@ -455,7 +477,7 @@ def run_gpu_arm(args):
     # ---- (3) per-family device time of one more step (roofline of the dominant kernel family)
     peaks, peaks_src = load_peaks()
     with ops.KernelTimer() as kt:
-        train_step(dev_a[0], dev_v[0])
+        (eager_step if graphed is not None else train_step)(dev_a[0], dev_v[0])   # per-kernel events need eager launches
     fam = kt.summary()
     fam_total = sum(f["ms"] for f in fam.values())
     gemm = fam.get("gemm", {"ms": 0.0, "work": 0.0, "calls": 0})
@@ -509,6 +531,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
+            "cuda_graph": graphed is not None,
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
@@ -535,6 +558,7 @@ def main():
     ap.add_argument("--arrangement", default="single_pass", choices=["single_pass", "two_pass"])
     ap.add_argument("--model", default="vit_b", choices=sorted(MODEL_DIMS), help="encoder geometry (config 5: vit_l)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="issue every launch from Python (no CUDA graph)")
     ap.add_argument("--no-loss-check", action="store_true", help="skip the untimed step-0 loss check against the fp32 oracle")
     ap.add_argument("--no-library-baseline", dest="library_baseline", action="store_false",
                     help="skip the torch-eager bf16 comparator (N=1 only)")

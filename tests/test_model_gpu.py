@@ -490,3 +490,43 @@ def test_vit_large_single_pass_against_fp32_oracle_on_gpu():
     assert not low, low[:8]
     del model, out
     torch.cuda.empty_cache()
+
+
+def test_graphed_train_step_matches_eager():
+    """GraphedTrainStep (forward + reverse pass + fused Adam in one CUDA graph, device-side step counter) against the
+    same steps issued eagerly. Mask ratio 0 with the contrastive loss only makes the step independent of the mask draws
+    (every token is kept; pooling and attention are permutation-invariant), so both runs follow the same trajectory."""
+    from avsiam_b200 import GraphedTrainStep
+    d = O.TINY
+    B, K, W = 4, 4, 2
+    audio, imgs = synth_inputs(B, d, 61)
+    audio, imgs = audio.to(DEV), imgs.to(DEV)
+    adam_kw = dict(lr=2e-4, weight_decay=5e-7, betas=(0.95, 0.999))
+    runs = []
+    for graphed in (False, True):
+        model, sd = make_model(d, "single_pass")
+        model.direct_grads = True
+        opt = FusedAdam(model.parameters(), **adam_kw)
+        losses = []
+        if graphed:
+            step = GraphedTrainStep(model, opt, 0.0, 0.0, mae_loss_weight=0.0, contrast_loss_weight=1.0, warmup=W)
+            for _ in range(K):
+                losses.append(float(step(audio, imgs)))
+            assert step.launches_per_step > 20 and opt.steps_taken() == W + K
+        else:
+            for _ in range(W + K):
+                out = model(audio, imgs, 0.0, 0.0, mae_loss_weight=0.0, contrast_loss_weight=1.0)
+                opt.zero_grad()
+                out[0].backward()
+                opt.step()
+                losses.append(float(out[0]))
+            losses = losses[W:]
+        runs.append((losses, model.arena.flat[:model.arena.n_hot].detach().cpu().clone(), sd))
+    (l0, w0, sd), (l1, w1, _) = runs
+    for a, b in zip(l0, l1):
+        assert b == pytest.approx(a, rel=2e-3, abs=1e-4), (l0, l1)
+    assert l0[-1] < l0[0]                                   # it trains
+    model, _ = make_model(d, "single_pass")
+    init = model.arena.flat[:model.arena.n_hot].detach().cpu()
+    moved = (w0 - init).abs() > 1e-6
+    assert cos((w1 - init)[moved], (w0 - init)[moved]) > 0.97
