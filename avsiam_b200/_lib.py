@@ -9,7 +9,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libavsiam_b200.so")
+# AVSIAM_B200_LIB: developer override (A/B and trace builds of the same C-ABI); the product default is the in-tree build
+LIB_PATH = os.environ.get("AVSIAM_B200_LIB") or os.path.join(_HERE, "libavsiam_b200.so")
 
 
 class GemmEpilogue(Structure):

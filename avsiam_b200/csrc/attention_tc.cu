@@ -284,26 +284,17 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
       }
     };
     if (warp == 2) {
-      const uint64_t kK = make_desc(sK, 0, C::SBO, C::LT), kV = make_desc(sV, 0, C::SBO, C::LT);
-      const uint64_t kQ = make_desc(sQ, 0, C::SBO, C::LT), kDO = make_desc(sDO, 0, C::SBO, C::LT);
-      auto issue_s = [&](uint32_t g, int j, int i, int hh) {    // S^T(u) = K_j Q_half^T  -> buffer g
+      // "QK" issuer: S^T(u) = K_j Q_half^T into buffer u & 1 as soon as the softmax warps have read S^T(u-2)
+      const uint64_t kK = make_desc(sK, 0, C::SBO, C::LT);
+      const uint64_t kQ = make_desc(sQ, 0, C::SBO, C::LT);
+      auto issue_s = [&](uint32_t g, int j, int i, int hh) {
         const uint32_t kvo = (uint32_t)(j & 1) * BLK16, qo = (uint32_t)(i * 2 + hh) * HALF16;
         if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < C::KSTEPS; ++k)
             umma_bf16_ss(tmem + C::COL_S + g * 64, kK + (kvo + 2 * k), kQ + (qo + 2 * k), ID_S, k > 0 ? 1u : 0u);
           umma_commit(&s_full[g]);
-        }
-        __syncwarp();
-      };
-      auto issue_dp = [&](uint32_t g, int j, int i, int hh) {   // dP^T(u) = V_j dO_half^T -> buffer g
-        const uint32_t kvo = (uint32_t)(j & 1) * BLK16, qo = (uint32_t)(i * 2 + hh) * HALF16;
-        if (elect_one_sync()) {
-#pragma unroll
-          for (int k = 0; k < C::KSTEPS; ++k)
-            umma_bf16_ss(tmem + C::COL_DP + g * 64, kV + (kvo + 2 * k), kDO + (qo + 2 * k), ID_S, k > 0 ? 1u : 0u);
-          umma_commit(&dp_full[g]);
-          if (i == NB - 1 && hh == 1) umma_commit(&kv_empty[j & 1]);   // last read of K_j / V_j by this warp
+          if (i == NB - 1 && hh == 1) umma_commit(&kv_empty[j & 1]);   // last read of K_j by this warp
         }
         __syncwarp();
       };
@@ -311,34 +302,44 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
       tc_fence_after();
       issue_s(0, 0, 0, 0);
       issue_s(1, 0, 0, 1);
-      issue_dp(0, 0, 0, 0);
-      issue_dp(1, 0, 0, 1);
-      int sj = 0, si = 0, sh = 0;   // position of sub-step u     (S^T stream)
-      int dj = 0, di = 0, dh = 0;   // position of sub-step u - 2 (dP^T stream)
+      int sj = 0, si = 0, sh = 0;   // position of sub-step u
       advance(sj, si, sh); advance(sj, si, sh);
-      for (int u = 2; u < T + 2; ++u) {
+      for (int u = 2; u < T; ++u) {
         const uint32_t g = (uint32_t)(u & 1);
-        if (u < T) {
-          if (si == 0 && sh == 0) {
-            mbar_wait(&kv_full[sj & 1], (uint32_t)((sj >> 1) & 1));
-            tc_fence_after();
-          }
-          mbar_wait(&s_read[g], (uint32_t)(((u - 2) >> 1) & 1));
+        if (si == 0 && sh == 0) {
+          mbar_wait(&kv_full[sj & 1], (uint32_t)((sj >> 1) & 1));
           tc_fence_after();
-          issue_s(g, sj, si, sh);
-          advance(sj, si, sh);
         }
-        if (u >= 4) {  // dP^T(u - 2) overwrites the buffer that held P^T / dS^T of sub-step u - 4
-          mbar_wait(&pv_done[g], (uint32_t)(((u - 4) >> 1) & 1));
-          tc_fence_after();
-          issue_dp(g, dj, di, dh);
-        }
-        if (u >= 2) advance(dj, di, dh);
+        mbar_wait(&s_read[g], (uint32_t)(((u - 2) >> 1) & 1));
+        tc_fence_after();
+        issue_s(g, sj, si, sh);
+        advance(sj, si, sh);
       }
     } else {
       const uint64_t mQ = make_desc(sQ, C::SBO, C::SBO, C::LT), mDO = make_desc(sDO, C::SBO, C::SBO, C::LT);
       const uint64_t mK = make_desc(sK, C::SBO, C::SBO, C::LT);
       const uint64_t aDS = make_desc(sDS, 16384, 1024, 2u);
+      // dP^T(u) = V_j dO_half^T lands in the buffer that holds P^T / dS^T of sub-step u-2, so it must follow dV / dK(u-2):
+      // issued by THIS warp directly behind them (the tensor pipe runs one thread's MMAs in order) instead of by the QK
+      // warp after a commit -> barrier -> poll round trip — the softmax groups wait on exactly this chain
+      // (AVS_TC_TRACE: 1350 cycles from S^T to dP^T per sub-step, 500 of compute).
+      const uint64_t kV = make_desc(sV, 0, C::SBO, C::LT), kDO = make_desc(sDO, 0, C::SBO, C::LT);
+      auto issue_dp = [&](uint32_t g, int j, int i, int hh) {
+        const uint32_t kvo = (uint32_t)(j & 1) * BLK16, qo = (uint32_t)(i * 2 + hh) * HALF16;
+#pragma unroll
+        for (int k = 0; k < C::KSTEPS; ++k)
+          umma_bf16_ss(tmem + C::COL_DP + g * 64, kV + (kvo + 2 * k), kDO + (qo + 2 * k), ID_S, k > 0 ? 1u : 0u);
+        umma_commit(&dp_full[g]);
+      };
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        issue_dp(0, 0, 0, 0);
+        issue_dp(1, 0, 0, 1);
+      }
+      __syncwarp();
+      int dj = 0, di = 0, dh = 0;   // position of sub-step u + 2 (dP^T stream)
+      advance(dj, di, dh); advance(dj, di, dh);
       int cj = 0, ci = 0, ch = 0;
       for (int u = 0; u < T; ++u) {
         const uint32_t g = (uint32_t)(u & 1);
@@ -355,6 +356,11 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
         const int n = u >> 1;
         const uint32_t dso = (uint32_t)(n & 1) * (DS_TILE_BYTES >> 4);
         const uint32_t kvo = (uint32_t)(cj & 1) * BLK16;
+        const bool more_dp = (u + 2 < T);
+        if (more_dp && di == 0 && dh == 0) {   // sub-step u + 2 opens a key block: its V_j must have landed
+          mbar_wait(&kv_full[dj & 1], (uint32_t)((dj >> 1) & 1));
+          tc_fence_after();
+        }
         if (elect_one_sync()) {
           // dV_j += P^T dO_i ,  dK_j += dS^T Q_i : A = bf16 pairs in TMEM (8 columns per 16-query k-step), written by
           // the softmax warps over the dP^T buffer: per 16-column chunk  [P^T (8) | dS^T (8)]
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
           for (int k = 0; k < 4; ++k)
             umma_bf16_ts(tmem + C::COL_DK, tmem + C::COL_DP + g * 64 + k * 16 + 8, mQ + (qo + k * K16ROWS), ID_TS,
                          (first && k == 0) ? 0u : 1u);
-          umma_commit(&pv_done[g]);
+          if (more_dp) issue_dp(g, dj, di, dh);
           if (ch == 1) {
             // dQ_i += dS K_j : A = dS^T tile [128 keys][128 queries] read MN-major (two 64-query atoms 16 KB apart)
 #pragma unroll
@@ -383,6 +389,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
         __syncwarp();
         if (lane == 0) TC_TRACE(12, u);
         advance(cj, ci, ch);
+        advance(dj, di, dh);
       }
     }
   } else {

@@ -3,7 +3,7 @@ AVS_EXTRA_NVCC_FLAGS=-DAVS_TC_TRACE)."""
 import sys, os, ctypes, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from avsiam_b200 import ops, _lib
-lib = ctypes.CDLL(os.path.join(os.path.dirname(_lib.__file__), "libavsiam_b200.so"))
+lib = ctypes.CDLL(_lib.LIB_PATH)
 import sys as _s
 n_seq, S, H, hd = (64, 708, 16, 32) if len(_s.argv) < 2 else (256, int(_s.argv[1]), 12, 64)
 D = H * hd
