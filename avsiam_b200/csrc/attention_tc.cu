@@ -33,7 +33,7 @@ namespace {
 
 constexpr int TCB_GROUP_WARPS = 8;                 // softmax warps per ping-pong group (4 lane quarters x 2 column halves)
 constexpr int TCB_COMPUTE_WARPS = 2 * TCB_GROUP_WARPS;
-constexpr int TCB_FIRST_SOFTMAX_WARP = 3;           // warp 0 loader, warp 1 PV issuer, warp 2 QK issuer
+constexpr int TCB_FIRST_SOFTMAX_WARP = 4;           // warp 0 loader, warp 1 PV issuer, warp 2 QK issuer, warp 3 dQ issuer
 constexpr int TCB_THREADS = 32 * (TCB_FIRST_SOFTMAX_WARP + TCB_COMPUTE_WARPS);
 constexpr int DS_TILE_BYTES = 128 * 128 * 2;  // [128 keys][128 queries] bf16 = two SWIZZLE_128B atoms of 64 queries
 
@@ -196,8 +196,9 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
   uint64_t* dkv_empty = bars + 11; // softmax warps -> MMA: dK_j, dV_j read out
   uint64_t* s_read = bars + 12;    // [2] softmax warps -> MMA: S^T of a sub-step is in registers, buffer reusable
   uint64_t* dp_full = bars + 14;   // [2] MMA -> softmax warps: dP^T of a sub-step is in TMEM
-  uint64_t* pv_done = bars + 16;   // [2] PV issuer -> QK issuer: dV/dK of a sub-step have consumed P^T / dS^T
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* dq_done = bars + 16;   // dQ issuer -> softmax warps: every dQ product of the head has retired
+  uint64_t* pq_full = bars + 17;   // [2] all 16 softmax warps -> dQ issuer: both halves of dS^T tile n & 1 are written
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
   float* s_db = reinterpret_cast<float*>(bars + 20);   // [3 * HD] column sums of dQ | dK | dV of this head
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -210,14 +211,16 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 2);      // both MMA issuers commit
+      mbar_init(&kv_empty[i], 3);      // the three MMA issuers commit
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], TCB_GROUP_WARPS);
       mbar_init(&ds_empty[i], 1);
       mbar_init(&s_read[i], TCB_GROUP_WARPS);
       mbar_init(&dp_full[i], 1);
-      mbar_init(&pv_done[i], 1);
     }
+    mbar_init(dq_done, 1);
+    mbar_init(&pq_full[0], TCB_COMPUTE_WARPS);
+    mbar_init(&pq_full[1], TCB_COMPUTE_WARPS);
     mbar_init(dkv_full, 1);
     mbar_init(dkv_empty, TCB_GROUP_WARPS);
     fence_mbar_init();
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
       __syncwarp();
       if (lane == 0) mbar_arrive(&kv_full[j & 1]);
     }
-  } else if (warp == 1 || warp == 2) {
+  } else if (warp >= 1 && warp <= 3) {
     // ============================ MMA issuers ============================
     // The MMAs of this kernel are small (16-48 tensor cycles each), so ONE issuing warp's scalar work (descriptor
     // adds, barrier waits: ~4 cycles per dependent instruction) would bound the kernel.  Two warps issue
@@ -315,10 +318,38 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
         issue_s(g, sj, si, sh);
         advance(sj, si, sh);
       }
-    } else {
-      const uint64_t mQ = make_desc(sQ, C::SBO, C::SBO, C::LT), mDO = make_desc(sDO, C::SBO, C::SBO, C::LT);
+    } else if (warp == 3) {
+      // "dQ" issuer: dQ_i += dS K_j once both halves of a 128-query block have their dS^T in shared memory. A warp of its
+      // own: the PV issuer's instruction stream (10 small MMAs per sub-step, ~50 issue cycles each) is what paces the
+      // kernel (AVS_TC_TRACE), and these 8 MMAs per pair of sub-steps need nothing from it.
       const uint64_t mK = make_desc(sK, C::SBO, C::SBO, C::LT);
       const uint64_t aDS = make_desc(sDS, 16384, 1024, 2u);
+      int n = 0;
+      for (int j = 0; j < NB; ++j) {
+        mbar_wait(&kv_full[j & 1], (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
+        for (int i = 0; i < NB; ++i, ++n) {
+          // one barrier per tile buffer, completed by both softmax groups: its next phase needs this warp's ds_empty
+          // commit first, so a waiter can never fall two phases behind (the per-group p_full barriers can)
+          mbar_wait(&pq_full[n & 1], (uint32_t)((n >> 1) & 1));
+          tc_fence_after();
+          const uint32_t dso = (uint32_t)(n & 1) * (DS_TILE_BYTES >> 4);
+          const uint32_t kvo = (uint32_t)(j & 1) * BLK16;
+          if (elect_one_sync()) {
+            // A = dS^T tile [128 keys][128 queries] read MN-major (two 64-query atoms 16 KB apart)
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_bf16_ss(tmem + C::COL_DQ + i * HD, aDS + (dso + k * 128), mK + (kvo + k * K16ROWS), ID_DQ,
+                           (j > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&ds_empty[n & 1]);
+            if (i == NB - 1) umma_commit(&kv_empty[j & 1]);   // last read of K_j by this warp
+            if (i == NB - 1 && j == NB - 1) umma_commit(dq_done);
+          }
+          __syncwarp();
+        }
+      }
+    } else {
+      const uint64_t mQ = make_desc(sQ, C::SBO, C::SBO, C::LT), mDO = make_desc(sDO, C::SBO, C::SBO, C::LT);
       // dP^T(u) = V_j dO_half^T lands in the buffer that holds P^T / dS^T of sub-step u-2, so it must follow dV / dK(u-2):
       // issued by THIS warp directly behind them (the tensor pipe runs one thread's MMAs in order) instead of by the QK
       // warp after a commit -> barrier -> poll round trip — the softmax groups wait on exactly this chain
@@ -373,17 +404,9 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
             umma_bf16_ts(tmem + C::COL_DK, tmem + C::COL_DP + g * 64 + k * 16 + 8, mQ + (qo + k * K16ROWS), ID_TS,
                          (first && k == 0) ? 0u : 1u);
           if (more_dp) issue_dp(g, dj, di, dh);
-          if (ch == 1) {
-            // dQ_i += dS K_j : A = dS^T tile [128 keys][128 queries] read MN-major (two 64-query atoms 16 KB apart)
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              umma_bf16_ss(tmem + C::COL_DQ + ci * HD, aDS + (dso + k * 128), mK + (kvo + k * K16ROWS), ID_DQ,
-                           (cj > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&ds_empty[n & 1]);
-            if (ci == NB - 1) {
-              umma_commit(dkv_full);
-              umma_commit(&kv_empty[cj & 1]);
-            }
+          if (ch == 1 && ci == NB - 1) {   // last sub-step of key block cj: dK_j / dV_j complete, V_j no longer read
+            umma_commit(dkv_full);
+            umma_commit(&kv_empty[cj & 1]);
           }
         }
         __syncwarp();
@@ -523,7 +546,10 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[grp]);
+      if (lane == 0) {
+        mbar_arrive(&p_full[grp]);
+        mbar_arrive(&pq_full[n & 1]);
+      }
       if (tr) TC_TRACE(6 + grp * 4, n);
     };
     {
@@ -538,7 +564,9 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
         }
       }
     }
-    epilogue_dkv(NB - 1);  // also orders every dQ product before the reads below
+    epilogue_dkv(NB - 1);
+    mbar_wait(dq_done, 0);   // every dQ product has retired
+    tc_fence_after();
 #pragma unroll 1
     for (int i = grp; i < NB; i += 2) {
       uint32_t rq[EC];
