@@ -129,6 +129,9 @@ class _TapeFn(torch.autograd.Function):
         up[1:2].copy_((gv if gv is not None else zero).reshape(1).to(F32))
         up[2:3].copy_((gc if gc is not None else zero).reshape(1).to(F32))
         arena = mod._arena
+        if not h["tape"]:
+            raise RuntimeError("avsiam_b200: backward through this forward a second time — the activation tape is freed "
+                               "after its first backward (retain_graph is not supported); call forward again")
         if not mod.accumulate_into_arena:
             arena.zero_grads()
         order = list(reversed(h["tape"]))
@@ -352,11 +355,14 @@ class CAVMAE_BASE(nn.Module):
 
         la, lv, lc_raw, acc = losses[0], losses[1], losses[2], losses[3]
         if want_grad:
-            key = (self.arrangement, do_mae, do_c)
+            # the set of gradient-receiving parameters also depends on requires_grad (freeze / unfreeze schedules)
+            rg = hash(tuple(p.requires_grad for p in arena.params.values()))
+            key = (self.arrangement, do_mae, do_c, rg)
             if key not in self._used_cache:
                 names = self._used_param_names(do_mae, do_c)
                 self._used_cache[key] = (names, arena.active_bitmap(names))
             used, active = self._used_cache[key]
+            self._last_used = used
             holder = {"module": self, "tape": tape, "up": up, "used": used, "active": active, "key": key}
             la, lv, lc_raw = _TapeFn.apply(holder, la, lv, lc_raw, *[arena.params[n] for n in used])
         acc = acc.detach().clone()
@@ -452,6 +458,10 @@ class CAVMAE_BASE(nn.Module):
             bwd.touch = ()
             tape.append(bwd)
         return outs[0][0], outs[1][0]
+
+    def last_used_names(self) -> List[str]:
+        """Names of the parameters that received a gradient in the most recent forward that recorded a tape."""
+        return list(self._last_used) if getattr(self, "_last_used", None) is not None else []
 
     def _used_param_names(self, do_mae: bool, do_c: bool) -> List[str]:
         """Parameters that receive gradient in this call — the reference's sets, SURVEY.md §3.1 [probe]."""

@@ -268,10 +268,11 @@ class CAVMAEFT_BASE(nn.Module):
 
         tensors = [o.t for o in outs]
         if want_grad:
-            if mode not in self._used_cache:
+            rg = hash(tuple(p.requires_grad for p in arena.params.values()))
+            if (mode, rg) not in self._used_cache:
                 names = self._used_param_names(mode)
-                self._used_cache[mode] = (names, arena.active_bitmap(names))
-            used, active = self._used_cache[mode]
+                self._used_cache[(mode, rg)] = (names, arena.active_bitmap(names))
+            used, active = self._used_cache[(mode, rg)]
             holder = {"module": self, "tape": tape, "outs": outs, "used": used, "active": active, "key": ("ft", mode)}
             tensors = list(_FtTapeFn.apply(holder, len(outs), *tensors, *[arena.params[n] for n in used]))
         if mode == "audioonly":

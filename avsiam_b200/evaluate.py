@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .losses import bce_with_logits
+from .losses import bce_with_logits, cross_entropy
 from .stats import calculate_stats
 
 F32 = torch.float32
@@ -66,6 +66,20 @@ def validate_mlp(audio_model, val_loader, val_sampler, mode, args=None, output_p
     `stats` is avsiam_b200.calculate_stats' dict of device tensors (AP [C], auc [C], acc)."""
     device = torch.device("cuda")
     audio_model.eval()
+    # traintest_ft_base.py:328 evaluates `args.loss_fn` (BCEWithLogits for AudioSet, CrossEntropy for VGGSound, set at
+    # :106-110); traintest_cavmae_base.py:436 hard-codes BCE. args.loss_fn may be the torch module, a callable, or the
+    # run script's --loss string ('BCE' / 'CE'); absent -> BCE.
+    lf = getattr(args, "loss_fn", None) if args is not None else None
+    if lf is None and args is not None and isinstance(getattr(args, "loss", None), str):
+        lf = getattr(args, "loss")
+    if isinstance(lf, str):
+        loss_of = bce_with_logits if lf.upper().startswith("BCE") else cross_entropy
+    elif isinstance(lf, torch.nn.CrossEntropyLoss):
+        loss_of = cross_entropy
+    elif lf is None or isinstance(lf, torch.nn.BCEWithLogitsLoss):
+        loss_of = bce_with_logits
+    else:
+        loss_of = lf
     preds, labels_all = [], []
     loss_sum = torch.zeros((), dtype=F32, device=device)
     n = 0
@@ -77,7 +91,7 @@ def validate_mlp(audio_model, val_loader, val_sampler, mode, args=None, output_p
             out = audio_model(a_input, v_input, mode, is_eval=True)
             preds.append(out)
             labels_all.append(labels)
-            loss_sum += bce_with_logits(out.float().mean(dim=1), labels.float())
+            loss_sum += loss_of(out.float().mean(dim=1), labels.float())
             n += 1
         total = len(val_sampler.dataset) if val_sampler is not None else sum(p.shape[0] for p in preds)
         audio_output = distributed_concat(torch.cat(preds, dim=0), total)

@@ -87,7 +87,7 @@ def run_case(name, d, arrangement, B, dev, rank, world, seed):
     named = dict(model.named_parameters())
     # gradients: every parameter against the global-batch oracle
     worst, bad = 1.0, []
-    used = set(model._used_cache[(arrangement, True, True)][0])
+    used = set(model.last_used_names())
     assert used == set(ref_grads), (sorted(used - set(ref_grads))[:4], sorted(set(ref_grads) - used)[:4])
     for k, g in ref_grads.items():
         if float(g.norm()) < 1e-12:

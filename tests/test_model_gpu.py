@@ -197,7 +197,7 @@ def test_fused_adam_step_matches_oracle_adam():
     sd = {k: v for k, v in sd.items()}
     # (1) exact: the fused launch == torch.optim.Adam applied to the SAME gradients (the arena's), parameter by parameter
     arena = model.arena
-    used = model._used_cache[("single_pass", True, True)][0]
+    used = model.last_used_names()
     for k in used:
         p0 = sd[k].clone()
         g = arena.grad(k).detach().cpu().clone()
