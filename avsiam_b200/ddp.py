@@ -150,9 +150,11 @@ class B200DDP(nn.Module):
         """A communicator of its own for the gradient buckets, limited to a few CTAs per all-reduce: the buckets overlap
         the persistent 148-CTA GEMMs of the reverse pass, every SM an NCCL kernel holds is taken from them, and over
         NVLink 5 / NVSwitch a handful of channels already carries the bandwidth the overlap needs
-        (AVS_DDP_MAX_CTAS, default 8; 0 = share the caller's group as it is)."""
+        (AVS_DDP_MAX_CTAS = n > 0 enables it; default 0 = share the caller's group as it is). Measured on 8 x B200
+        (profiles/r02_bench_8gpu*.log): 8 CTAs 95.3 ms / step against 94.4 ms with NCCL's own choice — the limit costs more
+        all-reduce time at the tail of the reverse pass than it returns to the GEMMs, so it is off by default."""
         import os
-        max_ctas = int(os.environ.get("AVS_DDP_MAX_CTAS", "8"))
+        max_ctas = int(os.environ.get("AVS_DDP_MAX_CTAS", "0"))
         if (not dist.is_initialized() or dist.get_world_size(process_group) == 1 or max_ctas <= 0
                 or dist.get_backend(process_group) != "nccl"):
             return process_group

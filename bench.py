@@ -544,6 +544,14 @@ def run_gpu_arm(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # the captured graph holds NCCL kernels: release it (and everything else that references the communicators)
+        # before the process group goes away, or the teardown waits forever
+        if graphed is not None:
+            graphed.graph = None
+            graphed.static_out = None
+        graphed = None
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 
