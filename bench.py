@@ -552,7 +552,13 @@ def run_gpu_arm(args):
         graphed = None
         torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        # bounded teardown: the measurement is printed; a communicator that refuses to die must not hold the launcher
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(30.0)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
