@@ -168,7 +168,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int m_tiles = (args.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int n_tiles = (args.N + BLOCK_N - 1) / BLOCK_N;
   const int total_kb = (args.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
-  const int num_tiles = m_tiles * n_tiles * args.split_k;
+  // Work item t = (k-split ks, output tile mn) with mn FASTEST: the ~148 CTAs in flight then cover all output tiles of a
+  // few k-ranges, so every A / B slice is fetched from HBM once and shared through L2 (with ks fastest each CTA streamed
+  // private k-ranges and the long-reduction wgrad GEMMs re-read their operands once per output tile), and concurrent
+  // red.global.add traffic goes to different output tiles instead of piling onto one.
+  const int mn_tiles = m_tiles * n_tiles;
+  const int num_tiles = mn_tiles * args.split_k;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -206,8 +211,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int ks = t % args.split_k;
-      const int mn = t / args.split_k;
+      const int ks = t / mn_tiles;   // output tile fastest: the CTAs that run together share a k-range (see mn_tiles)
+      const int mn = t - ks * mn_tiles;
       const int m0 = (mn / n_tiles) * GEMM_BLOCK_M;
       const int n0 = (mn % n_tiles) * BLOCK_N;
       const int kb0 = ks * args.kb_per_split;
@@ -267,7 +272,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int ks = t % args.split_k;
+      const int ks = t / mn_tiles;
       const int kb0 = ks * args.kb_per_split;
       const int kb1 = min(total_kb, kb0 + args.kb_per_split);
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -326,7 +331,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (dbg_no_in) return;
       const int t = blockIdx.x + (q / CH) * (int)gridDim.x;
       if (t >= num_tiles) return;
-      const int mn = t / args.split_k;
+      const int mn = t % mn_tiles;
       const int m0 = (mn / n_tiles) * GEMM_BLOCK_M;
       const int n0 = (mn % n_tiles) * BLOCK_N;
       const int col = n0 + half * (BLOCK_N / 2) + (q % CH) * GEMM_EPI_CHUNK;
@@ -343,8 +348,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     int q = 0;
     int tile_par = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int ks = t % args.split_k;
-      const int mn = t / args.split_k;
+      const int ks = t / mn_tiles;   // output tile fastest: the CTAs that run together share a k-range (see mn_tiles)
+      const int mn = t - ks * mn_tiles;
       const int m0 = (mn / n_tiles) * GEMM_BLOCK_M;
       const int n0 = (mn % n_tiles) * BLOCK_N;
       mbar_wait(&tfull_bar[acc], acc_phase);

@@ -53,8 +53,36 @@ def t(fn, n=12):
     return e0.elapsed_time(e1) / n
 
 
+def wgrad(l, dy, x, dw, n_out, k_in, M):
+    """dW[n_out, k_in] += dY[M, n_out]^T X[M, k_in]: both operands MN-major, fp32 red.global.add, automatic split-K."""
+    e = GemmEpilogue()
+    e.flags = 8
+    e.alpha = 1.0
+    rc = l.avs_gemm_bf16(dy.data_ptr(), dy.stride(0), 1, x.data_ptr(), x.stride(0), 1, dw.data_ptr(), dw.stride(0), n_out,
+                         k_in, M, ctypes.byref(e), 0, torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise RuntimeError(l.avs_last_error())
+
+
 libs = [(p, load(p)) for p in sys.argv[1:]]
 print("columns:", [p for p, _ in libs])
+if os.environ.get("AB_WGRAD", "1") != "0":
+    for (tokens, n_out, k_in, name) in [(181248, 512, 2048, "dec fc2 wgrad"), (181248, 2048, 512, "dec fc1 wgrad"),
+                                         (181248, 1536, 512, "dec qkv wgrad"), (181248, 512, 512, "dec proj wgrad"),
+                                         (45312, 768, 3072, "enc fc2 wgrad"), (45312, 3072, 768, "enc fc1 wgrad"),
+                                         (45312, 2304, 768, "enc qkv wgrad"), (45312, 768, 768, "enc proj wgrad")]:
+        dy = torch.randn(tokens, n_out, device="cuda").bfloat16()
+        x = torch.randn(tokens, k_in, device="cuda").bfloat16()
+        dw = torch.zeros(n_out, k_in, device="cuda")
+        cells = []
+        for rep in range(2):
+            for p, l in libs:
+                ms = t(lambda: wgrad(l, dy, x, dw, n_out, k_in, tokens))
+                cells.append(f"{ms:.3f} ({2.0 * tokens * n_out * k_in / ms / 1e9:.0f})")
+        print(f"{name} M={n_out} N={k_in} K={tokens}: " + " | ".join(cells), flush=True)
+        del dy, x, dw
+if os.environ.get("AB_WGRAD_ONLY"):
+    sys.exit(0)
 for (M, N, K, name) in [(181248, 2048, 512, "dec"), (45312, 3072, 768, "enc")]:
     x = torch.randn(M, K, device="cuda").bfloat16()
     w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
