@@ -332,10 +332,8 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
           // one barrier per tile buffer, completed by both softmax groups: its next phase needs this warp's ds_empty
           // commit first, so a waiter can never fall two phases behind (the per-group p_full barriers can)
           mbar_wait(&pq_full[n & 1], (uint32_t)((n >> 1) & 1));
-          // ... and stay out of the tensor pipe's in-order queue until the PV issuer's answer to the same event — dV / dK
-          // of sub-step 2n+1 and dP^T(2n+3), the product both softmax groups are about to wait for — has retired: these
-          // 8 MMAs (320 tensor cycles) have two sub-steps of slack, that chain has none
-          if (2 * n + 3 < T) mbar_wait(&dp_full[1], (uint32_t)((n + 1) & 1));
+          // (holding these MMAs back until the PV issuer's dP^T has retired was measured: 1.67 -> 1.75 ms — the queue is
+          //  not what delays that chain)
           tc_fence_after();
           const uint32_t dso = (uint32_t)(n & 1) * (DS_TILE_BYTES >> 4);
           const uint32_t kvo = (uint32_t)(j & 1) * BLK16;
