@@ -228,8 +228,61 @@ __global__ void sgemm_strided_kernel(const float* __restrict__ A, long long ai, 
     if (i < M && j < N) C[i * ldc + j] = alpha * acc[u];
   }
 }
+// Same contraction with 64x64 tiles and 4x4 outputs per thread (16 FMA per 2 float4 shared-memory reads): the global
+// InfoNCE logits are N^2 D fp32 multiply-adds with N = world x batch — 6.4 GFLOP at 8 x 256 — and every rank computes
+// all of them, so this product is what grows with W^2 in the 8-GPU step (1.1 ms with the 32x32 kernel above).
+__global__ void __launch_bounds__(256) sgemm64_kernel(const float* __restrict__ A, long long ai, long long ak,
+                                                      const float* __restrict__ B, long long bj, long long bk,
+                                                      float* __restrict__ C, long long ldc, int M, int N, int K,
+                                                      float alpha) {
+  __shared__ __align__(16) float sa[16][68], sb[16][68];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = tid + 256 * u;
+      // the index that is contiguous in memory varies fastest across the threads
+      const int r = (ak == 1) ? idx >> 4 : idx & 63, k = (ak == 1) ? idx & 15 : idx >> 6;
+      const int rb = (bk == 1) ? idx >> 4 : idx & 63, kb = (bk == 1) ? idx & 15 : idx >> 6;
+      sa[k][r] = (i0 + r < M && k0 + k < K) ? A[(long long)(i0 + r) * ai + (long long)(k0 + k) * ak] : 0.f;
+      sb[kb][rb] = (j0 + rb < N && k0 + kb < K) ? B[(long long)(j0 + rb) * bj + (long long)(k0 + kb) * bk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&sa[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&sb[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = i0 + ty * 4 + u;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int j = j0 + tx * 4 + v;
+      if (i < M && j < N) C[(long long)i * ldc + j] = alpha * acc[u][v];
+    }
+  }
+}
 static void sgemm(const float* A, long long ai, long long ak, const float* B, long long bj, long long bk, float* C,
                   long long ldc, int M, int N, int K, float alpha, cudaStream_t st) {
+  if ((long long)M * N >= 64 * 64 * 16) {   // enough 64x64 tiles to matter; the small kernel keeps more CTAs busy below
+    dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
+    sgemm64_kernel<<<grid, 256, 0, st>>>(A, ai, ak, B, bj, bk, C, ldc, M, N, K, alpha);
+    return;
+  }
   dim3 grid(ceil_div(N, 32), ceil_div(M, 32)), block(32, 8);
   sgemm_strided_kernel<<<grid, block, 0, st>>>(A, ai, ak, B, bj, bk, C, ldc, M, N, K, alpha);
 }

@@ -491,7 +491,7 @@ def test_mae_loss_fwd_bwd():
     assert rel_err(dpv.cpu(), pvr.grad.reshape(-1, 768)) < 4e-3
 
 
-@pytest.mark.parametrize("N,D,bidirect", [(10, 768, True), (300, 128, True), (64, 768, False)])
+@pytest.mark.parametrize("N,D,bidirect", [(10, 768, True), (300, 128, True), (64, 768, False), (520, 768, True), (2048, 768, True)])
 def test_infonce_fwd_bwd(N, D, bidirect):
     ea, ev = rnd(N, D, seed=3), rnd(N, D, seed=4)
     ev = ev + 0.5 * ea  # correlated pairs => non-trivial accuracy
