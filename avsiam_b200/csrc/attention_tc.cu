@@ -159,6 +159,7 @@ __device__ __forceinline__ void load_rows_async(uint32_t tile, const bf16* __res
 #endif
 
 struct TcArgs {
+  CUtensorMap map_q, map_do;   // [rows, 3D] / [rows, D] bf16, boxes of 128 rows x head_dim columns (Q_i / dO_i blocks i >= 1)
   long long* trace;   // debug timeline (AVS_TC_TRACE builds only)
   const bf16* qkv;
   const bf16* dout;
@@ -172,7 +173,7 @@ struct TcArgs {
 };
 
 template <int HD>
-__global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ TcArgs a) {
   using C = TcCfg<HD>;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
   uint64_t* pq_full = bars + 17;   // [2] all 16 softmax warps -> dQ issuer: both halves of dS^T tile n & 1 are written
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
   float* s_db = reinterpret_cast<float*>(bars + 20);   // [3 * HD] column sums of dQ | dK | dV of this head
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(s_db + 3 * 64);   // [8] TMA -> MMA issuers: Q_i / dO_i (i >= 1) landed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, seq = blockIdx.y;
@@ -219,6 +221,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
       mbar_init(&dp_full[i], 1);
     }
     mbar_init(dq_done, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&q_full[i], 1);
     mbar_init(&pq_full[0], TCB_COMPUTE_WARPS);
     mbar_init(&pq_full[1], TCB_COMPUTE_WARPS);
     mbar_init(dkv_full, 1);
@@ -230,9 +233,17 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
     tmem_relinquish();
   }
   if (threadIdx.x < 3 * HD) s_db[threadIdx.x] = 0.f;
-  // whole-head Q, dO, log-sum-exp and delta
-  load_rows_async<HD>(sQ, qb, a.ld_qkv, 0, S_pad, S, threadIdx.x, TCB_THREADS);
-  load_rows_async<HD>(sDO, dob, a.ld_o, 0, S_pad, S, threadIdx.x, TCB_THREADS);
+  // The first 128-query block of Q and dO, log-sum-exp and delta of the whole head come in with the cooperative load; the
+  // other Q / dO blocks arrive by TMA (one box each, issued by one thread right after the prologue barrier) while the
+  // first key block's sub-steps already run: the whole-head load was a 10 k-cycle prologue per CTA with every pipe idle,
+  // 11 % of the CTA's life (AVS_TC_TRACE). A box that reaches past the sequence brings the next sequence's rows (or zero
+  // fill past the tensor); those query columns have lse = +inf, i.e. P = dS = 0 exactly.
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.map_q);
+    tma_prefetch_desc(&a.map_do);
+  }
+  load_rows_async<HD>(sQ, qb, a.ld_qkv, 0, 128, S, threadIdx.x, TCB_THREADS);
+  load_rows_async<HD>(sDO, dob, a.ld_o, 0, 128, S, threadIdx.x, TCB_THREADS);
   // the first key block comes in with the same cooperative load (one exposed HBM round trip per CTA, not two)
   load_rows_async<HD>(sK, qb + a.D, a.ld_qkv, 0, 128, S, threadIdx.x, TCB_THREADS);
   load_rows_async<HD>(sV, qb + 2 * a.D, a.ld_qkv, 0, 128, S, threadIdx.x, TCB_THREADS);
@@ -254,7 +265,15 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
 
   if (warp == 0) {
     // ============================ loader: K_j, V_j ============================
-    if (lane == 0) mbar_arrive(&kv_full[0]);   // block 0 was loaded (and fenced) by the whole CTA above
+    if (lane == 0) {
+      mbar_arrive(&kv_full[0]);   // block 0 was loaded (and fenced) by the whole CTA above
+      for (int i = 1; i < NB; ++i) {
+        mbar_arrive_expect_tx(&q_full[i], 2 * C::BLK_BYTES);
+        tma_load_2d(smem + i * C::BLK_BYTES, &a.map_q, &q_full[i], h * HD, (int)row_base + i * 128);
+        tma_load_2d(smem + (NB + i) * C::BLK_BYTES, &a.map_do, &q_full[i], h * HD, (int)row_base + i * 128);
+      }
+    }
+    __syncwarp();
     for (int j = 1; j < NB; ++j) {
       if (j >= 2) mbar_wait(&kv_empty[j & 1], (uint32_t)(((j >> 1) - 1) & 1));
       load_rows_async<HD>(sK + (j & 1) * C::BLK_BYTES, qb + a.D, a.ld_qkv, j * 128, 128, S, lane, 32);
@@ -311,6 +330,10 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
         const uint32_t g = (uint32_t)(u & 1);
         if (si == 0 && sh == 0) {
           mbar_wait(&kv_full[sj & 1], (uint32_t)((sj >> 1) & 1));
+          tc_fence_after();
+        }
+        if (sj == 0 && sh == 0 && si > 0) {   // first touch of Q block si
+          mbar_wait(&q_full[si], 0);
           tc_fence_after();
         }
         mbar_wait(&s_read[g], (uint32_t)(((u - 2) >> 1) & 1));
@@ -392,6 +415,10 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) attn_bwd_tc_kernel(const TcArg
         const bool more_dp = (u + 2 < T);
         if (more_dp && di == 0 && dh == 0) {   // sub-step u + 2 opens a key block: its V_j must have landed
           mbar_wait(&kv_full[dj & 1], (uint32_t)((dj >> 1) & 1));
+          tc_fence_after();
+        }
+        if (more_dp && dj == 0 && dh == 0 && di > 0) {   // first touch of dO block di (Q_di is used two sub-steps later)
+          mbar_wait(&q_full[di], 0);
           tc_fence_after();
         }
         if (elect_one_sync()) {
@@ -1445,6 +1472,10 @@ int avs_attention_bwd_tc(const void* qkv, long long ld_qkv, const void* dout, lo
   a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.S = S; a.NB = NB; a.H = H; a.D = H * head_dim;
   a.scale = rsqrtf((float)head_dim);
   a.scale_log2 = a.scale * 1.4426950408889634f;
+  const long long rows = (long long)n_seq * S;
+  const int swz = head_dim == 64 ? 128 : 64;   // one row of the block = one swizzle span
+  if (int rc = avs_make_tmap_2d_bf16(&a.map_q, qkv, rows, 3LL * a.D, ld_qkv, head_dim, 128, swz)) return rc;
+  if (int rc = avs_make_tmap_2d_bf16(&a.map_do, dout, rows, a.D, ld_o, head_dim, 128, swz)) return rc;
   return head_dim == 64 ? launch_bwd<64>(a, n_seq, (cudaStream_t)stream) : launch_bwd<32>(a, n_seq, (cudaStream_t)stream);
 }
 

@@ -78,6 +78,15 @@ constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp0 TMA, warp1 MMA,
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_EPI_CHUNK = 32;                 // columns per epilogue chunk (one tcgen05.ld 32x32b.x32)
 constexpr int GEMM_EPI_BUF = 32 * GEMM_EPI_CHUNK * 2;  // one [32 rows x 32 cols] bf16 input staging tile = 2 KB
+#ifndef AVS_GEMM_IN_DEPTH
+#define AVS_GEMM_IN_DEPTH 2
+#endif
+#ifndef AVS_GEMM_TMEM_PF
+#define AVS_GEMM_TMEM_PF 0
+#endif
+constexpr int GEMM_IN_DEPTH = AVS_GEMM_IN_DEPTH;   // input tiles in flight per epilogue warp (ring; chunk q uses slot q % depth)
+constexpr bool GEMM_TMEM_PF = AVS_GEMM_TMEM_PF != 0;   // tcgen05.ld of chunk c+1 issued before chunk c's math
+static_assert(GEMM_IN_DEPTH >= 2 && GEMM_IN_DEPTH <= 4, "input-tile ring depth");
 // Output staging tiles are [32 rows x 64 cols] (128-byte rows, SWIZZLE_128B) and leave every SECOND chunk: the TMA
 // unit turns each box row into one L2 write request, so 64-byte rows (the 32-column tiles of v2) made the stores —
 // 2048 row requests per 128x256 tile — the bound of every bf16-output GEMM (ncu: MMA warp polling tmem_empty).
@@ -96,7 +105,7 @@ struct GemmCfg {
   // per epilogue warp: [in x2][out][aux_out] staging tiles (only the ones the launch uses).  (Double-buffering the
   // output tiles was measured and bought nothing: the mainloop, not the store latency, bounds these kernels.)
   static __host__ __device__ int epi_bytes_per_warp(int tma_epi, int has_in, int has_aux_out) {
-    return tma_epi ? GEMM_EPI_BUF * (has_in ? 2 : 0) + GEMM_OUT_BUF * (1 + (has_aux_out ? 1 : 0)) : 0;
+    return tma_epi ? GEMM_EPI_BUF * (has_in ? GEMM_IN_DEPTH : 0) + GEMM_OUT_BUF * (1 + (has_aux_out ? 1 : 0)) : 0;
   }
   static __host__ int pick_stages(int epi_per_warp, int extra = 0) {
     int s = (GEMM_SMEM_LIMIT - 1024 - BAR_BYTES - extra - GEMM_EPI_WARPS * epi_per_warp) / STAGE_BYTES;
@@ -159,8 +168,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint64_t* empty_bar = bars + GEMM_MAX_STAGES;            // [MAX_STAGES]
   uint64_t* tfull_bar = bars + 2 * GEMM_MAX_STAGES;        // [2]
   uint64_t* tempty_bar = bars + 2 * GEMM_MAX_STAGES + 2;   // [2]
-  uint64_t* in_bar = bars + 2 * GEMM_MAX_STAGES + 4;       // [EPI_WARPS][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_MAX_STAGES + 4 + 2 * GEMM_EPI_WARPS);
+  uint64_t* in_bar = bars + 2 * GEMM_MAX_STAGES + 4;       // [EPI_WARPS][4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_MAX_STAGES + 4 + 4 * GEMM_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -193,7 +202,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], GEMM_EPI_WARPS);
     }
-    for (int i = 0; i < 2 * GEMM_EPI_WARPS; ++i) mbar_init(&in_bar[i], 1);
+    for (int i = 0; i < 4 * GEMM_EPI_WARPS; ++i) mbar_init(&in_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -314,9 +323,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const GemmEpilogue& ep = args.epi;
     uint8_t* my_epi = smem_epi + ew * epi_per_warp;
     uint8_t* in_buf = my_epi;                                        // [2][2 KB] when has_in
-    uint8_t* out_buf = my_epi + (HAS_IN ? 2 * GEMM_EPI_BUF : 0);   // 1024-byte aligned (128 B swizzle pattern)
+    uint8_t* out_buf = my_epi + (HAS_IN ? GEMM_IN_DEPTH * GEMM_EPI_BUF : 0);   // 1024-byte aligned (128 B swizzle pattern)
     uint8_t* aux_buf = out_buf + GEMM_OUT_BUF;
-    uint64_t* my_in_bar = in_bar + 2 * ew;
+    uint64_t* my_in_bar = in_bar + 4 * ew;
     constexpr bool tma_epi = TMA_EPI;
     constexpr bool has_in = HAS_IN;
 
@@ -335,12 +344,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int m0 = (mn / n_tiles) * GEMM_BLOCK_M;
       const int n0 = (mn % n_tiles) * BLOCK_N;
       const int col = n0 + half * (BLOCK_N / 2) + (q % CH) * GEMM_EPI_CHUNK;
-      mbar_arrive_expect_tx(&my_in_bar[q & 1], GEMM_EPI_BUF);
-      tma_load_2d(in_buf + (q & 1) * GEMM_EPI_BUF, &tma_in, &my_in_bar[q & 1], col, m0 + quarter * 32);
+      const int slot = q % GEMM_IN_DEPTH;
+      mbar_arrive_expect_tx(&my_in_bar[slot], GEMM_EPI_BUF);
+      tma_load_2d(in_buf + slot * GEMM_EPI_BUF, &tma_in, &my_in_bar[slot], col, m0 + quarter * 32);
     };
     if (has_in && lane == 0) {
-      issue_in(0);
-      issue_in(1);
+#pragma unroll
+      for (int i = 0; i < GEMM_IN_DEPTH; ++i) issue_in(i);
     }
 
     int acc = 0;
@@ -362,13 +372,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         rowadd_ptr = ep.rowadd + (long long)ri * args.N;
       }
       const bool lead_split = (ks == 0);
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * (BLOCK_N / 2));
+      uint32_t rn[GEMM_TMEM_PF ? 32 : 1];
+      if constexpr (GEMM_TMEM_PF) tmem_ld_32x32b_x32(taddr0, reinterpret_cast<uint32_t(&)[32]>(rn));
 #pragma unroll 1
       for (int c = 0; c < CH; ++c, ++q) {
         const int ccol = half * (BLOCK_N / 2) + c * GEMM_EPI_CHUNK;  // column offset inside the tile
         uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + ccol);
-        tmem_ld_32x32b_x32(taddr, r);
-        tmem_ld_wait();
+        if constexpr (GEMM_TMEM_PF) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = rn[j];
+          if (c + 1 < CH) tmem_ld_32x32b_x32(taddr0 + (uint32_t)((c + 1) * GEMM_EPI_CHUNK), reinterpret_cast<uint32_t(&)[32]>(rn));
+        } else {
+          tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * GEMM_EPI_CHUNK), r);
+          tmem_ld_wait();
+        }
         if (c == CH - 1) {  // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -437,12 +456,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
           uint4 in4[4];
           if constexpr (has_in) {
-            if (!dbg_no_in) mbar_wait(&my_in_bar[q & 1], (uint32_t)((q >> 1) & 1));
+            const int in_slot = q % GEMM_IN_DEPTH;
+            if (!dbg_no_in) mbar_wait(&my_in_bar[in_slot], (uint32_t)((q / GEMM_IN_DEPTH) & 1));
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              in4[j] = *reinterpret_cast<const uint4*>(in_buf + (q & 1) * GEMM_EPI_BUF + epi_tile_off(lane, j));
+              in4[j] = *reinterpret_cast<const uint4*>(in_buf + in_slot * GEMM_EPI_BUF + epi_tile_off(lane, j));
             __syncwarp();                     // every lane has read its row: the tile may be refilled
-            if (lane == 0) issue_in(q + 2);
+            if (lane == 0) issue_in(q + GEMM_IN_DEPTH);
           }
           if constexpr (EPI == GEMM_E_MUL) {
            if (ep.flags & EPI_MUL_AUX) {
