@@ -4,7 +4,7 @@ Public surface mirrors the reference (GenjiB/AVSiam, src/models): `CAVMAE_BASE`,
 path `FusedAdam`, `B200DDP`, `patch()`.  Importing the package never touches the GPU; the first kernel call loads
 libavsiam_b200.so and raises if it is missing (there is no CPU / PyTorch fallback).
 """
-from .cav_mae_base import CAVMAE_BASE, _Dims as Dims  # noqa: F401
+from .cav_mae_base import CAVMAE_BASE, _Dims as Dims, VIT_L_DIMS, VIT_H_DIMS  # noqa: F401
 from .cav_mae_ft import CAVMAEFT_BASE  # noqa: F401
 from . import augment, checkpoint, evaluate, losses  # noqa: F401
 from .fbank import wav2fbank  # noqa: F401
@@ -14,7 +14,7 @@ from .gather_layer import GatherLayer  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .graph import GraphedTrainStep  # noqa: F401
 
-__all__ = ["CAVMAE_BASE", "CAVMAEFT_BASE", "Dims", "GatherLayer", "wav2fbank", "calculate_stats", "d_prime", "FusedAdam", "B200DDP", "GradSync", "GraphedTrainStep", "patch"]
+__all__ = ["CAVMAE_BASE", "CAVMAEFT_BASE", "Dims", "VIT_L_DIMS", "VIT_H_DIMS", "GatherLayer", "wav2fbank", "calculate_stats", "d_prime", "FusedAdam", "B200DDP", "GradSync", "GraphedTrainStep", "patch"]
 __version__ = "0.1.0"
 
 

@@ -96,6 +96,15 @@ class _Dims:
         self.Ta, self.Tv = self.fa * self.ta, (img // patch) ** 2
 
 
+# BASELINE config 5 geometries (recovered from src/models/__pycache__/cav_mae_{large,huge}.*.pyc;
+# models/__init__.py:8-17 imports both). ViT-H/14: head_dim 80, 73 x 9 = 657 audio tokens (the stride-14 conv reads
+# 1022 x 126 of the 1024 x 128 fbank), 16 x 16 = 256 video tokens; as shipped it builds no decoder — contrastive-only,
+# single pass, single-direction InfoNCE (construct with arrangement="single_pass", bidirect_contrast=False and call
+# with mae_loss_weight=0).
+VIT_L_DIMS = dict(embed_dim=1024, depth=24, heads=16, dec_depth=6)
+VIT_H_DIMS = dict(embed_dim=1280, depth=32, heads=16, patch=14)
+
+
 def len_keep_of(L: int, ratio: float) -> int:
     return int(L * (1 - ratio))  # cav_mae_base.py:372,399
 
@@ -313,6 +322,11 @@ class CAVMAE_BASE(nn.Module):
         mask_a = mask_v = None
         used_before = set()
         do_mae, do_c = mae_loss_weight != 0, contrast_loss_weight != 0
+        if do_mae and (d.audio_len % d.patch or d.mel % d.patch or d.img % d.patch or (d.patch * d.patch) % 8):
+            # the reference's patchify is a reshape into whole patches (cav_mae_base.py:343-351): it has no MAE target for
+            # a patch size that does not divide the input, and CAVMAE_HUGE (patch 14) builds no decoder at all
+            raise RuntimeError(f"avsiam_b200: the MAE branch needs a patch size dividing the inputs (patch {d.patch}, fbank "
+                               f"{d.audio_len}x{d.mel}, frame {d.img}); ViT-H/14 runs contrastive-only: mae_loss_weight=0")
 
         def run_mae(xcat, ira, irv, ma, mv, ka, kv):
             eng.mae_branch(tape, xcat, audio, imgs, B, ka, kv, ira, irv, ma, mv, up[0:1], up[1:2], losses)

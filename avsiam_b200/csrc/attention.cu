@@ -1,5 +1,5 @@
 // Fused (flash-style) multi-head self-attention forward + backward for the short sequences of the AVSiam
-// encoder / MAE decoder (S = 49..708, head_dim 32 or 64).  Reads q,k,v straight out of the packed QKV GEMM
+// encoder / MAE decoder (S = 49..913, head_dim 32, 64 or 80).  Reads q,k,v straight out of the packed QKV GEMM
 // output [tokens, 3*D] and writes O as [tokens, D] / dQKV as [tokens, 3*D], so there are no permute copies on
 // either side, and never materialises the [S,S] score matrix in HBM.
 //
@@ -50,8 +50,10 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // that the 8 row addresses of an ldmatrix 8x8 fetch hit 8 distinct bank groups.
 template <int HD>
 __device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
-  constexpr int CPR = HD / 8;  // 16-byte chunks per row (4 or 8)
-  const int sw = (CPR == 8) ? (row & 7) : ((row >> 1) & 3);
+  constexpr int CPR = HD / 8;  // 16-byte chunks per row (4, 8 or 10)
+  // head_dim 80 (ViT-H): a row is 10 chunks, so 8 consecutive rows start 2 bank groups apart (0,2,4,6,0,2,4,6);
+  // flipping the lowest chunk bit for rows 4..7 of every 8 moves them onto the odd groups
+  const int sw = (CPR == 8) ? (row & 7) : (CPR == 4) ? ((row >> 1) & 3) : ((row >> 2) & 1);
   return (uint32_t)(row * (HD * 2) + ((chunk ^ sw) << 4));
 }
 
@@ -101,6 +103,11 @@ __device__ __forceinline__ void gemm_a_tT(float (&acc)[NT][4], const uint32_t (&
       mma16816(acc[nt], a[2 * half], b[0], b[1]);
       mma16816(acc[nt], a[2 * half + 1], b[2], b[3]);
     }
+    if constexpr ((HD / 16) % 2 == 1) {   // head_dim 80: the fifth 16-column k-step (chunks 8, 9; lanes 16.. repeat them)
+      uint32_t b[4];
+      ldsm_x4(b, tile + tile_off<HD>(row, (HD / 32) * 4 + ((lane >> 3) & 1)));
+      mma16816(acc[nt], a[HD / 16 - 1], b[0], b[1]);
+    }
   }
 }
 
@@ -149,7 +156,7 @@ struct AttnArgs {
 // ------------------------------------------------ forward ------------------------------------------------
 // WARPS = 8 normally; 4 for sequences of at most 64 tokens (4 x 16-row tiles), so that no warp of a resident CTA idles
 template <int HD, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 256 / (WARPS * 32) * 2) attn_fwd_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, HD == 80 ? 1 : 256 / (WARPS * 32) * 2) attn_fwd_kernel(const AttnArgs a) {
   constexpr int NT = 8;  // 64 keys per inner block
   extern __shared__ __align__(128) uint8_t att_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -289,12 +296,40 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
   }
 }
 
+// Same for head dims whose 16-byte chunk count is not a power of two (80 = 10 chunks, ViT-H): one thread per
+// (row, head) walks the head's chunks; a warp's loads still cover one contiguous 32 * 2*HD-byte stretch of the row.
+template <int HD>
+__global__ void __launch_bounds__(256) attn_delta_rowhead_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout,
+                                                                 float* __restrict__ delta, long long ld_o, int S, int H,
+                                                                 long long rows) {
+  const long long total = rows * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / H;
+    const int h = (int)(i - row * H);
+    const bf16* po = o + row * ld_o + h * HD;
+    const bf16* pd = dout + row * ld_o + h * HD;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+      const uint4 x = *reinterpret_cast<const uint4*>(po + c * 8);
+      const uint4 y = *reinterpret_cast<const uint4*>(pd + c * 8);
+      float2 a, b;
+      a = unpack_bf16x2(x.x); b = unpack_bf16x2(y.x); acc += a.x * b.x + a.y * b.y;
+      a = unpack_bf16x2(x.y); b = unpack_bf16x2(y.y); acc += a.x * b.x + a.y * b.y;
+      a = unpack_bf16x2(x.z); b = unpack_bf16x2(y.z); acc += a.x * b.x + a.y * b.y;
+      a = unpack_bf16x2(x.w); b = unpack_bf16x2(y.w); acc += a.x * b.x + a.y * b.y;
+    }
+    const long long sq = row / S;
+    delta[(sq * H + h) * S + (row - sq * S)] = acc;
+  }
+}
+
 // ------------------------------------------------ backward: dQ ------------------------------------------------
 // warp owns 16 queries; K and V of the head resident in smem; dQ = sum_blocks dS * K
 // WARPS = 8 normally; 4 for sequences of at most 64 tokens (4 x 16-row tiles), so that no warp of a resident CTA idles
 template <int HD, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 256 / (WARPS * 32) * 2) attn_bwd_dq_kernel(const AttnArgs a) {
-  constexpr int NT = (HD == 64) ? 4 : 8;  // keys per inner block / 8 (register budget: 128/thread)
+__global__ void __launch_bounds__(WARPS * 32, HD == 80 ? 1 : 256 / (WARPS * 32) * 2) attn_bwd_dq_kernel(const AttnArgs a) {
+  constexpr int NT = (HD >= 64) ? 4 : 8;  // keys per inner block / 8 (register budget: 128/thread)
   extern __shared__ __align__(128) uint8_t att_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, seq = blockIdx.y;
@@ -356,8 +391,8 @@ __global__ void __launch_bounds__(WARPS * 32, 256 / (WARPS * 32) * 2) attn_bwd_d
 // warp owns 16 keys; Q and dO of the head (+ lse, delta) resident in smem
 // WARPS = 8 normally; 4 for sequences of at most 64 tokens (4 x 16-row tiles), so that no warp of a resident CTA idles
 template <int HD, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 256 / (WARPS * 32) * 2) attn_bwd_dkv_kernel(const AttnArgs a) {
-  constexpr int NT = (HD == 64) ? 4 : 8;  // queries per inner block / 8
+__global__ void __launch_bounds__(WARPS * 32, HD == 80 ? 1 : 256 / (WARPS * 32) * 2) attn_bwd_dkv_kernel(const AttnArgs a) {
+  constexpr int NT = (HD >= 64) ? 4 : 8;  // queries per inner block / 8
   extern __shared__ __align__(128) uint8_t att_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, seq = blockIdx.y;
@@ -443,7 +478,7 @@ int set_smem(K kernel, int bytes, const char* who) {
 
 int check_common(const void* qkv, long long ld_qkv, long long ld_o, int n_seq, int S, int H, int HD, const char* who) {
   AVS_REQUIRE(qkv != nullptr, "%s: null pointer", who);
-  AVS_REQUIRE(HD == 32 || HD == 64, "%s: head_dim must be 32 or 64 (got %d)", who, HD);
+  AVS_REQUIRE(HD == 32 || HD == 64 || HD == 80, "%s: head_dim must be 32, 64 or 80 (got %d)", who, HD);
   AVS_REQUIRE(S > 0 && H > 0 && n_seq >= 0 && n_seq <= 65535, "%s: bad shape", who);
   AVS_REQUIRE(ld_qkv % 8 == 0 && ld_o % 8 == 0 && ((uintptr_t)qkv & 15) == 0, "%s: 16-byte alignment", who);
   const int S_pad = (S + 63) & ~63;
@@ -490,7 +525,9 @@ extern "C" int avs_attention_fwd(const void* qkv, long long ld_qkv, void* out, l
     if ((rc = set_smem(attn_fwd_kernel<HD_, W_>, smem, "avs_attention_fwd"))) return rc;             \
     attn_fwd_kernel<HD_, W_><<<grid, W_ * 32, smem, (cudaStream_t)stream>>>(a);                      \
   } while (0)
-  if (head_dim == 64) {
+  if (head_dim == 80) {   // ViT-H/14: 5 MMA k-steps per row, one CTA per SM's register budget
+    if (small) AVS_LAUNCH_FWD(80, 4); else AVS_LAUNCH_FWD(80, 8);
+  } else if (head_dim == 64) {
     if (small) AVS_LAUNCH_FWD(64, 4); else AVS_LAUNCH_FWD(64, 8);
   } else {
     if (small) AVS_LAUNCH_FWD(32, 4); else AVS_LAUNCH_FWD(32, 8);
@@ -521,7 +558,8 @@ extern "C" int avs_attention_bwd(const void* qkv, long long ld_qkv, const void* 
   const long long chunks = rows * H * (head_dim / 8);
   AVS_REQUIRE(chunks + 32 < (1ll << 31), "avs_attention_bwd: too many rows for the delta pre-pass");
   const int dblocks = (int)min((long long)avs_num_sms() * 8, ceil_div_ll(chunks, 256));
-  if (head_dim == 64) attn_delta_kernel<64><<<dblocks, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, ld_o, S, H, rows);
+  if (head_dim == 80) attn_delta_rowhead_kernel<80><<<dblocks, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, ld_o, S, H, rows);
+  else if (head_dim == 64) attn_delta_kernel<64><<<dblocks, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, ld_o, S, H, rows);
   else attn_delta_kernel<32><<<dblocks, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, ld_o, S, H, rows);
   int rc = avs_check_launch("attn_delta_kernel");
   if (rc) return rc;
@@ -541,7 +579,9 @@ extern "C" int avs_attention_bwd(const void* qkv, long long ld_qkv, const void* 
     if ((rc = avs_check_launch("attn_bwd_dkv_kernel"))) return rc;                                   \
     attn_bwd_dq_kernel<HD_, W_><<<grid, W_ * 32, smem_dq, stream>>>(a);                              \
   } while (0)
-  if (head_dim == 64) {
+  if (head_dim == 80) {
+    if (small) AVS_LAUNCH_BWD(80, 4); else AVS_LAUNCH_BWD(80, 8);
+  } else if (head_dim == 64) {
     if (small) AVS_LAUNCH_BWD(64, 4); else AVS_LAUNCH_BWD(64, 8);
   } else {
     if (small) AVS_LAUNCH_BWD(32, 4); else AVS_LAUNCH_BWD(32, 8);

@@ -192,13 +192,63 @@ __global__ void patchify_video_kernel(const float* __restrict__ img, const int* 
   }
 }
 
+// Generic patch geometry (ViT-H/14: patch 14 is not a multiple of 8 and does not divide 1024 x 128 — the stride-14
+// conv of PatchEmbed simply never reads the last 2 rows / columns): one thread per 8 output columns
+// of the PADDED row [0, ld_out), every element addressed on its own; columns >= the patch vector length are written
+// as zeros, so the row can be the K-padded A operand of the patch-embed GEMM (TMA wants 16-byte row pitches:
+// 196 -> 200, 588 -> 592 columns).  kind 0: audio [B, T, F], kind 1: video [B, C, H, W].
+__global__ void patchify_generic_kernel(const float* __restrict__ in, const int* __restrict__ ids,
+                                        const int* __restrict__ sample_idx, bf16* __restrict__ out, int kind, int C, int d0,
+                                        int d1, int p, int gw, int keep, int ids_ld, int ld_out, long long total8) {
+  const int vec = C * p * p;
+  const int per_row = ld_out / 8;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total8;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(g % per_row);
+    const long long r = g / per_row;
+    const int bl = (int)(r / keep), i = (int)(r % keep);
+    const int tok = ids ? ids[(size_t)bl * ids_ld + i] : i;
+    const int b = sample_idx ? sample_idx[bl] : bl;
+    const int tr = tok / gw, tc = tok % gw;   // audio: (f, t)   video: (h, w)
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = c8 * 8 + j;
+      if (e >= vec) { v[j] = 0.f; continue; }
+      if (kind == 0) {
+        const int pf = e / p, pt = e % p;
+        v[j] = __ldg(in + ((size_t)b * d0 + (size_t)tc * p + pt) * d1 + tr * p + pf);
+      } else {
+        const int c = e / (p * p), pp = (e / p) % p, q = e % p;
+        v[j] = __ldg(in + (((size_t)b * C + c) * d0 + (size_t)tr * p + pp) * d1 + (size_t)tc * p + q);
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + (size_t)r * ld_out + c8 * 8) = o;
+  }
+}
+
+static int launch_patchify_generic(const float* in, const int32_t* ids, const int32_t* sample_idx, void* out, int kind, int B,
+                                   int C, int d0, int d1, int patch, int gw, int keep, int ids_ld, int ld_out, void* stream) {
+  const long long total8 = (long long)B * keep * (ld_out / 8);
+  if (total8 == 0) return 0;
+  const int blocks = (int)min((long long)avs_num_sms() * 8, ceil_div_ll(total8, 256));
+  patchify_generic_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, ids, sample_idx, (bf16*)out, kind, C, d0, d1, patch, gw,
+                                                                    keep, ids_ld, ld_out, total8);
+  return avs_check_launch("patchify_generic_kernel");
+}
+
 extern "C" int avs_patchify_audio(const float* audio, const int32_t* ids, const int32_t* sample_idx, void* out, int B, int T, int F, int patch,
                                   int keep, int ids_ld, int ld_out, void* stream) {
   AVS_REQUIRE(audio && out, "avs_patchify_audio: null pointer");
-  AVS_REQUIRE(patch % 8 == 0 && T % patch == 0 && F % patch == 0, "avs_patchify_audio: patch must divide T,F and be a multiple of 8");
+  AVS_REQUIRE(patch > 0 && T >= patch && F >= patch, "avs_patchify_audio: bad patch size");
   AVS_REQUIRE(ld_out >= patch * patch && ld_out % 8 == 0 && ((uintptr_t)out & 15) == 0, "avs_patchify_audio: bad ld_out/alignment");
-  const int ntok = (T / patch) * (F / patch);
+  const int ntok = (T / patch) * (F / patch);   // floor, as Conv2d(kernel = stride = patch) does
   AVS_REQUIRE(keep > 0 && keep <= ntok && (ids != nullptr || keep == ntok), "avs_patchify_audio: bad keep");
+  if (patch % 8 != 0)
+    return launch_patchify_generic(audio, ids, sample_idx, out, 0, B, 1, T, F, patch, T / patch, keep, ids_ld, ld_out, stream);
   const long long total8 = (long long)B * keep * (patch * patch / 8);
   if (total8 == 0) return 0;
   const int blocks = (int)min((long long)avs_num_sms() * 8, ceil_div_ll(total8, 256));
@@ -210,10 +260,12 @@ extern "C" int avs_patchify_audio(const float* audio, const int32_t* ids, const 
 extern "C" int avs_patchify_video(const float* img, const int32_t* ids, const int32_t* sample_idx, void* out, int B, int C, int H, int W,
                                   int patch, int keep, int ids_ld, int ld_out, void* stream) {
   AVS_REQUIRE(img && out, "avs_patchify_video: null pointer");
-  AVS_REQUIRE(patch % 8 == 0 && H % patch == 0 && W % patch == 0, "avs_patchify_video: patch must divide H,W and be a multiple of 8");
+  AVS_REQUIRE(patch > 0 && H >= patch && W >= patch, "avs_patchify_video: bad patch size");
   AVS_REQUIRE(ld_out >= C * patch * patch && ld_out % 8 == 0 && ((uintptr_t)out & 15) == 0, "avs_patchify_video: bad ld_out/alignment");
   const int ntok = (H / patch) * (W / patch);
   AVS_REQUIRE(keep > 0 && keep <= ntok && (ids != nullptr || keep == ntok), "avs_patchify_video: bad keep");
+  if (patch % 8 != 0)
+    return launch_patchify_generic(img, ids, sample_idx, out, 1, B, C, H, W, patch, W / patch, keep, ids_ld, ld_out, stream);
   const long long total8 = (long long)B * keep * (C * patch * patch / 8);
   if (total8 == 0) return 0;
   const int blocks = (int)min((long long)avs_num_sms() * 8, ceil_div_ll(total8, 256));

@@ -214,25 +214,38 @@ class Engine:
             rows = s.n * s.keep
             if s.mod == "a":
                 K = d.patch * d.patch
-                Ap = self._empty(rows, K)
+                Kp = (K + 7) // 8 * 8   # TMA row pitch: 16-byte multiples (patch 14: 196 -> 200; pad columns are zeros)
+                Ap = self._empty(rows, Kp)
                 ops.patchify_audio(audio, s.ids_shuffle, s.keep, d.patch, Ap, s.sample_idx)
                 wname, bname, pos = vit + "patch_embed_a.proj.weight", vit + "patch_embed_a.proj.bias", vit + "pos_embed_a"
                 pos_t, gpos = self.P.f32(pos)[0], self.P.grad(pos)[0]
             else:
                 K = d.patch * d.patch * d.in_chans
-                Ap = self._empty(rows, K)
+                Kp = (K + 7) // 8 * 8   # patch 14: 588 -> 592
+                Ap = self._empty(rows, Kp)
                 ops.patchify_video(imgs, s.ids_shuffle, s.keep, d.patch, Ap, s.sample_idx)
                 wname, bname, pos = vit + "patch_embed.proj.weight", vit + "patch_embed.proj.bias", vit + "pos_embed"
                 pos_t, gpos = self.P.f32(pos)[0, 1:], self.P.grad(pos)[0, 1:]
             rowidx = s.ids_shuffle[:, :s.keep].contiguous().view(-1)
             xs = x.t[r0:r0 + rows]
-            ops.gemm(Ap, self._w2d(wname), xs, rows, D, K, bias=self.P.f32(bname), rowadd=pos_t, rowidx=rowidx,
-                     alpha=2.0)
+            w2d = self._w2d(wname)
+            if Kp != K:   # projection weight re-pitched to the padded K (a [D, K] view has no 16-byte row pitch)
+                wp = torch.zeros(D, Kp, dtype=BF16, device=self.dev)
+                wp[:, :K].copy_(w2d)
+                w2d = wp
+            ops.gemm(Ap, w2d, xs, rows, D, Kp, bias=self.P.f32(bname), rowadd=pos_t, rowidx=rowidx, alpha=2.0)
             groups.append(Group(r0, s.n, s.keep, s.mod))
             if tape is not None:
-                def bwd(r0=r0, rows=rows, Ap=Ap, wname=wname, bname=bname, gpos=gpos, rowidx=rowidx, K=K):
+                def bwd(r0=r0, rows=rows, Ap=Ap, wname=wname, bname=bname, gpos=gpos, rowidx=rowidx, K=K, Kp=Kp):
                     dx = x.g[r0:r0 + rows]
-                    self._linear_bwd(dx, Ap, wname, bname, rows, D, K, None, alpha=2.0)
+                    if Kp == K:
+                        self._linear_bwd(dx, Ap, wname, bname, rows, D, K, None, alpha=2.0)
+                    else:   # wgrad into a K-padded fp32 tile, its first K columns added to the [D, K] gradient
+                        gw = torch.zeros(D, Kp, dtype=F32, device=self.dev)
+                        ops.gemm(dx, Ap, gw, D, Kp, rows, a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
+                                 split_k=0, alpha=2.0)
+                        self._g2d(wname).add_(gw[:, :K])
+                        ops.colsum(dx, self.P.grad(bname), rows, D, 2.0)
                     ops.scatter_add_rows(dx, rowidx, gpos, 2.0)
                 bwd.touch = (wname, bname, pos)
                 tape.append(bwd)

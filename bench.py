@@ -32,12 +32,16 @@ import torch  # noqa: E402
 METRIC = "AV pretrain samples/sec"
 UNIT = "samples/s"
 TRAIN_GFLOP_PER_SAMPLE = {"single_pass": 242.0, "two_pass": 474.0}   # BASELINE.md §4 (3 x forward), ViT-B/16
-# BASELINE config 5 geometries. ViT-H/14 (head_dim 80, patch 14) is not built: no attention tile
-# shape for head_dim 80 in this library.
-MODEL_DIMS = {"vit_b": {}, "vit_l": dict(embed_dim=1024, depth=24, heads=16, dec_depth=6)}
+# BASELINE config 5 geometries. ViT-H/14 (head_dim 80, patch 14, 657 + 256 tokens) runs as the
+# reference ships it: no decoder, contrastive-only, single-direction InfoNCE (cav_mae_huge.cpython-39.pyc).
+MODEL_DIMS = {"vit_b": {}, "vit_l": dict(embed_dim=1024, depth=24, heads=16, dec_depth=6),
+              "vit_h": dict(embed_dim=1280, depth=32, heads=16, patch=14, dec_depth=1)}
+MODEL_NAME = {"vit_b": "ViT-B/16", "vit_l": "ViT-L/16", "vit_h": "ViT-H/14"}
+# (mae_loss_weight, contrast_loss_weight, bidirectional InfoNCE) of the step each model runs
+MODEL_LOSS = {"vit_b": (1.0, 0.01, True), "vit_l": (1.0, 0.01, True), "vit_h": (0.0, 0.01, False)}
 
 
-def train_gflop_per_sample(dims, keep_a, keep_v):
+def train_gflop_per_sample(dims, keep_a, keep_v, with_mae=True):
     """3 x forward FLOPs of the single-pass step (2 per multiply-add): encoder over the kept tokens, two fusion blocks,
     decoder over all tokens, patch embedding and prediction heads; attention 4 S^2 hd per head."""
     D, Dd, p = dims.embed_dim, dims.dec_dim, dims.patch
@@ -49,6 +53,8 @@ def train_gflop_per_sample(dims, keep_a, keep_v):
 
     enc_tokens = keep_a + keep_v
     f = dims.depth * block(enc_tokens, [keep_a, keep_v], D, dims.heads)
+    if not with_mae:      # contrastive-only (ViT-H/14): encoder + patch embedding
+        return 3.0 * (f + 2.0 * keep_a * D * p * p + 2.0 * keep_v * D * p * p * dims.in_chans) / 1e9
     f += 2 * block(enc_tokens, [enc_tokens], D, dims.heads)
     f += dims.dec_depth * block(dims.Ta + dims.Tv, [dims.Ta + dims.Tv], Dd, dims.dec_heads)
     f += 2.0 * keep_a * D * p * p + 2.0 * keep_v * D * p * p * dims.in_chans + 2.0 * enc_tokens * D * Dd
@@ -194,9 +200,11 @@ def run_reference_arm(args):
 
 
 def workload_config(args, per_gpu_batch: int, world: int):
-    name = {"vit_b": "ViT-B/16", "vit_l": "ViT-L/16"}[getattr(args, "model", "vit_b")]
+    model = getattr(args, "model", "vit_b")
+    name = MODEL_NAME[model]
+    what = "MAE + global-batch InfoNCE" if MODEL_LOSS[model][0] else "global-batch InfoNCE only (no decoder, as shipped)"
     return {"workload": f"{name} AVSiam pretrain step ({args.arrangement}), 1024x128 fbank + 1x224x224 frame, "
-                        f"mask 0.75, MAE + global-batch InfoNCE, Adam",
+                        f"mask 0.75, {what}, Adam",
             "arrangement": args.arrangement, "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * world,
             "parallelism": f"dp{world}", "l2": "inputs (288 MB/step) and activations (>40 GB/step) exceed the 126 MB L2"}
 
@@ -221,8 +229,9 @@ def check_step0_loss(model, net, args, dev, rank, world, dist):
     imgs = torch.randn(B, d.in_chans, d.img, d.img, generator=g).to(dev)
     plan = O.make_mask_plan(B, d, 99 + rank, two_pass=(args.arrangement == "two_pass"))
     model.mask_plan = plan
+    mae_w, c_w, bidirect = MODEL_LOSS[args.model]
     with torch.no_grad():
-        out = net(audio, imgs, 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+        out = net(audio, imgs, 0.75, 0.75, mae_loss_weight=mae_w, contrast_loss_weight=c_w)
     model.mask_plan = None
     state = oracle_state_from_model(model, dev)
 
@@ -235,8 +244,8 @@ def check_step0_loss(model, net, args, dev, rank, world, dist):
 
     with torch.no_grad():
         if args.arrangement == "single_pass":
-            ref = O.forward_single_pass(audio, imgs, state, d, plan.to(dev), mae_loss_weight=1.0,
-                                        contrast_loss_weight=0.01, gather=gather)
+            ref = O.forward_single_pass(audio, imgs, state, d, plan.to(dev), mae_loss_weight=mae_w,
+                                        contrast_loss_weight=c_w, gather=gather, bidirect=bidirect)
         else:
             ref = O.forward(audio, imgs, state, d, plan.to(dev), mae_loss_weight=1.0, contrast_loss_weight=0.01,
                             gather=lambda x: gather(x))
@@ -254,6 +263,7 @@ def time_library_baseline(args, dev, model, steps=3, warmup=2):
     from oracle import avsiam_oracle as O
     import torch.nn.functional as F
     d = O.Dims(**MODEL_DIMS[args.model])
+    mae_w, c_w, bidirect = MODEL_LOSS[args.model]
     B = args.batch
     torch.cuda.empty_cache()
     state = {k: v.requires_grad_(True) for k, v in oracle_state_from_model(model, dev).items()}
@@ -276,7 +286,8 @@ def time_library_baseline(args, dev, model, steps=3, warmup=2):
     try:
         def step():
             with torch.autocast("cuda", dtype=torch.bfloat16):
-                out = O.forward_single_pass(audio, imgs, state, d, plan, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+                out = O.forward_single_pass(audio, imgs, state, d, plan, mae_loss_weight=mae_w, contrast_loss_weight=c_w,
+                                            bidirect=bidirect)
             opt.zero_grad(set_to_none=True)
             out[0].backward()
             opt.step()
@@ -299,7 +310,7 @@ def time_library_baseline(args, dev, model, steps=3, warmup=2):
         torch.cuda.empty_cache()
     return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
             "what": "torch 2.11 eager, autocast(bfloat16), cuBLAS GEMMs + F.scaled_dot_product_attention + torch autograd + "
-                    "torch.optim.Adam(fused=True); same ViT-B/16 single_pass step, same batch, same GPU; activations kept "
+                    f"torch.optim.Adam(fused=True); same {MODEL_NAME[args.model]} single_pass step, same batch, same GPU; activations kept "
                     "by autograd (no recomputation)"}
 
 
@@ -324,7 +335,8 @@ def run_gpu_arm(args):
     torch.manual_seed(0)                      # identical random-init weights on every rank
     dims = avsiam_b200.Dims(**MODEL_DIMS[args.model]) if MODEL_DIMS[args.model] else None
     model = CAVMAE_BASE(audio_length=1024, norm_pix_loss=False, modality_specific_depth=23, tr_pos=False,
-                        arrangement=args.arrangement, dims=dims).to(dev)
+                        arrangement=args.arrangement, dims=dims, bidirect_contrast=MODEL_LOSS[args.model][2]).to(dev)
+    mae_w, c_w, _ = MODEL_LOSS[args.model]
     with torch.no_grad():                     # the reference zero-inits these (cav_mae_base.py:312-337); any value works
         for n in ("mask_token", "decoder_pos_embed_a", "decoder_pos_embed_v", "decoder_modality_a", "decoder_modality_v"):
             getattr(model, n).normal_(std=0.02)
@@ -347,7 +359,7 @@ def run_gpu_arm(args):
         # forward + reverse pass + Adam as ONE CUDA graph (avsiam_b200.GraphedTrainStep); falls back to eager launches,
         # and says so on the JSON line, if this torch / NCCL combination cannot capture the step
         try:
-            graphed = avsiam_b200.GraphedTrainStep(net, opt1, 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+            graphed = avsiam_b200.GraphedTrainStep(net, opt1, 0.75, 0.75, mae_loss_weight=mae_w, contrast_loss_weight=c_w)
             graphed(torch.randn(B, 1024, 128, device=dev), torch.randn(B, 3, 224, 224, device=dev))
             torch.cuda.synchronize()
         except Exception as e:   # noqa: BLE001
@@ -356,7 +368,7 @@ def run_gpu_arm(args):
             opt1.capturable = False
 
     def eager_step(a, v):
-        out = net(a, v, 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+        out = net(a, v, 0.75, 0.75, mae_loss_weight=mae_w, contrast_loss_weight=c_w)
         opt1.zero_grad()
         out[0].backward()
         opt1.step()
@@ -366,7 +378,7 @@ def run_gpu_arm(args):
         if graphed is not None:
             return graphed(a, v)
         if args.arrangement == "single_pass":
-            out = net(a, v, 0.75, 0.75, mae_loss_weight=1.0, contrast_loss_weight=0.01)
+            out = net(a, v, 0.75, 0.75, mae_loss_weight=mae_w, contrast_loss_weight=c_w)
             opt1.zero_grad()
             out[0].backward()
             opt1.step()
@@ -502,7 +514,7 @@ def run_gpu_arm(args):
         gflop_sample = TRAIN_GFLOP_PER_SAMPLE[args.arrangement]
     else:
         md = model.dims
-        gflop_sample = train_gflop_per_sample(md, int(md.Ta * 0.25), int(md.Tv * 0.25))
+        gflop_sample = train_gflop_per_sample(md, int(md.Ta * 0.25), int(md.Tv * 0.25), with_mae=mae_w != 0)
     step_util = (value / world) * gflop_sample * 1e9 / (peaks["bf16_tflops"] * 1e12)
 
     # ---- (4) CPU baseline (rank 0, N=1 only): bounded sample of the same step on the host cores
@@ -570,7 +582,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE.json config 2: 256)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the CPU reference sample (config 1: 2)")
     ap.add_argument("--arrangement", default="single_pass", choices=["single_pass", "two_pass"])
-    ap.add_argument("--model", default="vit_b", choices=sorted(MODEL_DIMS), help="encoder geometry (config 5: vit_l)")
+    ap.add_argument("--model", default="vit_b", choices=sorted(MODEL_DIMS), help="encoder geometry (config 5: vit_l, vit_h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="issue every launch from Python (no CUDA graph)")
     ap.add_argument("--no-loss-check", action="store_true", help="skip the untimed step-0 loss check against the fp32 oracle")
@@ -581,6 +593,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3                       # timing rule: W >= 3
+    if args.model == "vit_h" and args.arrangement != "single_pass":
+        raise SystemExit("bench.py: --model vit_h runs the single_pass arrangement only (CAVMAE_HUGE as shipped)")
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -60,6 +60,9 @@ class Dims:
 
 
 VIT_B = Dims()
+VIT_L = Dims(embed_dim=1024, depth=24, heads=16, dec_depth=6)   # SURVEY.md Appendix C (cav_mae_large.cpython-39.pyc)
+VIT_H = Dims(embed_dim=1280, depth=32, heads=16, patch=14)      # Appendix C (cav_mae_huge.cpython-39.pyc): head_dim 80,
+#                                                                 657 + 256 tokens; contrastive-only as shipped
 TINY = Dims(embed_dim=128, depth=2, heads=2, dec_dim=64, dec_depth=2, dec_heads=2, patch=16, audio_len=256, mel=32,
             img=64, head_classes=16)
 
@@ -184,6 +187,9 @@ def patch_embed_audio(audio: torch.Tensor, w: torch.Tensor, b: torch.Tensor, d: 
     the 256-vector of a patch is the (freq, time) tile (SURVEY.md §8a identity 3)."""
     B = audio.shape[0]
     p = d.patch
+    # Conv2d(kernel = stride = p) never reads past the last whole patch: with ViT-H's patch 14 the 1024 x 128 fbank
+    # contributes its first 1022 x 126 samples (73 x 9 = 657 tokens, SURVEY.md Appendix C); a no-op when p divides both
+    audio = audio[:, :d.ta * p, :d.fa * p]
     x = audio.transpose(1, 2).reshape(B, d.fa, p, d.ta, p)           # [B, f, pf, t, pt]
     x = x.permute(0, 1, 3, 2, 4).reshape(B, d.Ta, p * p)             # token (f,t); vec (pf,pt)
     return x @ w.reshape(w.shape[0], -1).t() + b
@@ -194,6 +200,7 @@ def patch_embed_video(img: torch.Tensor, w: torch.Tensor, b: torch.Tensor, d: Di
     B, C = img.shape[0], img.shape[1]
     p = d.patch
     g = d.img // p
+    img = img[:, :, :g * p, :g * p]
     x = img.reshape(B, C, g, p, g, p).permute(0, 2, 4, 1, 3, 5).reshape(B, g * g, C * p * p)
     return x @ w.reshape(w.shape[0], -1).t() + b
 

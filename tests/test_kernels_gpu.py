@@ -1,5 +1,6 @@
 """Per-kernel parity tests (B200): every C-ABI entry against the oracle / a plain fp32 torch statement of the op.
 Index work is bit-exact; floating point within the tolerance written beside each assert (bf16 operands)."""
+import dataclasses
 import math
 import os
 
@@ -215,6 +216,35 @@ def test_patchify_matches_patch_embed_order():
     assert torch.equal(full.cpu(), O.patch_embed_audio(audio.cpu(), eye_a, torch.zeros(256), d).reshape(-1, 256).to(torch.bfloat16))
 
 
+def test_patchify_patch14_matches_strided_conv_order():
+    """ViT-H/14 geometry: patch 14 neither divides 1024 x 128 nor is a multiple of 8; the kernel must
+    read exactly what Conv2d(kernel = stride = 14) reads (73 x 9 = 657 audio tokens from the first 1022 x 126 samples,
+    16 x 16 video tokens) and zero the K padding (196 -> 200, 588 -> 592 columns). Checker: torch's own conv2d with
+    identity weights (the reference's PatchEmbed is that Conv2d, cav_mae_base.py:96-100), and the oracle's restatement."""
+    d = dataclasses.replace(O.VIT_B, patch=14)
+    assert (d.ta, d.fa, d.Ta, d.Tv) == (73, 9, 657, 256)
+    B = 2
+    audio, img = rnd(B, d.audio_len, d.mel), rnd(B, 3, d.img, d.img)
+    ids_a = torch.argsort(torch.rand(B, d.Ta, device=DEV), dim=1).int()
+    ids_v = torch.argsort(torch.rand(B, d.Tv, device=DEV), dim=1).int()
+    ka, kv = 164, 64
+    pa = torch.full((B * ka, 200), float("nan"), dtype=torch.bfloat16, device=DEV)
+    pv = torch.full((B * kv, 592), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.patchify_audio(audio, ids_a, ka, 14, pa)
+    ops.patchify_video(img, ids_v, kv, 14, pv)
+    eye_a = torch.eye(196).reshape(196, 1, 14, 14)
+    eye_v = torch.eye(588).reshape(588, 3, 14, 14)
+    conv_a = torch.nn.functional.conv2d(audio.cpu().unsqueeze(1).transpose(2, 3), eye_a, stride=14).flatten(2).transpose(1, 2)
+    conv_v = torch.nn.functional.conv2d(img.cpu(), eye_v, stride=14).flatten(2).transpose(1, 2)
+    assert torch.equal(conv_a, O.patch_embed_audio(audio.cpu(), eye_a, torch.zeros(196), d))
+    assert torch.equal(conv_v, O.patch_embed_video(img.cpu(), eye_v, torch.zeros(588), d))
+    ref_a = torch.gather(conv_a, 1, ids_a[:, :ka].cpu().long().unsqueeze(-1).expand(-1, -1, 196)).reshape(B * ka, 196)
+    ref_v = torch.gather(conv_v, 1, ids_v[:, :kv].cpu().long().unsqueeze(-1).expand(-1, -1, 588)).reshape(B * kv, 588)
+    assert torch.equal(pa[:, :196].cpu(), ref_a.to(torch.bfloat16))
+    assert torch.equal(pv[:, :588].cpu(), ref_v.to(torch.bfloat16))
+    assert float(pa[:, 196:].abs().max()) == 0.0 and float(pv[:, 588:].abs().max()) == 0.0
+
+
 def test_decoder_restore_fwd_bwd():
     B, Ta, Tv, ka, kv, D = 3, 64, 36, 16, 9, 64
     torch.manual_seed(11)
@@ -329,7 +359,11 @@ def test_layernorm_rowmap_and_pool_grad():
                                           (7, 17, 2, 64), (64, 128, 12, 64), (101, 49, 12, 64),
                                           # tcgen05 forward range (head_dim 32, 256 <= S <= 768): unit / block edges
                                           (1, 256, 4, 32), (3, 257, 2, 32), (2, 300, 2, 32), (1, 511, 2, 32),
-                                          (1, 640, 2, 32), (2, 768, 2, 32)])
+                                          (1, 640, 2, 32), (2, 768, 2, 32),
+                                          # ViT-H/14 (BASELINE config 5): head_dim 80 at its kept-token counts 164 / 64,
+                                          # block / tile edges, and its 913-token sequence at the decoder's head_dim 32
+                                          (2, 164, 16, 80), (3, 64, 4, 80), (1, 657, 2, 80), (2, 65, 2, 80), (1, 7, 2, 80),
+                                          (2, 228, 2, 80), (1, 913, 2, 32)])
 def test_attention_fwd_bwd(n_seq, S, H, hd):
     D = H * hd
     qkv = rnd(n_seq * S, 3 * D, dtype=torch.bfloat16)

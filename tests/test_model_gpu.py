@@ -492,6 +492,70 @@ def test_vit_large_single_pass_against_fp32_oracle_on_gpu():
     torch.cuda.empty_cache()
 
 
+# ------------------------------------------------------------------------------------------------ ViT-H/14 (config 5)
+def _huge_case(d, B, seed, ratio=0.75):
+    """CAVMAE_HUGE as shipped (cav_mae_huge.cpython-39.pyc): single pass over the shared blocks, no
+    decoder, single-direction InfoNCE."""
+    model, sd = make_model(d, "single_pass", bidirect_contrast=False)
+    audio, imgs = synth_inputs(B, d, seed)
+    plan = O.make_mask_plan(B, d, seed + 1, two_pass=False)
+    kw = dict(mae_loss_weight=0.0, contrast_loss_weight=1.0, ratio_a=ratio, ratio_v=ratio, bidirect=False)
+    return model, sd, audio, imgs, plan, kw
+
+
+def _check_contrastive_only(model, out, ref, ref_grads, rtol, tag):
+    for i in (0, 4):        # loss, loss_c (the MAE losses are zero on both sides)
+        assert float(out[i]) == pytest.approx(float(ref[i]), rel=rtol, abs=1e-4), (i, float(out[i]), float(ref[i]))
+    assert float(out[1]) == 0.0 and float(ref[1]) == 0.0
+    assert float(out[7]) == pytest.approx(float(ref[7]), abs=1e-6)      # c_acc
+    out[0].backward()
+    named = dict(model.named_parameters())
+    got = {k for k, p in named.items() if p.grad is not None}
+    assert got == set(ref_grads), (sorted(got - set(ref_grads))[:5], sorted(set(ref_grads) - got)[:5])
+    cosines = {k: cos(named[k].grad, g) for k, g in ref_grads.items() if float(g.norm()) > 1e-12}
+    low = sorted((c, k) for k, c in cosines.items() if c < GRAD_COS_MIN)
+    print(f"[parity {tag}] loss {float(out[0]):.6f} vs {float(ref[0]):.6f}; worst gradient cosine "
+          f"{min(cosines.values()):.6f} over {len(cosines)} parameters")
+    assert not low, low[:8]
+
+
+@pytest.mark.parametrize("B,ratio", [(5, 0.5), (3, 0.0)])
+def test_huge_geometry_tiny_against_oracle(B, ratio):
+    """head_dim 80 (2 heads of 80), patch 14 on inputs it does not divide (100 x 30 fbank -> 7 x 2 tokens, 60 x 60 frame
+    -> 4 x 4), K-padded patch embedding (196 -> 200, 588 -> 592), every parameter's gradient against the live oracle."""
+    d = dataclasses.replace(O.TINY, embed_dim=160, heads=2, patch=14, audio_len=100, mel=30, img=60)
+    assert (d.Ta, d.Tv) == (14, 16)
+    model, sd, audio, imgs, plan, kw = _huge_case(d, B, 300 + B, ratio)
+    ref, state = run_oracle(O.forward_single_pass, audio, imgs, sd, d, plan, **kw)
+    model.mask_plan = plan
+    out = model(audio.to(DEV), imgs.to(DEV), ratio, ratio, mae_loss_weight=0.0, contrast_loss_weight=1.0)
+    ref_grads = {k: v.grad for k, v in state.items() if v.grad is not None}
+    _check_contrastive_only(model, out, ref, ref_grads, LOSS_RTOL_TINY, f"huge-geometry tiny B={B} ratio={ratio}")
+    with pytest.raises(RuntimeError, match="MAE branch needs a patch size dividing"):
+        model(audio.to(DEV), imgs.to(DEV), ratio, ratio, mae_loss_weight=1.0, contrast_loss_weight=1.0)
+
+
+def test_vit_huge_contrastive_against_fp32_oracle_on_gpu():
+    """BASELINE config 5, ViT-H/14 at FULL width and depth (D 1280, 32 blocks, 16 heads of 80, patch 14, 657 / 256 tokens,
+    164 / 64 kept at 75 %) against the fp32 oracle on the GPU: loss 1e-3, every parameter's gradient cosine >= 0.999."""
+    d = dataclasses.replace(O.VIT_H, head_classes=64, dec_depth=1)     # the (unused) decoder kept minimal
+    assert (d.Ta, d.Tv, d.embed_dim // d.heads) == (657, 256, 80)
+    B = 4
+    torch.cuda.empty_cache()
+    model, sd, audio, imgs, plan, kw = _huge_case(d, B, 95)
+    sd = {k: v for k, v in sd.items() if ".head." not in k}
+    ref, state = run_oracle_gpu(O.forward_single_pass, audio, imgs, sd, d, plan, **kw)
+    ref_vals = [float(r) for r in ref[:5]] + [None, None, float(ref[7])]
+    ref_grads = {k: v.grad.detach().cpu() for k, v in state.items() if v.grad is not None}
+    del ref, state
+    torch.cuda.empty_cache()
+    model.mask_plan = plan
+    out = model(audio.to(DEV), imgs.to(DEV), 0.75, 0.75, mae_loss_weight=0.0, contrast_loss_weight=1.0)
+    _check_contrastive_only(model, out, ref_vals, ref_grads, LOSS_RTOL_BF16, f"ViT-H/14 B={B}")
+    del model, out
+    torch.cuda.empty_cache()
+
+
 def test_graphed_train_step_matches_eager():
     """GraphedTrainStep (forward + reverse pass + fused Adam in one CUDA graph, device-side step counter) against the
     same steps issued eagerly. Mask ratio 0 with the contrastive loss only makes the step independent of the mask draws

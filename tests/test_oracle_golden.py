@@ -211,3 +211,21 @@ def test_augment_oracle_matches_torchvision_and_torchaudio_golden(golden_dir):
                              r=float(d.scale[0]) if c["noise"] else 0.0, shift=shift)
         assert np.array_equal(y, c["out"].numpy())                         # bit-exact, bands and roll included
     assert AO.band(0.5, 0.5, 0, 128) == (0, 0)
+
+
+def test_patch14_embed_is_the_strided_conv_and_huge_geometry():
+    """ViT-H/14 (BASELINE config 5): the reference's PatchEmbed is Conv2d(kernel = stride = patch)
+    (cav_mae_base.py:96-100); with patch 14 it reads 1022 x 126 of the 1024 x 128 fbank. The oracle's reshape-based patch
+    embedding must equal torch's conv2d on that geometry, and the geometry must give the pyc's token counts."""
+    d = O.VIT_H
+    assert (d.ta, d.fa, d.Ta, d.Tv, d.embed_dim // d.heads) == (73, 9, 657, 256, 80)
+    assert (O.len_keep_of(d.Ta, 0.75), O.len_keep_of(d.Tv, 0.75)) == (164, 64)
+    g = torch.Generator().manual_seed(5)
+    audio = torch.randn(2, d.audio_len, d.mel, generator=g)
+    img = torch.randn(2, 3, d.img, d.img, generator=g)
+    wa, wv, b = torch.randn(24, 1, 14, 14, generator=g), torch.randn(24, 3, 14, 14, generator=g), torch.randn(24, generator=g)
+    F = torch.nn.functional
+    ref_a = F.conv2d(audio.unsqueeze(1).transpose(2, 3), wa, b, stride=14).flatten(2).transpose(1, 2)
+    ref_v = F.conv2d(img, wv, b, stride=14).flatten(2).transpose(1, 2)
+    assert torch.allclose(O.patch_embed_audio(audio, wa, b, d), ref_a, atol=2e-5, rtol=1e-5)
+    assert torch.allclose(O.patch_embed_video(img, wv, b, d), ref_v, atol=2e-5, rtol=1e-5)
