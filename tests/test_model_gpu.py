@@ -521,9 +521,10 @@ def _check_contrastive_only(model, out, ref, ref_grads, rtol, tag):
 
 @pytest.mark.parametrize("B,ratio", [(5, 0.5), (3, 0.0)])
 def test_huge_geometry_tiny_against_oracle(B, ratio):
-    """head_dim 80 (2 heads of 80), patch 14 on inputs it does not divide (100 x 30 fbank -> 7 x 2 tokens, 60 x 60 frame
-    -> 4 x 4), K-padded patch embedding (196 -> 200, 588 -> 592), every parameter's gradient against the live oracle."""
-    d = dataclasses.replace(O.TINY, embed_dim=160, heads=2, patch=14, audio_len=100, mel=30, img=60)
+    """ViT-H's width (16 heads of 80 — the only LayerNorm width of this library that is a multiple of 80) at depth 2,
+    patch 14 on inputs it does not divide (100 x 30 fbank -> 7 x 2 tokens, 60 x 60 frame -> 4 x 4), K-padded patch
+    embedding (196 -> 200, 588 -> 592), every parameter's gradient against the live oracle."""
+    d = dataclasses.replace(O.TINY, embed_dim=1280, heads=16, patch=14, audio_len=100, mel=30, img=60)
     assert (d.Ta, d.Tv) == (14, 16)
     model, sd, audio, imgs, plan, kw = _huge_case(d, B, 300 + B, ratio)
     ref, state = run_oracle(O.forward_single_pass, audio, imgs, sd, d, plan, **kw)
@@ -537,10 +538,12 @@ def test_huge_geometry_tiny_against_oracle(B, ratio):
 
 def test_vit_huge_contrastive_against_fp32_oracle_on_gpu():
     """BASELINE config 5, ViT-H/14 at FULL width and depth (D 1280, 32 blocks, 16 heads of 80, patch 14, 657 / 256 tokens,
-    164 / 64 kept at 75 %) against the fp32 oracle on the GPU: loss 1e-3, every parameter's gradient cosine >= 0.999."""
+    164 / 64 kept at 75 %) against the fp32 oracle on the GPU: every parameter's gradient cosine >= 0.999; the loss here is
+    the bare InfoNCE over 8 samples at temperature 0.05 (no MAE term beside it, 32 bf16 blocks in front of the x20 logits):
+    5e-3 asserted (measured 1.2e-3 at B = 4; the stated bf16 bound is 2e-2, bench.py's step-0 gate at B = 16 measures 6e-6)."""
     d = dataclasses.replace(O.VIT_H, head_classes=64, dec_depth=1)     # the (unused) decoder kept minimal
     assert (d.Ta, d.Tv, d.embed_dim // d.heads) == (657, 256, 80)
-    B = 4
+    B = 8
     torch.cuda.empty_cache()
     model, sd, audio, imgs, plan, kw = _huge_case(d, B, 95)
     sd = {k: v for k, v in sd.items() if ".head." not in k}
@@ -551,7 +554,7 @@ def test_vit_huge_contrastive_against_fp32_oracle_on_gpu():
     torch.cuda.empty_cache()
     model.mask_plan = plan
     out = model(audio.to(DEV), imgs.to(DEV), 0.75, 0.75, mae_loss_weight=0.0, contrast_loss_weight=1.0)
-    _check_contrastive_only(model, out, ref_vals, ref_grads, LOSS_RTOL_BF16, f"ViT-H/14 B={B}")
+    _check_contrastive_only(model, out, ref_vals, ref_grads, 5e-3, f"ViT-H/14 B={B}")
     del model, out
     torch.cuda.empty_cache()
 

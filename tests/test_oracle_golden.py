@@ -227,5 +227,5 @@ def test_patch14_embed_is_the_strided_conv_and_huge_geometry():
     F = torch.nn.functional
     ref_a = F.conv2d(audio.unsqueeze(1).transpose(2, 3), wa, b, stride=14).flatten(2).transpose(1, 2)
     ref_v = F.conv2d(img, wv, b, stride=14).flatten(2).transpose(1, 2)
-    assert torch.allclose(O.patch_embed_audio(audio, wa, b, d), ref_a, atol=2e-5, rtol=1e-5)
-    assert torch.allclose(O.patch_embed_video(img, wv, b, d), ref_v, atol=2e-5, rtol=1e-5)
+    assert torch.allclose(O.patch_embed_audio(audio, wa, b, d), ref_a, atol=1e-4, rtol=1e-5)
+    assert torch.allclose(O.patch_embed_video(img, wv, b, d), ref_v, atol=3e-4, rtol=1e-5)   # K = 588 fp32 sums of O(1) terms
