@@ -84,6 +84,10 @@ constexpr int GEMM_EPI_BUF = 32 * GEMM_EPI_CHUNK * 2;  // one [32 rows x 32 cols
 #ifndef AVS_GEMM_TMEM_PF
 #define AVS_GEMM_TMEM_PF 0
 #endif
+#ifndef AVS_GEMM_L2_PF
+#define AVS_GEMM_L2_PF 0
+#endif
+constexpr int GEMM_L2_PF = AVS_GEMM_L2_PF;         // k-blocks of L2 prefetch ahead of the A-operand loads (0 = off)
 constexpr int GEMM_IN_DEPTH = AVS_GEMM_IN_DEPTH;   // input tiles in flight per epilogue warp (ring; chunk q uses slot q % depth)
 constexpr bool GEMM_TMEM_PF = AVS_GEMM_TMEM_PF != 0;   // tcgen05.ld of chunk c+1 issued before chunk c's math
 static_assert(GEMM_IN_DEPTH >= 2 && GEMM_IN_DEPTH <= 4, "input-tile ring depth");
@@ -219,6 +223,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // The whole warp runs the loop convergently (loop state stays in uniform registers); one elected lane issues.
     int stage = 0;
     uint32_t phase = 0;
+    // L2 prefetch cursor (K-major A = the activation stream of forward / dgrad products): runs GEMM_L2_PF k-blocks ahead
+    // of the load cursor through this CTA's own (tile, k-block) sequence, so that the ring's TMA loads find their A boxes
+    // in L2 instead of waiting for HBM behind the epilogue's stores (the ring holds only 3-4 k-blocks = ~1 us of MMAs)
+    constexpr bool L2_PF = GEMM_L2_PF > 0 && A_MAJOR == MAJOR_K;
+    int tp = blockIdx.x, kbp = 0, kb1p = 0, m0p = 0;
+    auto pf_tile = [&]() {
+      if (tp < num_tiles) {
+        const int ksp = tp / mn_tiles;
+        m0p = ((tp - ksp * mn_tiles) / n_tiles) * GEMM_BLOCK_M;
+        kbp = ksp * args.kb_per_split;
+        kb1p = min(total_kb, kbp + args.kb_per_split);
+      }
+    };
+    auto pf_step = [&]() {
+      if (tp >= num_tiles) return;
+      if (elect_one_sync()) tma_prefetch_l2_2d(&tma_a, kbp * GEMM_BLOCK_K, m0p);
+      if (++kbp == kb1p) {
+        tp += gridDim.x;
+        pf_tile();
+      }
+    };
+    if constexpr (L2_PF) {
+      pf_tile();
+#pragma unroll 1
+      for (int i = 0; i < GEMM_L2_PF; ++i) pf_step();
+    }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int ks = t / mn_tiles;   // output tile fastest: the CTAs that run together share a k-range (see mn_tiles)
       const int mn = t - ks * mn_tiles;
@@ -227,6 +257,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int kb0 = ks * args.kb_per_split;
       const int kb1 = min(total_kb, kb0 + args.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
+        if constexpr (L2_PF) pf_step();
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
