@@ -487,6 +487,14 @@ int check_common(const void* qkv, long long ld_qkv, long long ld_o, int n_seq, i
   return 0;
 }
 
+// head_dim 80 runs at one 8-warp or two 4-warp CTAs per SM (registers): with 16-row tiles dealt round-robin to the warps,
+// S = 164 (ViT-H's kept audio tokens: 11 tiles) leaves 5 of 16 warp-slots idle with 8 warps and 1 of 12 with 4.
+bool few_warps_balance_better(int S) {
+  const int tiles = (S + 15) / 16;
+  const int waste4 = (tiles + 3) / 4 * 4 - tiles, waste8 = (tiles + 7) / 8 * 8 - tiles;
+  return waste4 * (long long)((tiles + 7) / 8 * 8) < waste8 * (long long)((tiles + 3) / 4 * 4);   // idle fraction
+}
+
 }  // namespace
 
 bool avs_attention_tc_enabled() {
@@ -525,8 +533,8 @@ extern "C" int avs_attention_fwd(const void* qkv, long long ld_qkv, void* out, l
     if ((rc = set_smem(attn_fwd_kernel<HD_, W_>, smem, "avs_attention_fwd"))) return rc;             \
     attn_fwd_kernel<HD_, W_><<<grid, W_ * 32, smem, (cudaStream_t)stream>>>(a);                      \
   } while (0)
-  if (head_dim == 80) {   // ViT-H/14: 5 MMA k-steps per row, one CTA per SM's register budget
-    if (small) AVS_LAUNCH_FWD(80, 4); else AVS_LAUNCH_FWD(80, 8);
+  if (head_dim == 80) {   // ViT-H/14: 5 MMA k-steps per row, ~230 registers per thread
+    if (small || few_warps_balance_better(S)) AVS_LAUNCH_FWD(80, 4); else AVS_LAUNCH_FWD(80, 8);
   } else if (head_dim == 64) {
     if (small) AVS_LAUNCH_FWD(64, 4); else AVS_LAUNCH_FWD(64, 8);
   } else {
@@ -580,7 +588,7 @@ extern "C" int avs_attention_bwd(const void* qkv, long long ld_qkv, const void* 
     attn_bwd_dq_kernel<HD_, W_><<<grid, W_ * 32, smem_dq, stream>>>(a);                              \
   } while (0)
   if (head_dim == 80) {
-    if (small) AVS_LAUNCH_BWD(80, 4); else AVS_LAUNCH_BWD(80, 8);
+    if (small || few_warps_balance_better(S)) AVS_LAUNCH_BWD(80, 4); else AVS_LAUNCH_BWD(80, 8);
   } else if (head_dim == 64) {
     if (small) AVS_LAUNCH_BWD(64, 4); else AVS_LAUNCH_BWD(64, 8);
   } else {
