@@ -152,8 +152,14 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
 // RG row groups and each group keeps LNB_R rows in flight.  The per-column accumulators (dgamma, dbeta, and the
 // column sum of the produced dx = bias gradient of the Linear that feeds this residual stream) are therefore
 // 3 x 8 registers per thread instead of 3 x D/32, and x / dy / resid stay packed in bf16 until used.
-constexpr int LNB_R = 2;
-constexpr int LNB_STAGES = 3;   // iterations of x / dy / resid chunks in flight per thread (cp.async ring)
+#ifndef AVS_LNB_R
+#define AVS_LNB_R 2
+#endif
+#ifndef AVS_LNB_STAGES
+#define AVS_LNB_STAGES 3
+#endif
+constexpr int LNB_R = AVS_LNB_R;
+constexpr int LNB_STAGES = AVS_LNB_STAGES;   // iterations of x / dy / resid chunks in flight per thread (cp.async ring)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
@@ -346,7 +352,13 @@ __global__ void __launch_bounds__(TPR * RG, 2) layernorm_bwd_kernel(
 // TPR consecutive threads, LNF_R rows per row group and iteration, x travels through a per-thread cp.async ring
 // LNF_STAGES iterations deep, and the two reductions (mean, centred second moment) synchronise only the WPG warps of a
 // row group through a named barrier.
-constexpr int LNF_R = 2, LNF_STAGES = 4;
+#ifndef AVS_LNF_R
+#define AVS_LNF_R 4   // rows in flight per row group: 2 -> 4 measured +5 % (decoder) ... +10 % (encoder shapes), profiles/r02_ln_ab.log
+#endif
+#ifndef AVS_LNF_STAGES
+#define AVS_LNF_STAGES 4
+#endif
+constexpr int LNF_R = AVS_LNF_R, LNF_STAGES = AVS_LNF_STAGES;
 template <int TPR, int RG>
 __global__ void __launch_bounds__(TPR * RG, 2) layernorm_fwd_rg_kernel(
     const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
