@@ -8,8 +8,13 @@
 #include "../../include/avsiam_b200.h"
 #include "common.cuh"
 #include "gemm_sm100.cuh"
+#include "gemm_sm100_2cta.cuh"
 
 using namespace avs;
+
+#ifndef AVS_GEMM_2CTA_DEFAULT
+#define AVS_GEMM_2CTA_DEFAULT 1   // AVS_GEMM_2CTA=0 in the environment keeps the one-CTA kernel everywhere (A/B)
+#endif
 
 #ifdef AVS_GEMM_DEBUG   // probe / timing builds only: the release library carries no debug switches in its epilogue
 static int g_desc_variant = getenv("AVS_GEMM_DEBUG") ? atoi(getenv("AVS_GEMM_DEBUG")) : 0;
@@ -133,6 +138,45 @@ static int launch_gemm(const GemmMaps& tm, GemmArgs& args, int grid, cudaStream_
   return avs_check_launch("gemm_bf16_kernel");
 }
 
+// ---- two-CTA (cta_group::2) kernel: forward / dgrad products with bf16 outputs at N > 128 (gemm_sm100_2cta.cuh) ----
+template <int BM, int EPI>
+static int launch_gemm_pair(const GemmMaps& tm, GemmArgs& args, int grid, cudaStream_t stream) {
+  static bool attr_set = false;  // idempotent; benign race
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<BM, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GEMM_SMEM_LIMIT);
+    if (e != cudaSuccess) {
+      avs_set_error("cudaFuncSetAttribute(gemm pair smem=%d): %s", GEMM_SMEM_LIMIT, cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  const int epw = Gemm2Cfg::epi_bytes_per_warp(args.tma_epi, args.has_in, args.has_aux_out);
+  const int extra = (EPI == GEMM_E_MUL) ? GEMM_COLSUM_BYTES : 0;
+  args.stages = Gemm2Cfg::pick_stages(epw, extra);
+  const int smem = Gemm2Cfg::smem_bytes(args.stages, epw, extra);
+  gemm2_bf16_kernel<BM, EPI><<<grid, GEMM_THREADS, smem, stream>>>(tm.a, tm.b, tm.c, tm.in, tm.aux, args);   // __cluster_dims__(2)
+  return avs_check_launch("gemm2_bf16_kernel");
+}
+
+template <int BM>
+static int launch_gemm_pair_class(int cls, const GemmMaps& tm, GemmArgs& args, int grid, cudaStream_t stream) {
+  switch (cls) {
+    case GEMM_E_PLAIN: return launch_gemm_pair<BM, GEMM_E_PLAIN>(tm, args, grid, stream);
+    case GEMM_E_GELU: return launch_gemm_pair<BM, GEMM_E_GELU>(tm, args, grid, stream);
+    case GEMM_E_RESID: return launch_gemm_pair<BM, GEMM_E_RESID>(tm, args, grid, stream);
+    default: return launch_gemm_pair<BM, GEMM_E_MUL>(tm, args, grid, stream);
+  }
+}
+
+static bool gemm_pair_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("AVS_GEMM_2CTA");
+    return e ? atoi(e) != 0 : AVS_GEMM_2CTA_DEFAULT != 0;
+  }();
+  return on;
+}
+
 template <int AM, int BM, int BN>
 static int launch_gemm_class(int cls, const GemmMaps& tm, GemmArgs& args, int grid, cudaStream_t stream) {
   switch (cls) {
@@ -174,7 +218,9 @@ extern "C" int avs_gemm_bf16(const void* A, long long lda, int a_major, const vo
   AVS_REQUIRE(!(epi->resid && cls == GEMM_E_GELU), "avs_gemm_bf16: GELU and resid cannot be combined");
 
   const int BN = (N > 128) ? 256 : 128;
-  const int m_tiles = ceil_div(M, GEMM_BLOCK_M), n_tiles = ceil_div(N, BN);
+  // forward / dgrad products with bf16 outputs and N > 128: a pair of CTAs per 256 x 256 tile (gemm_sm100_2cta.cuh)
+  const bool pair = gemm_pair_enabled() && !out_f32 && a_major == 0 && BN == 256 && split_k <= 1 && M > GEMM_BLOCK_M;
+  const int m_tiles = ceil_div(M, pair ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M), n_tiles = ceil_div(N, BN);
   const int total_kb = ceil_div(K, GEMM_BLOCK_K);
   const int sms = avs_num_sms();
   if (split_k <= 0) {  // auto: only meaningful with atomic accumulation
@@ -207,7 +253,7 @@ extern "C" int avs_gemm_bf16(const void* A, long long lda, int a_major, const vo
   if (a_major == 0) rc = make_tmap_2d(&tm.a, A, M, K, lda, GEMM_BLOCK_K, GEMM_BLOCK_M);
   else rc = make_tmap_2d(&tm.a, A, K, M, lda, 64, GEMM_BLOCK_K);
   if (rc) return rc;
-  if (b_major == 0) rc = make_tmap_2d(&tm.b, B, N, K, ldb, GEMM_BLOCK_K, BN);
+  if (b_major == 0) rc = make_tmap_2d(&tm.b, B, N, K, ldb, GEMM_BLOCK_K, pair ? BN / 2 : BN);   // pair: each CTA loads half
   else rc = make_tmap_2d(&tm.b, B, K, N, ldb, 64, GEMM_BLOCK_K);
   if (rc) return rc;
   // bf16 outputs leave as [32 x 64] tiles (128-byte swizzle), the residual / dGELU operand arrives as [32 x 32]
@@ -254,6 +300,11 @@ extern "C" int avs_gemm_bf16(const void* A, long long lda, int a_major, const vo
   args.epi.colsum = epi->colsum;
 
   const int num_tiles = m_tiles * n_tiles * split_k;
+  if (pair) {
+    const int clusters = num_tiles < sms / 2 ? num_tiles : sms / 2;
+    if (b_major == 0) return launch_gemm_pair_class<MAJOR_K>(cls, tm, args, 2 * clusters, stream);
+    return launch_gemm_pair_class<MAJOR_MN>(cls, tm, args, 2 * clusters, stream);
+  }
   const int grid = num_tiles < sms ? num_tiles : sms;
   const int key = a_major * 2 + b_major;
   if (BN == 256) {
