@@ -12,6 +12,9 @@
 
 using namespace avs;
 
+#ifndef AVS_GEMM_EW16_DEFAULT
+#define AVS_GEMM_EW16_DEFAULT 1
+#endif
 #ifndef AVS_GEMM_2CTA_DEFAULT
 #define AVS_GEMM_2CTA_DEFAULT 1   // AVS_GEMM_2CTA=0 in the environment keeps the one-CTA kernel everywhere (A/B)
 #endif
@@ -139,11 +142,11 @@ static int launch_gemm(const GemmMaps& tm, GemmArgs& args, int grid, cudaStream_
 }
 
 // ---- two-CTA (cta_group::2) kernel: forward / dgrad products with bf16 outputs at N > 128 (gemm_sm100_2cta.cuh) ----
-template <int BM, int EPI>
+template <int BM, int EPI, int EW = GEMM_EPI_WARPS>
 static int launch_gemm_pair(const GemmMaps& tm, GemmArgs& args, int grid, cudaStream_t stream) {
   static bool attr_set = false;  // idempotent; benign race
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<BM, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<BM, EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GEMM_SMEM_LIMIT);
     if (e != cudaSuccess) {
       avs_set_error("cudaFuncSetAttribute(gemm pair smem=%d): %s", GEMM_SMEM_LIMIT, cudaGetErrorString(e));
@@ -155,7 +158,7 @@ static int launch_gemm_pair(const GemmMaps& tm, GemmArgs& args, int grid, cudaSt
   const int extra = (EPI == GEMM_E_MUL) ? GEMM_COLSUM_BYTES : 0;
   args.stages = Gemm2Cfg::pick_stages(epw, extra);
   const int smem = Gemm2Cfg::smem_bytes(args.stages, epw, extra);
-  gemm2_bf16_kernel<BM, EPI><<<grid, GEMM_THREADS, smem, stream>>>(tm.a, tm.b, tm.c, tm.in, tm.aux, args);   // __cluster_dims__(2)
+  gemm2_bf16_kernel<BM, EPI, EW><<<grid, 64 + 32 * EW, smem, stream>>>(tm.a, tm.b, tm.c, tm.in, tm.aux, args);   // __cluster_dims__(2)
   return avs_check_launch("gemm2_bf16_kernel");
 }
 
@@ -163,7 +166,11 @@ template <int BM>
 static int launch_gemm_pair_class(int cls, const GemmMaps& tm, GemmArgs& args, int grid, cudaStream_t stream) {
   switch (cls) {
     case GEMM_E_PLAIN: return launch_gemm_pair<BM, GEMM_E_PLAIN>(tm, args, grid, stream);
-    case GEMM_E_GELU: return launch_gemm_pair<BM, GEMM_E_GELU>(tm, args, grid, stream);
+    case GEMM_E_GELU: {   // fc1: 16 epilogue warps in pairs (AVS_GEMM_EW16=0 keeps 8)
+      static const bool ew16 = getenv("AVS_GEMM_EW16") ? atoi(getenv("AVS_GEMM_EW16")) != 0 : AVS_GEMM_EW16_DEFAULT != 0;
+      if (ew16) return launch_gemm_pair<BM, GEMM_E_GELU, 16>(tm, args, grid, stream);
+      return launch_gemm_pair<BM, GEMM_E_GELU>(tm, args, grid, stream);
+    }
     case GEMM_E_RESID: return launch_gemm_pair<BM, GEMM_E_RESID>(tm, args, grid, stream);
     default: return launch_gemm_pair<BM, GEMM_E_MUL>(tm, args, grid, stream);
   }

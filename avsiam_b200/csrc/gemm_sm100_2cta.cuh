@@ -96,8 +96,14 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                : "memory");
 }
 
-template <int B_MAJOR, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+// EW = epilogue warps per CTA: 8 (two per TMEM lane quarter, each walking half of the tile's columns through its own
+// staging tiles) or, for the GELU class, 16: four per quarter, where the two warps of a PAIR fill the left / right 32 columns
+// of the same 64-column staging tile and meet on a 64-thread named barrier — the staging memory, and with it the depth of
+// the operand ring, stays what it is with 8 warps.  The GELU (+ derivative) epilogue is ~15 FP32 / MUFU instructions per
+// element with two warps per scheduler eligible 44 % of the time; four warps per scheduler hide the
+// TMEM-load / MUFU / barrier waits.
+template <int B_MAJOR, int EPI, int EW = GEMM_EPI_WARPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_in,
                   const __grid_constant__ CUtensorMap tma_aux, const GemmArgs args) {
@@ -150,7 +156,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 2 * GEMM_EPI_WARPS);
+      mbar_init(&tempty_bar[a], 2 * EW);
     }
     for (int i = 0; i < 4 * GEMM_EPI_WARPS; ++i) mbar_init(&in_bar[i], 1);
     fence_mbar_init();
@@ -238,6 +244,100 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         if (acc == 0) acc_phase ^= 1;
       }
     }
+  } else if constexpr (EW == 16) {
+    // ============================ epilogue, 16 warps in pairs (GELU class) ============================
+    static_assert(EW != 16 || EPI == GEMM_E_GELU, "16 epilogue warps: GELU class");
+    const int ew = warp - 2;
+    const int quarter = warp & 3;          // TMEM lane quarter (= scheduler) of this warp
+    const int kq = ew >> 2;                // 0..3: which of the quarter's four warps
+    const int pairi = kq >> 1;             // the pair's half of the tile's columns (128 each)
+    const int side = kq & 1;               // left / right 32 columns of each 64-column block
+    const int slot = quarter * 2 + pairi;  // staging slot shared by the pair
+    const int bar_id = 1 + slot;           // named barrier of the pair (64 threads)
+    const GemmEpilogue& ep = args.epi;
+    uint8_t* out_buf = smem_epi + slot * epi_per_warp;
+    uint8_t* aux_buf = out_buf + GEMM_OUT_BUF;
+    const bool has_aux = args.has_aux_out != 0;
+    const bool aux_grad = has_aux && (ep.flags & EPI_AUX_GRAD);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int m0 = (t / n_tiles) * (2 * GEMM_BLOCK_M) + (int)cta_rank * GEMM_BLOCK_M;
+      const int n0 = (t % n_tiles) * BLOCK_N;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int b = 0; b < 2; ++b) {
+        const int ccol = pairi * 128 + b * 64 + side * 32;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + ccol), r);
+        tmem_ld_wait();
+        if (b == 1) {  // accumulator fully read by this warp: hand it back to the pair's issuer (CTA 0)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)acc * 8u);
+        }
+        const int nc = n0 + ccol;
+        const bool col_ok = nc < args.N;
+        const bool full = (nc + 32 <= args.N);
+        uint4 o[4], ax[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {      // 16 columns at a time: bounded live registers (112 per thread at 576 threads)
+          float v[16], dg[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[16 * h + j]);
+          if (ep.bias != nullptr && col_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              if (full || nc + 16 * h + j < args.N) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + nc + 16 * h + j));
+                v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+              }
+            }
+          }
+          if (aux_grad) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) gelu_and_grad(v[j], v[j], dg[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { dg[j] = v[j]; v[j] = gelu_erf(v[j]); }   // aux (if any) = pre-activation
+          }
+          if (ep.alpha != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] *= ep.alpha;
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            o[2 * h + j].x = pack_bf16x2(v[8 * j], v[8 * j + 1]); o[2 * h + j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            o[2 * h + j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); o[2 * h + j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            ax[2 * h + j].x = pack_bf16x2(dg[8 * j], dg[8 * j + 1]); ax[2 * h + j].y = pack_bf16x2(dg[8 * j + 2], dg[8 * j + 3]);
+            ax[2 * h + j].z = pack_bf16x2(dg[8 * j + 4], dg[8 * j + 5]); ax[2 * h + j].w = pack_bf16x2(dg[8 * j + 6], dg[8 * j + 7]);
+          }
+        }
+        // the pair's previous stores have finished reading the staging tiles (only the issuing thread holds bulk groups)
+        if (side == 0 && lane == 0) bulk_wait_read0();
+        asm volatile("bar.sync %0, 64;\n" ::"r"(bar_id) : "memory");
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(out_buf + out_tile_off(lane, side * 4 + j)) = o[j];
+        if (has_aux) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(aux_buf + out_tile_off(lane, side * 4 + j)) = ax[j];
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 64;\n" ::"r"(bar_id) : "memory");
+        if (side == 0 && lane == 0) {
+          const int nc0 = n0 + pairi * 128 + b * 64;   // first column of the 64-column block
+          if (nc0 < args.N && m0 + quarter * 32 < args.M) {   // TMA clips the M / N tails
+            tma_store_2d(&tma_c, out_buf, nc0, m0 + quarter * 32);
+            if (has_aux) tma_store_2d(&tma_aux, aux_buf, nc0, m0 + quarter * 32);
+          }
+          bulk_commit();
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (side == 0 && lane == 0) bulk_wait0();  // all stores retired before the CTA exits
   } else {
     // ============================ epilogue (8 warps) ============================
     // warp w may only touch TMEM lanes 32*(w%4)..+32; the two warps sharing a quarter split the tile's columns.
