@@ -483,7 +483,7 @@ static int ln_fwd_impl(const void* x, const float* gamma, const float* beta, flo
   if (rg_path && (D == 512 || D == 768 || D == 1024 || D == 1280)) {
     if (D == 512) launch_ln_fwd_rg<64, 4>(x, gamma, beta, eps, y, mean, rstd, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off, gamma1, beta1, split, stream);
     else if (D == 1280) launch_ln_fwd_rg<160, 2>(x, gamma, beta, eps, y, mean, rstd, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off, gamma1, beta1, split, stream);   // ViT-H
-    else if (D == 768) launch_ln_fwd_rg<96, 2>(x, gamma, beta, eps, y, mean, rstd, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off, gamma1, beta1, split, stream);
+    else if (D == 768) launch_ln_fwd_rg<96, 4>(x, gamma, beta, eps, y, mean, rstd, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off, gamma1, beta1, split, stream);
     else launch_ln_fwd_rg<128, 2>(x, gamma, beta, eps, y, mean, rstd, M, seq_len, x_seq_stride, x_off, y_seq_stride, y_off, gamma1, beta1, split, stream);
     return avs_check_launch("layernorm_fwd_rg_kernel");
   }
