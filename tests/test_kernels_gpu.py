@@ -30,7 +30,12 @@ def rel_err(a, b):
 
 
 # ------------------------------------------------------------------------------------------------ GEMM
-@pytest.mark.parametrize("M,N,K", [(354, 768, 768), (1000, 2304, 768), (256, 128, 200), (45, 512, 3072)])
+@pytest.mark.parametrize("M,N,K", [(354, 768, 768), (1000, 2304, 768), (256, 128, 200), (45, 512, 3072),
+                                   # two-CTA kernel edges (N > 128, M > 128): a pair whose second CTA has no valid row
+                                   # (M = 129, 300), ragged N / K tails, one more tile than clusters (74 on a B200),
+                                   # many tiles per cluster with both TMEM buffers and every ring phase in play
+                                   (129, 136, 72), (257, 264, 64), (300, 520, 200), (256, 256, 64), (19200, 256, 512),
+                                   (4000, 3072, 768)])
 def test_gemm_fwd_bias_gelu_resid(M, N, K):
     a, w = rnd(M, K, dtype=torch.bfloat16), rnd(N, K, scale=K ** -0.5, dtype=torch.bfloat16)
     bias, res = rnd(N), rnd(M, N, dtype=torch.bfloat16)
@@ -48,6 +53,20 @@ def test_gemm_fwd_bias_gelu_resid(M, N, K):
     assert rel_err(out, 0.5 * ref_pre) < 6e-3
     with pytest.raises(RuntimeError):                                        # one epilogue class per launch
         ops.gemm(a, w, out, M, N, K, bias=bias, gelu=True, resid=res)
+
+
+@pytest.mark.parametrize("env", [{"AVS_GEMM_2CTA": "0"}, {"AVS_GEMM_EW16": "0"}])
+def test_gemm_fallback_kernels_in_a_subprocess(env):
+    """The kernel choice is read from the environment once per process: the one-CTA kernel for every product
+    (AVS_GEMM_2CTA=0) and the 8-warp GELU epilogue of the two-CTA kernel (AVS_GEMM_EW16=0) stay covered by running this
+    file's GEMM tests in a child process with the switch set."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                        "gemm and not subprocess"], cwd=root, env={**os.environ, **env}, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_gemm_rowadd_alpha_patch_embed_epilogue():
