@@ -12,6 +12,9 @@
 
 using namespace avs;
 
+#ifndef AVS_GEMM_MUL16_DEFAULT
+#define AVS_GEMM_MUL16_DEFAULT 1
+#endif
 #ifndef AVS_GEMM_EW16_DEFAULT
 #define AVS_GEMM_EW16_DEFAULT 1
 #endif
@@ -154,10 +157,10 @@ static int launch_gemm_pair(const GemmMaps& tm, GemmArgs& args, int grid, cudaSt
     }
     attr_set = true;
   }
-  const int epw = Gemm2Cfg::epi_bytes_per_warp(args.tma_epi, args.has_in, args.has_aux_out);
+  const int staging = Gemm2Cfg::staging_bytes(EW, args.has_in, args.has_aux_out);
   const int extra = (EPI == GEMM_E_MUL) ? GEMM_COLSUM_BYTES : 0;
-  args.stages = Gemm2Cfg::pick_stages(epw, extra);
-  const int smem = Gemm2Cfg::smem_bytes(args.stages, epw, extra);
+  args.stages = Gemm2Cfg::pick_stages(staging, extra);
+  const int smem = Gemm2Cfg::smem_bytes(args.stages, staging, extra);
   gemm2_bf16_kernel<BM, EPI, EW><<<grid, 64 + 32 * EW, smem, stream>>>(tm.a, tm.b, tm.c, tm.in, tm.aux, args);   // __cluster_dims__(2)
   return avs_check_launch("gemm2_bf16_kernel");
 }
@@ -172,7 +175,11 @@ static int launch_gemm_pair_class(int cls, const GemmMaps& tm, GemmArgs& args, i
       return launch_gemm_pair<BM, GEMM_E_GELU>(tm, args, grid, stream);
     }
     case GEMM_E_RESID: return launch_gemm_pair<BM, GEMM_E_RESID>(tm, args, grid, stream);
-    default: return launch_gemm_pair<BM, GEMM_E_MUL>(tm, args, grid, stream);
+    default: {            // fc2 dgrad x derivative: 16 epilogue warps, 3 operand stages (AVS_GEMM_MUL16=0: 8 warps, 4 stages)
+      static const bool mul16 = getenv("AVS_GEMM_MUL16") ? atoi(getenv("AVS_GEMM_MUL16")) != 0 : AVS_GEMM_MUL16_DEFAULT != 0;
+      if (mul16) return launch_gemm_pair<BM, GEMM_E_MUL, 16>(tm, args, grid, stream);
+      return launch_gemm_pair<BM, GEMM_E_MUL>(tm, args, grid, stream);
+    }
   }
 }
 

@@ -27,16 +27,23 @@ struct Gemm2Cfg {
   static constexpr int B_BYTES = (BLOCK_N / 2) * GEMM_BLOCK_K * 2;      // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;                 // 32 KB
   static constexpr int TMEM_COLS = 512;
-  static constexpr int BAR_BYTES = 512;
+  static constexpr int BAR_BYTES = 1024;   // [8 full][8 empty][2 tfull][2 tempty][16 x 4 in-stream] barriers + the TMEM slot
   static __host__ __device__ int epi_bytes_per_warp(int tma_epi, int has_in, int has_aux_out) {
     return GemmCfg<BLOCK_N>::epi_bytes_per_warp(tma_epi, has_in, has_aux_out);
   }
-  static __host__ int pick_stages(int epi_per_warp, int extra = 0) {
-    int s = (GEMM_SMEM_LIMIT - 1024 - BAR_BYTES - extra - GEMM_EPI_WARPS * epi_per_warp) / STAGE_BYTES;
+  // staging bytes of the whole CTA: 8 slots of [in ring][out][aux] with 8 epilogue warps; with 16 warps the 8 PAIRS share
+  // the out (/ aux) tiles and every warp keeps its own in-stream ring
+  static __host__ __device__ int staging_bytes(int ew, int has_in, int has_aux_out) {
+    if (ew == 16)
+      return 16 * (has_in ? GEMM_IN_DEPTH * GEMM_EPI_BUF : 0) + 8 * GEMM_OUT_BUF * (1 + (has_aux_out ? 1 : 0));
+    return GEMM_EPI_WARPS * epi_bytes_per_warp(1, has_in, has_aux_out);
+  }
+  static __host__ int pick_stages(int staging, int extra = 0) {
+    int s = (GEMM_SMEM_LIMIT - 1024 - BAR_BYTES - extra - staging) / STAGE_BYTES;
     return s > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : s;
   }
-  static __host__ int smem_bytes(int stages, int epi_per_warp, int extra = 0) {
-    return stages * STAGE_BYTES + GEMM_EPI_WARPS * epi_per_warp + 1024 + BAR_BYTES + extra;
+  static __host__ int smem_bytes(int stages, int staging, int extra = 0) {
+    return stages * STAGE_BYTES + staging + 1024 + BAR_BYTES + extra;
   }
 };
 
@@ -122,13 +129,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
   const int epi_per_warp = Cfg::epi_bytes_per_warp(args.tma_epi, args.has_in, args.has_aux_out);
   uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + GEMM_EPI_WARPS * epi_per_warp);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::staging_bytes(EW, args.has_in, args.has_aux_out));
   uint64_t* full_bar = bars;                               // [MAX_STAGES]   (the leader's are used)
   uint64_t* empty_bar = bars + GEMM_MAX_STAGES;            // [MAX_STAGES]
   uint64_t* tfull_bar = bars + 2 * GEMM_MAX_STAGES;        // [2]
   uint64_t* tempty_bar = bars + 2 * GEMM_MAX_STAGES + 2;   // [2]            (the leader's are used)
   uint64_t* in_bar = bars + 2 * GEMM_MAX_STAGES + 4;       // [EPI_WARPS][4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_MAX_STAGES + 4 + 4 * GEMM_EPI_WARPS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_MAX_STAGES + 4 + 4 * 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -158,7 +165,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 2 * EW);
     }
-    for (int i = 0; i < 4 * GEMM_EPI_WARPS; ++i) mbar_init(&in_bar[i], 1);
+    for (int i = 0; i < 4 * 16; ++i) mbar_init(&in_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -244,9 +251,133 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         if (acc == 0) acc_phase ^= 1;
       }
     }
+  } else if constexpr (EW == 16 && EPI == GEMM_E_MUL) {
+    // ============================ epilogue, 16 warps in pairs (product class) ============================
+    // out = acc * in-stream (the stored gelu', or gelu'(pre) evaluated here) with the fused column sums; every warp keeps
+    // its own ring of [32 x 32] in-stream tiles (its two chunks of a tile, requested one tile ahead), pairs share the
+    // [32 x 64] output staging tiles.
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int kq = ew >> 2;
+    const int pairi = kq >> 1;
+    const int side = kq & 1;
+    const int slot = quarter * 2 + pairi;
+    const int bar_id = 1 + slot;           // pair barriers 1..8; 9 = all 16 epilogue warps (column sums)
+    const GemmEpilogue& ep = args.epi;
+    uint8_t* in_buf = smem_epi + ew * (GEMM_IN_DEPTH * GEMM_EPI_BUF);
+    uint8_t* out_buf = smem_epi + 16 * (GEMM_IN_DEPTH * GEMM_EPI_BUF) + slot * GEMM_OUT_BUF;
+    uint64_t* my_in_bar = in_bar + 4 * ew;
+    float* s_colsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);   // [2][4][256]
+    auto issue_in = [&](int q) {
+      const int t = cluster_id + (q >> 1) * num_clusters;
+      if (t >= num_tiles) return;
+      const int m0 = (t / n_tiles) * (2 * GEMM_BLOCK_M) + (int)cta_rank * GEMM_BLOCK_M;
+      const int col = (t % n_tiles) * BLOCK_N + pairi * 128 + (q & 1) * 64 + side * 32;
+      const int sl = q % GEMM_IN_DEPTH;
+      mbar_arrive_expect_tx(&my_in_bar[sl], GEMM_EPI_BUF);
+      tma_load_2d(in_buf + sl * GEMM_EPI_BUF, &tma_in, &my_in_bar[sl], col, m0 + quarter * 32);
+    };
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < GEMM_IN_DEPTH; ++i) issue_in(i);
+    }
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int q = 0;
+    int tile_par = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int m0 = (t / n_tiles) * (2 * GEMM_BLOCK_M) + (int)cta_rank * GEMM_BLOCK_M;
+      const int n0 = (t % n_tiles) * BLOCK_N;
+      const bool row_ok = (m0 + quarter * 32 + lane) < args.M;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int b = 0; b < 2; ++b, ++q) {
+        const int ccol = pairi * 128 + b * 64 + side * 32;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + ccol), r);
+        tmem_ld_wait();
+        if (b == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)acc * 8u);
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        uint4 in4[4];
+        {
+          const int in_slot = q % GEMM_IN_DEPTH;
+          mbar_wait(&my_in_bar[in_slot], (uint32_t)((q / GEMM_IN_DEPTH) & 1));
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            in4[j] = *reinterpret_cast<const uint4*>(in_buf + in_slot * GEMM_EPI_BUF + epi_tile_off(lane, j));
+          __syncwarp();                     // every lane has read its row: the tile may be refilled
+          if (lane == 0) issue_in(q + GEMM_IN_DEPTH);
+        }
+        if (ep.flags & EPI_MUL_AUX) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f;
+            f = unpack_bf16x2(in4[j].x); v[8 * j] *= f.x; v[8 * j + 1] *= f.y;
+            f = unpack_bf16x2(in4[j].y); v[8 * j + 2] *= f.x; v[8 * j + 3] *= f.y;
+            f = unpack_bf16x2(in4[j].z); v[8 * j + 4] *= f.x; v[8 * j + 5] *= f.y;
+            f = unpack_bf16x2(in4[j].w); v[8 * j + 6] *= f.x; v[8 * j + 7] *= f.y;
+          }
+        } else {   // EPI_DGELU
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f;
+            f = unpack_bf16x2(in4[j].x); v[8 * j] *= dgelu_erf(f.x); v[8 * j + 1] *= dgelu_erf(f.y);
+            f = unpack_bf16x2(in4[j].y); v[8 * j + 2] *= dgelu_erf(f.x); v[8 * j + 3] *= dgelu_erf(f.y);
+            f = unpack_bf16x2(in4[j].z); v[8 * j + 4] *= dgelu_erf(f.x); v[8 * j + 5] *= dgelu_erf(f.y);
+            f = unpack_bf16x2(in4[j].w); v[8 * j + 6] *= dgelu_erf(f.x); v[8 * j + 7] *= dgelu_erf(f.y);
+          }
+        }
+        if (ep.alpha != 1.0f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+        }
+        uint4 o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o[j].x = pack_bf16x2(v[8 * j], v[8 * j + 1]); o[j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+          o[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); o[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        }
+        if (ep.colsum != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = row_ok ? v[j] : 0.f;
+          warp_colsum<32>(v, lane);                   // lane L now holds the sum of column L over the warp's 32 rows
+          s_colsum[((tile_par * 4 + quarter) << 8) + ccol + lane] = v[0];
+        }
+        if (side == 0 && lane == 0) bulk_wait_read0();
+        asm volatile("bar.sync %0, 64;\n" ::"r"(bar_id) : "memory");
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(out_buf + out_tile_off(lane, side * 4 + j)) = o[j];
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 64;\n" ::"r"(bar_id) : "memory");
+        if (side == 0 && lane == 0) {
+          const int nc0 = n0 + pairi * 128 + b * 64;
+          if (nc0 < args.N && m0 + quarter * 32 < args.M) tma_store_2d(&tma_c, out_buf, nc0, m0 + quarter * 32);
+          bulk_commit();
+        }
+      }
+      if (ep.colsum != nullptr) {
+        asm volatile("bar.sync 9, 512;\n" ::: "memory");      // every epilogue warp has added its rows of this tile
+        const int et = ew * 32 + lane;
+        if (et < BLOCK_N && n0 + et < args.N) {
+          const float* sc = s_colsum + (tile_par << 10) + et;
+          atomicAdd(ep.colsum + n0 + et, (sc[0] + sc[256]) + (sc[512] + sc[768]));
+        }
+        tile_par ^= 1;
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (side == 0 && lane == 0) bulk_wait0();
   } else if constexpr (EW == 16) {
     // ============================ epilogue, 16 warps in pairs (GELU class) ============================
-    static_assert(EW != 16 || EPI == GEMM_E_GELU, "16 epilogue warps: GELU class");
+    static_assert(EW != 16 || EPI == GEMM_E_GELU || EPI == GEMM_E_MUL, "16 epilogue warps: GELU and product classes");
     const int ew = warp - 2;
     const int quarter = warp & 3;          // TMEM lane quarter (= scheduler) of this warp
     const int kq = ew >> 2;                // 0..3: which of the quarter's four warps

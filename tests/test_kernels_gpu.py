@@ -55,10 +55,10 @@ def test_gemm_fwd_bias_gelu_resid(M, N, K):
         ops.gemm(a, w, out, M, N, K, bias=bias, gelu=True, resid=res)
 
 
-@pytest.mark.parametrize("env", [{"AVS_GEMM_2CTA": "0"}, {"AVS_GEMM_EW16": "0"}])
+@pytest.mark.parametrize("env", [{"AVS_GEMM_2CTA": "0"}, {"AVS_GEMM_EW16": "0", "AVS_GEMM_MUL16": "0"}])
 def test_gemm_fallback_kernels_in_a_subprocess(env):
     """The kernel choice is read from the environment once per process: the one-CTA kernel for every product
-    (AVS_GEMM_2CTA=0) and the 8-warp GELU epilogue of the two-CTA kernel (AVS_GEMM_EW16=0) stay covered by running this
+    (AVS_GEMM_2CTA=0) and the 8-warp GELU / product epilogues of the two-CTA kernel (AVS_GEMM_EW16=0, AVS_GEMM_MUL16=0) stay covered by running this
     file's GEMM tests in a child process with the switch set."""
     import subprocess
     import sys
