@@ -500,7 +500,8 @@ def run_gpu_arm(args):
         tj = json.load(open(tpath))
         traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     roofline = {
-        "kernel": "avs::gemm_bf16_kernel (tcgen05.mma + TMEM + TMA, all Linear / patch-embed fwd, dgrad, wgrad)",
+        "kernel": "avs::gemm2_bf16_kernel (two-CTA tcgen05.mma.cta_group::2 + TMEM + TMA: Linear / patch-embed fwd, dgrad) + "
+                  "avs::gemm_bf16_kernel (one-CTA: wgrad)",
         "bound": "tensor", "achieved": gemm_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
         "frac": gemm_tflops / peaks["bf16_tflops_sustained"], "peak_source": f"{peaks_src} (sustained cuBLAS bf16)",
         "traffic": traffic, "traffic_unit": "bytes of DRAM read + write per launch (average over the launches of one step)",

@@ -40,6 +40,10 @@ void avs_reset(void);
  *                      1 = M/N contiguous        (A is [K,M], B is [K,N]).
  * Replaces nn.Linear / Conv2d(k=s=16) forward+backward: cav_mae_base.py:51,55 (qkv, proj), :96 (patch embed),
  * :311 (decoder_embed), :334-335 (decoder_pred_*), timm Mlp fc1/fc2 (:138-143).
+ * Kernels behind the one entry point: products with a bf16 output, K-major A, M > 128 and N > 128 (every forward and
+ * dgrad of the model) run on clusters of two CTAs (tcgen05.mma.cta_group::2, 256 x 256 tiles); fp32 / accumulating
+ * outputs (wgrad, split-K) and narrow products on the one-CTA kernel. Both pass the same parity tests; AVS_GEMM_2CTA=0 in
+ * the environment forces the one-CTA kernel everywhere.
  * ---------------------------------------------------------------------------------------------- */
 enum {
   AVS_EPI_GELU = 1,       /* v = gelu_erf(v); aux_out (optional) receives the pre-activation (bf16) */
