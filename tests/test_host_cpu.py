@@ -289,3 +289,24 @@ def test_patch_rebinds_the_names_the_reference_train_loop_resolves():
     finally:
         undo()
     assert tt.DDP is orig_ddp and tt.torch is orig_torch
+
+
+def test_bench_flop_model_matches_baseline_figure():
+    """bench.py's per-sample training FLOP model (3 x forward: encoder over the kept tokens, two fusion blocks, decoder over
+    all tokens, embeddings, prediction heads, attention 4 S^2 hd) against the figure BASELINE.md quotes for the ViT-B/16
+    single-pass step (242.0 GFLOP), and its contrastive-only variant against a hand count for ViT-H/14."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    d = O.VIT_B
+    got = bench.train_gflop_per_sample(d, int(d.Ta * 0.25), int(d.Tv * 0.25))
+    assert abs(got - bench.TRAIN_GFLOP_PER_SAMPLE["single_pass"]) < 0.01 * got, got
+    h = O.VIT_H
+    ka, kv = int(h.Ta * 0.25), int(h.Tv * 0.25)
+    assert (ka, kv) == (164, 64)
+    D, hd = h.embed_dim, h.embed_dim // h.heads
+    per_block = 2.0 * (ka + kv) * D * D * 12 + 4.0 * (ka * ka + kv * kv) * hd * h.heads
+    embed = 2.0 * ka * D * 196 + 2.0 * kv * D * 588
+    want = 3.0 * (h.depth * per_block + embed) / 1e9
+    assert abs(bench.train_gflop_per_sample(h, ka, kv, with_mae=False) - want) < 1e-6 * want
